@@ -1,0 +1,132 @@
+/* orz.h -- C ABI of the B200-native occlusion-culling rasterizer.
+ *
+ * Drop-in boundary for the hot path of rawrunprotected/rasterizer (SoftwareRasterizer/):
+ * every entry point below replaces one public method of the reference's `Occluder` /
+ * `Rasterizer` classes (file:line cited per function), or batches the per-frame loop of
+ * Main.cpp:181-206 over many independent camera views.  Plain C types only: pointers, sizes,
+ * opaque handles.  The C++ classes in rasterizer_b200/csrc/dropin/{Occluder.h,Rasterizer.h}
+ * keep the reference's signatures on top of this ABI; INTEGRATION.md shows the binding.
+ *
+ * All functions return 0 on success and a non-zero code on failure (orz_last_error() gives
+ * the message); there is no CPU fallback -- without a CUDA device every compute entry fails.
+ */
+#ifndef ORZ_H
+#define ORZ_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orz_context orz_context;       /* one per (host thread, GPU): stream, tables */
+typedef struct orz_occluder orz_occluder;     /* one baked batch resident in HBM (Occluder.h:7-21) */
+typedef struct orz_rasterizer orz_rasterizer; /* one view's depth + HiZ + matrices (Rasterizer.h:10-61) */
+typedef struct orz_scene orz_scene;           /* all baked batches + occludee boxes of a scene in HBM */
+
+enum { ORZ_OK = 0, ORZ_ERR_CUDA = 1, ORZ_ERR_ARG = 2, ORZ_ERR_NO_DEVICE = 3 };
+
+const char* orz_last_error(void);
+int orz_version(void);
+
+/* ---- context ---------------------------------------------------------------------------------
+ * Builds the 64x64 edge-mask table (Rasterizer.cpp:547-604, once per process) and probes the
+ * host's rcpps into the table the kernels use (Rasterizer.cpp:218,223,456,717-727,981 depend on
+ * the CPU's approximate reciprocal). */
+int orz_context_create(int device, orz_context** out);
+void orz_context_destroy(orz_context* ctx);
+int orz_context_synchronize(orz_context* ctx);
+void* orz_context_stream(orz_context* ctx); /* cudaStream_t all work of this context is ordered on */
+/* Replace the probed rcpps model: table[i] = bits of rcpps(1.0 + i * 2^-bits), 2^bits entries. */
+int orz_context_set_rcp_table(orz_context* ctx, const uint32_t* table, int bits);
+int orz_context_get_rcp_table(orz_context* ctx, uint32_t* table, int* bits); /* table: room for 2^23 max; pass NULL to get bits */
+int orz_context_get_lut(orz_context* ctx, int64_t* lut4096);
+/* host-only helpers (no device needed): the edge-mask table and the rcpps probe themselves.
+ * orz_probe_host_rcp: table may be NULL; *bits = leading mantissa bits rcpps depends on on this
+ * CPU (11 on Intel), *exact = 1 when the exponent/special-value model matched the instruction. */
+int orz_edge_mask_table(int64_t* lut4096);
+int orz_probe_host_rcp(uint32_t* table, int* bits, int* exact);
+
+/* ---- Occluder::bake (Occluder.h:9, Occluder.cpp:7-181), host side -------------------------------
+ * vertices: nVerts float4 (4 per quad, nVerts % 32 == 0).  packets: nVerts uint32 in the
+ * reference's packet layout (group of 8 quads = 4 x 8 words, Occluder.cpp:146-156).
+ * Returns m_packetCount.  rsqrtps (VectorMath.h:22) is taken from the host CPU unless a table
+ * was installed with orz_set_rsqrt_table (2 << bits entries: [exponent parity][mantissa]). */
+uint32_t orz_bake(const float* vertices, uint32_t nVerts, const float* refMin4, const float* refMax4,
+                  uint32_t* packets, float* center4, float* boundsMin4, float* boundsMax4);
+int orz_set_rsqrt_table(const uint32_t* table, int bits); /* NULL: back to the host instruction */
+
+/* ---- single-view path: the reference's per-call API ------------------------------------------- */
+/* upload one baked batch (re-laid out as one 16-byte record per quad for 128-bit coalesced loads) */
+int orz_occluder_create(orz_context* ctx, const uint32_t* packets, uint32_t packetCount, const float* refMin4,
+                        const float* refMax4, orz_occluder** out);
+void orz_occluder_destroy(orz_occluder* occ);
+
+int orz_rasterizer_create(orz_context* ctx, uint32_t width, uint32_t height, orz_rasterizer** out); /* Rasterizer.cpp:66-74 */
+void orz_rasterizer_destroy(orz_rasterizer* r);
+int orz_rasterizer_set_mvp(orz_rasterizer* r, const float* matrix16);                    /* Rasterizer.cpp:76-105 */
+int orz_rasterizer_clear(orz_rasterizer* r);                                             /* Rasterizer.cpp:107-121 (+ depth := 0) */
+int orz_rasterizer_rasterize(orz_rasterizer* r, const orz_occluder* occ, int possiblyNearClipped); /* Rasterizer.cpp:606-1295 */
+int orz_rasterizer_query_visibility(orz_rasterizer* r, const float* boundsMin4, const float* boundsMax4,
+                                    int* visible, int* needsClipping);                   /* Rasterizer.cpp:123-281 */
+int orz_rasterizer_query2d(orz_rasterizer* r, uint32_t minX, uint32_t maxX, uint32_t minY, uint32_t maxY,
+                           uint32_t maxZ, int* visible);                                 /* Rasterizer.cpp:283-349 */
+/* many boxes at once (host arrays): boxes = n x (min4, max4); out[i] bit0 visible, bit1 needsClipping */
+int orz_rasterizer_query_boxes(orz_rasterizer* r, const float* boxes, uint32_t n, uint8_t* out);
+int orz_rasterizer_readback_depth(orz_rasterizer* r, void* targetBGRA8);                 /* Rasterizer.cpp:351-399 */
+/* raw buffers in the reference's layout: depth u16 [block][row][px] (cleared blocks zero), HiZ u16 [block] */
+int orz_rasterizer_download(orz_rasterizer* r, uint16_t* depth, uint16_t* hiz);
+/* debug / parity: setup records of every quad of `occ` (orz_prim_record each, mode 0 = culled) */
+typedef struct {
+  uint32_t mode;
+  int32_t minX, minY, rangeX, rangeY;
+  uint32_t maxZ;
+  float dzdx, dzdy, plane0;
+  float nx[4], ny[4], off[4];
+  uint32_t slope[4];
+} orz_prim_record;
+int orz_rasterizer_debug_setup(orz_rasterizer* r, const orz_occluder* occ, int possiblyNearClipped,
+                               orz_prim_record* out /* quadCount records, host */);
+
+/* ---- view-batch path: Main.cpp:181-206 for many independent views -------------------------------
+ * Scene: nOccluders baked batches (packets concatenated in the reference layout, packetCounts[i]
+ * packets each), per-occluder refMin/refMax/boundsMin/boundsMax/center (4 floats each). */
+int orz_scene_create(orz_context* ctx, const uint32_t* packets, const uint32_t* packetCounts, uint32_t nOccluders,
+                     const float* refMin, const float* refMax, const float* boundsMin, const float* boundsMax,
+                     const float* centers, orz_scene** out);
+int orz_scene_set_occludees(orz_scene* scene, const float* boxes, uint32_t nBoxes); /* n x (min4, max4) */
+void orz_scene_destroy(orz_scene* scene);
+
+enum {
+  ORZ_BATCH_NO_GATE = 1u,      /* submit every occluder, no queryVisibility gate (config 4 shape) */
+  ORZ_BATCH_FORCE_CLIPPED = 2u /* with NO_GATE: use rasterize<true> for every occluder */
+};
+typedef struct {
+  uint32_t width, height;
+  uint32_t nViews;
+  uint32_t flags;
+  const float* mvps;      /* nViews x 16 (Main.cpp:172-178) */
+  const uint32_t* orders; /* nViews x nOccluders front-to-back order (Main.cpp:185-190), or NULL ... */
+  const float* camPos;    /* ... then nViews x 3 camera positions: the order is computed on the GPU */
+  /* outputs, any may be NULL */
+  uint32_t* visBits;      /* nViews x ceil(nBoxes/32): occludee visible bits (needsClipping counts as visible) */
+  uint32_t* clipBits;     /* same shape: needsClipping bits */
+  uint8_t* gate;          /* nViews x nOccluders, per order slot: bit0 visible, bit1 needsClipping */
+  uint16_t* depth;        /* nViews x (w*h) u16, reference block layout */
+  uint16_t* hiz;          /* nViews x (w/8*h/8) u16 */
+  uint32_t* quadsSubmitted; /* nViews: quads handed to rasterize (2 x packetCount per rasterised occluder) */
+} orz_view_batch;
+
+/* Host pointers; copies inputs to the GPU, renders, copies the requested outputs back, synchronises. */
+int orz_render_views(orz_context* ctx, orz_scene* scene, const orz_view_batch* batch);
+/* Device pointers (inputs already resident in HBM); asynchronous on the context stream. */
+int orz_render_views_device(orz_context* ctx, orz_scene* scene, const orz_view_batch* batch);
+/* kernels launched by the last render / rasterizer call on this context (for launch accounting) */
+uint64_t orz_context_launch_count(orz_context* ctx);
+/* tuning: warps cooperating on one view in the batch kernel (1, 2, 4, 8); 0 = default */
+int orz_context_set_group_warps(orz_context* ctx, int warps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORZ_H */

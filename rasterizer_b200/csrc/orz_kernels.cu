@@ -1,0 +1,1042 @@
+// CUDA kernels (sm_100a) + C ABI of the B200-native occlusion-culling rasterizer.
+//
+// Execution model (DESIGN.md has the long form):
+//   * A *view group* of GW warps (one CTA) owns one camera view at a time and walks its
+//     occluders front to back exactly like Main.cpp:192-206: gate query -> setup -> traversal.
+//     Views are independent, so a persistent grid pulls views from an atomic counter and the
+//     machine is filled by views, not by splitting one view.
+//   * Setup (Rasterizer.cpp:660-1063): one lane per quad, one 128-bit coalesced load of the four
+//     packed vertices, valid primitives compacted in order (ballot + popc prefix) into
+//     shared-memory records.
+//   * Binning: screen block-rows are interleaved over the warps of the group
+//     (row r belongs to warp r mod GW); every warp walks the compacted list in order and touches
+//     only its own rows, so per-block primitive order -- which the HiZ early-out makes
+//     observable -- is preserved without atomics or sorting.
+//   * Traversal (Rasterizer.cpp:1098-1292): the whole warp works on one 8x8 block at a time, one
+//     32-bit word (2 pixels) of the 128-byte block per lane: coalesced 128 B read-modify-write,
+//     edge masks from the 32 KB table through 4 lanes + shuffle-AND, packed-u16 SIMD depth
+//     (vavg/vmax), HiZ by one warp-wide REDUX min.  The 12 iterated float add chains
+//     (4 edge offsets, 8 depth lanes) are distributed over the lanes (3 FADDs per block step) and
+//     advanced exactly as the reference does (y chain, then x chain from the row start).
+//   * Queries (Rasterizer.cpp:123-349): one thread per box; the occluder gate uses all threads of
+//     the group on the blocks of one rectangle.
+// No tensor cores: nothing here is a contraction.  Build: -fmad=false (see orz_core.h).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/orz.h"
+#include "orz_core.h"
+#include "orz_host.h"
+
+namespace orz {
+
+__constant__ uint32_t c_modeNibbles[32] = {ORZ_MODE_NIBBLES};
+
+constexpr uint32_t kFull = 0xffffffffu;
+constexpr int kRecWords = 20;   // words per primitive record
+constexpr int kRecStride = 21;  // odd stride: conflict-free lane-per-record stores
+constexpr int kWindow = 64;     // occluders whose front half is precomputed at a time
+
+struct OccMeta {
+  uint32_t quadOffset, quadCount, pad0, pad1;
+  float refMin[4], refMax[4], boundsMin[4], boundsMax[4], center[4];
+};
+
+struct Target {
+  uint16_t* depth;  // [block][row][px], 128 B per 8x8 block
+  uint16_t* hiz;    // [block]
+  uint32_t width, height, blocksX, blocksY;
+};
+
+// ---------------------------------------------------------------------------------------------
+// primitive record <-> registers
+__device__ __forceinline__ void store_record(uint32_t* rec, const Prim& P) {
+  rec[0] = (uint32_t)P.minX | ((uint32_t)P.minY << 16);
+  rec[1] = (uint32_t)P.rangeX | ((uint32_t)P.rangeY << 16);
+  rec[2] = P.maxZ | (P.mode << 16);
+  rec[3] = f2u(P.dzdx); rec[4] = f2u(P.dzdy); rec[5] = f2u(P.plane0);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { rec[6 + e] = f2u(P.nx[e]); rec[10 + e] = f2u(P.ny[e]); rec[14 + e] = f2u(P.off[e]); }
+  rec[18] = (P.slope[0] & 0xfc0u) | ((P.slope[1] & 0xfc0u) << 16);
+  rec[19] = (P.slope[2] & 0xfc0u) | ((P.slope[3] & 0xfc0u) << 16);
+}
+
+// avg_epu16 on two packed halves: (a + b + 1) >> 1 without overflow
+__device__ __forceinline__ uint32_t avg_u16x2(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) >> 1) & 0x7fff7fffu); }
+
+// ---------------------------------------------------------------------------------------------
+// Traversal of one primitive by one warp, restricted to the screen block-rows the warp owns
+// (row % rowStride == rowPhase).  Rasterizer.cpp:1098-1292.
+//
+// Lane roles: lane = 4*y + w addresses word w (pixels 2w, 2w+1) of row y of the 8x8 block.
+//   edge e = lane & 3 (offset chain e is replicated in the 8 lanes with that residue)
+//   depth chains: row parity r = y & 1 -> reference lanes 4r + 2(w&1) and 4r + 2(w&1) + 1;
+//   words 2,3 (pixels 4-7) use depth1 = depth0 + dzdx/2 (Rasterizer.cpp:1243).
+// Block addressing is linear with the reference's 16-bit wrap of the first-row offset
+// (Rasterizer.cpp:1054); ownership follows the linear index, so a wrapped row that
+// straddles two screen rows is split between their owners.
+template <int kStride>
+__device__ __forceinline__ void raster_prim(const uint32_t* __restrict__ rec, const int lane, const uint32_t rowPhase,
+                                            const uint32_t rowStrideRt, const Target& T, const uint2* __restrict__ lut) {
+  const uint32_t rowStride = kStride > 0 ? (uint32_t)kStride : rowStrideRt;
+  const uint32_t w0 = rec[0], w1 = rec[1], w2 = rec[2];
+  const uint32_t minX = w0 & 0xffffu, minY = w0 >> 16, rangeX = w1 & 0xffffu, rangeY = w1 >> 16;
+  const uint32_t maxZ = w2 & 0xffffu, mode = w2 >> 16;
+  const uint32_t blocksX = T.blocksX;
+
+  const uint32_t fb = ((minY * blocksX) & 0xffffu) + minX;
+  uint32_t r0 = minY, c0 = minX;
+  if (blocksX * T.blocksY > 65536u) { r0 = fb / blocksX; c0 = fb - r0 * blocksX; }
+  const uint32_t split = min(rangeX, blocksX - c0);  // blocks of a primitive row inside screen row r0 + by
+  const bool crossing = split < rangeX;
+  {  // any row of mine in [r0, r0 + rangeY + crossing) ?
+    const uint32_t first = r0 + (rowPhase + rowStride - r0 % rowStride) % rowStride;
+    if (first >= r0 + rangeY + (crossing ? 1u : 0u)) return;
+  }
+
+  const int e = lane & 3;
+  const float nxe = u2f(rec[6 + e]), nye = u2f(rec[10 + e]);
+  float lineOff = u2f(rec[14 + e]);
+  const uint32_t slope = (rec[18 + (e >> 1)] >> ((e & 1) * 16)) & 0xffffu;
+  const float dzdx = u2f(rec[3]), dzdy = u2f(rec[4]), plane0 = u2f(rec[5]);
+  const int rpar = (lane >> 2) & 1, wIdx = lane & 3, k2 = lane >> 3;
+  const float s = -0.5f + 1.0f / 16.0f;  // Rasterizer.cpp:1103
+  const float sy = rpar ? s + 0.125f : s;
+  const float sxA = s + 0.125f * (float)(2 * (wIdx & 1)), sxB = s + 0.125f * (float)(2 * (wIdx & 1) + 1);
+  const float base = ORZ_FMA(dzdy, sy, plane0);  // Rasterizer.cpp:1104-1107
+  float lineA = ORZ_FMA(dzdx, sxA, base), lineB = ORZ_FMA(dzdx, sxB, base);
+  const bool upperHalf = (wIdx & 2) != 0;
+  const uint32_t sh0 = (uint32_t)(wIdx & 1) * 16u + (rpar ? 0u : 4u) + (uint32_t)k2;  // mask bit of pixel 2w (Rasterizer.cpp:1257-1268)
+  const uint32_t sh1 = sh0 + 8u;
+
+  for (uint32_t by = 0; by < rangeY; ++by) {
+    const uint32_t R = r0 + by;
+    const bool mineA = (R % rowStride) == rowPhase;
+    const bool mineB = crossing && ((R + 1) % rowStride) == rowPhase;
+    if (mineA || mineB) {
+      float o = lineOff, dA = lineA, dB = lineB;
+      const uint32_t L = fb + by * blocksX;
+      uint32_t a = 0;
+#pragma unroll 1
+      for (int piece = 0; piece < 2; ++piece) {
+        const uint32_t b = piece == 0 ? split : rangeX;
+        const bool mine = piece == 0 ? mineA : mineB;
+        if (!mine) {
+          if (piece == 0 && mineB)
+            for (uint32_t i = a; i < b; ++i) { o = nxe + o; dA = dzdx + dA; dB = dzdx + dB; }
+          a = b;
+          continue;
+        }
+        // ---- walk blocks [a, b) of this primitive row, 32 HiZ entries at a time
+        for (uint32_t s0 = a; s0 < b; s0 += 32) {
+          const uint32_t m = min(32u, b - s0);
+          const uint32_t hv = (uint32_t)lane < m ? (uint32_t)T.hiz[L + s0 + lane] : 0xffffu;
+          uint32_t cand = __ballot_sync(kFull, hv < maxZ);  // Rasterizer.cpp:1148-1152
+          uint32_t pos = 0;
+          while (cand) {
+            const uint32_t j = (uint32_t)__ffs((int)cand) - 1u;
+            cand &= cand - 1u;
+            for (; pos < j; ++pos) { o = nxe + o; dA = dzdx + dA; dB = dzdx + dB; }  // Rasterizer.cpp:1145-1146
+            const uint32_t h = __shfl_sync(kFull, hv, (int)j);
+            const uint32_t blk = L + s0 + j;
+            uint2 mk;
+            if (mode == kConvex) {  // Rasterizer.cpp:1155-1187
+              if (__any_sync(kFull, o >= 63.0f)) continue;
+              int q = cvtt_x86(o);
+              q = q < 0 ? 0 : q;
+              uint2 t = lut[(slope | (uint32_t)q) & 4095u];
+              t.x &= __shfl_xor_sync(kFull, t.x, 1); t.y &= __shfl_xor_sync(kFull, t.y, 1);
+              t.x &= __shfl_xor_sync(kFull, t.x, 2); t.y &= __shfl_xor_sync(kFull, t.y, 2);
+              mk = t;  // no empty-mask test on this path (Rasterizer.cpp:1186)
+            } else {  // Rasterizer.cpp:1188-1239
+              int q = cvtt_x86(o);
+              q = q < 0 ? 0 : (q > 63 ? 63 : q);
+              const uint2 t = lut[(slope | (uint32_t)q) & 4095u];
+              const int g = lane & ~3;
+              uint2 A, B, C, D;
+              A.x = __shfl_sync(kFull, t.x, g + 0); A.y = __shfl_sync(kFull, t.y, g + 0);
+              B.x = __shfl_sync(kFull, t.x, g + 1); B.y = __shfl_sync(kFull, t.y, g + 1);
+              C.x = __shfl_sync(kFull, t.x, g + 2); C.y = __shfl_sync(kFull, t.y, g + 2);
+              D.x = __shfl_sync(kFull, t.x, g + 3); D.y = __shfl_sync(kFull, t.y, g + 3);
+              if (mode == kTriangle0) { mk.x = A.x & B.x & C.x; mk.y = A.y & B.y & C.y; }
+              else if (mode == kTriangle1) { mk.x = A.x & C.x & D.x; mk.y = A.y & C.y & D.y; }
+              else if (mode == kConcaveRight) { mk.x = (A.x | D.x) & (B.x & C.x); mk.y = (A.y | D.y) & (B.y & C.y); }
+              else if (mode == kConcaveCenter) { mk.x = (A.x & B.x) | (C.x & D.x); mk.y = (A.y & B.y) | (C.y & D.y); }
+              else { mk.x = (A.x & D.x) & (B.x | C.x); mk.y = (A.y & D.y) & (B.y | C.y); }
+              if ((mk.x | mk.y) == 0u) continue;
+            }
+            // ---- depth of this lane's two pixels, Rasterizer.cpp:1241-1254
+            float a0 = dA, b0 = dB;
+            if (upperHalf) { a0 = ORZ_FMA(dzdx, 0.5f, a0); b0 = ORZ_FMA(dzdx, 0.5f, b0); }
+            const float a8 = dzdy + a0, b8 = dzdy + b0;
+            const uint32_t v0 = pack16(a0) | (pack16(b0) << 16);  // row rpar
+            const uint32_t v8 = pack16(a8) | (pack16(b8) << 16);  // row 8 + rpar
+            const uint32_t mid = avg_u16x2(v0, v8);               // row 4 + rpar
+            const uint32_t quarter = avg_u16x2((k2 & 2) ? v8 : v0, mid);  // rows 2 + rpar / 6 + rpar
+            uint32_t val = k2 == 0 ? v0 : (k2 == 2 ? mid : quarter);
+            // ---- coverage of the two pixels, Rasterizer.cpp:1257-1268
+            const uint32_t mw = upperHalf ? mk.y : mk.x;
+            const uint32_t selMask = ((0u - ((mw >> sh0) & 1u)) & 0x0000ffffu) | ((0u - ((mw >> sh1) & 1u)) & 0xffff0000u);
+            val &= selMask;
+            // ---- merge, store, HiZ; Rasterizer.cpp:1271-1290
+            uint32_t* dptr = reinterpret_cast<uint32_t*>(T.depth) + (size_t)blk * 32u + (uint32_t)lane;
+            if (h != 1u) val = __vmaxu2(val, *dptr);
+            *dptr = val;
+            uint32_t mn = min(val & 0xffffu, val >> 16);
+            mn = __reduce_min_sync(kFull, mn);
+            if (lane == 0) T.hiz[blk] = (uint16_t)mn;
+          }
+          for (; pos < m; ++pos) { o = nxe + o; dA = dzdx + dA; dB = dzdx + dB; }
+        }
+        a = b;
+      }
+    }
+    lineA = lineA + dzdy; lineB = lineB + dzdy; lineOff = lineOff + nye;  // Rasterizer.cpp:1130-1131
+  }
+  // HiZ is written by lane 0 and prefetched by other lanes for the next primitive: order the
+  // warp's memory accesses (each block is visited at most once per primitive, so once is enough)
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// query2D, Rasterizer.cpp:283-349.  Depth of cleared blocks is zero (fresh state), so no HiZ==1
+// special case is needed on the read side.
+__device__ __forceinline__ bool block_fine_test(const uint16_t* __restrict__ depth, uint32_t b, uint32_t maxZ, int sX, int eX,
+                                                int sY, int eY) {
+  const uint4* rows = reinterpret_cast<const uint4*>(depth + (size_t)b * 64u);
+  const uint32_t mz = maxZ | (maxZ << 16);
+  uint32_t sel[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    sel[i] = ((2 * i >= sX && 2 * i <= eX) ? 0x0000ffffu : 0u) | ((2 * i + 1 >= sX && 2 * i + 1 <= eX) ? 0xffff0000u : 0u);
+  uint32_t any = 0;
+  for (int y = sY; y <= eY; ++y) {
+    const uint4 r = rows[y];  // visible where depth < maxZ (Rasterizer.cpp:335-339)
+    any |= (__vcmpltu2(r.x, mz) & sel[0]) | (__vcmpltu2(r.y, mz) & sel[1]) | (__vcmpltu2(r.z, mz) & sel[2]) |
+           (__vcmpltu2(r.w, mz) & sel[3]);
+  }
+  return any != 0u;
+}
+
+__device__ __forceinline__ bool query_block(const Target& T, uint32_t bx, uint32_t by, uint32_t minX, uint32_t maxX,
+                                            uint32_t minY, uint32_t maxY, uint32_t maxZ) {
+  const uint32_t b = by * T.blocksX + bx;
+  const uint32_t h = T.hiz[b];
+  if (maxZ <= h) return false;  // Rasterizer.cpp:310
+  const int sX = max((int)minX - (int)(8u * bx), 0), eX = min((int)maxX - (int)(8u * bx), 7);
+  const int sY = max((int)minY - (int)(8u * by), 0), eY = min((int)maxY - (int)(8u * by), 7);
+  if (sX == 0 && eX == 7 && sY == 0 && eY == 7) return true;  // Rasterizer.cpp:319-325
+  return block_fine_test(T.depth, b, maxZ, sX, eX, sY, eY);
+}
+
+// one thread walks the whole rectangle (occludee queries)
+__device__ bool query2d_serial(const Target& T, uint32_t minX, uint32_t maxX, uint32_t minY, uint32_t maxY, uint32_t maxZ) {
+  const uint32_t bx0 = minX >> 3, bx1 = maxX >> 3, by0 = minY >> 3, by1 = maxY >> 3;
+  for (uint32_t by = by0; by <= by1; ++by)
+    for (uint32_t bx = bx0; bx <= bx1; ++bx)
+      if (query_block(T, bx, by, minX, maxX, minY, maxY, maxZ)) return true;
+  return false;
+}
+
+// all threads of a group share one rectangle (occluder gate); `flag` is a shared-memory word that
+// any finder sets so the others can stop early
+__device__ __forceinline__ void query2d_coop(const Target& T, uint32_t minX, uint32_t maxX, uint32_t minY, uint32_t maxY,
+                                             uint32_t maxZ, uint32_t tid, uint32_t nThreads, volatile uint32_t* flag) {
+  const uint32_t bx0 = minX >> 3, by0 = minY >> 3;
+  const uint32_t cols = (maxX >> 3) - bx0 + 1u, rows = (maxY >> 3) - by0 + 1u;
+  const uint32_t n = cols * rows;
+  for (uint32_t i = tid; i < n; i += nThreads) {
+    if (*flag) return;
+    const uint32_t ry = i / cols, rx = i - ry * cols;
+    if (query_block(T, bx0 + rx, by0 + ry, minX, maxX, minY, maxY, maxZ)) { *flag = 1u; return; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Setup of up to 32 * nWarps quads starting at quad `q0`, compacted in order into `recs`
+// (warp w writes slots [32 w, 32 w + count[w])).  Rasterizer.cpp:657-1086.
+__device__ __forceinline__ void setup_chunk(const uint4* __restrict__ quads, uint32_t q0, uint32_t nq, bool clipped,
+                                            const CallMatrix& cm, const RcpTable& rt, const Target& T, int warp, int lane,
+                                            uint32_t* recs, uint32_t* counts) {
+  const uint32_t qi = q0 + (uint32_t)warp * 32u + (uint32_t)lane;
+  bool ok = false;
+  Prim P;
+  if (qi < nq) {
+    const uint4 v = quads[qi];  // 128-bit coalesced load: the four packed vertices of this lane's quad
+    const uint32_t word[4] = {v.x, v.y, v.z, v.w};
+    ok = clipped ? setup_quad<true>(word, cm, rt, c_modeNibbles, (int32_t)T.blocksX, (int32_t)T.blocksY, P)
+                 : setup_quad<false>(word, cm, rt, c_modeNibbles, (int32_t)T.blocksX, (int32_t)T.blocksY, P);
+  }
+  const uint32_t valid = __ballot_sync(kFull, ok);
+  if (ok) store_record(recs + ((uint32_t)warp * 32u + (uint32_t)__popc(valid & ((1u << lane) - 1u))) * kRecStride, P);
+  if (lane == 0) counts[warp] = (uint32_t)__popc(valid);
+}
+
+// ---------------------------------------------------------------------------------------------
+// View-batch kernel: Main.cpp:181-206 for every view, one CTA of GW warps per view at a time.
+struct FrameParams {
+  const uint4* quads;
+  const OccMeta* occ;
+  uint32_t nOcc;
+  const float4* boxes;
+  uint32_t nBoxes;
+  const uint32_t* rcp;
+  int rcpShift;
+  const uint2* lut;
+  uint32_t width, height, nViews, flags;
+  const float* mvps;
+  const uint32_t* orders;
+  const float* camPos;
+  uint16_t* depth;
+  uint16_t* hiz;
+  unsigned long long depthStride, hizStride;  // elements between consecutive views (or CTAs when scratch)
+  int perViewTarget;                          // 1: index by view, 0: index by CTA (scratch)
+  uint32_t* visBits;
+  uint32_t* clipBits;
+  uint32_t bitWords;
+  uint8_t* gate;
+  uint32_t* quadsSubmitted;
+  uint32_t* viewCounter;
+  uint32_t* orderScratch;  // per CTA nOcc entries, used when the order is computed here
+};
+
+template <int GW>
+__global__ void __launch_bounds__(GW * 32) k_render_views(const FrameParams p) {
+  constexpr uint32_t NT = GW * 32;
+  __shared__ ViewMatrices s_vm;
+  __shared__ uint32_t s_front[kWindow][6];
+  __shared__ float s_cm[kWindow][14];
+  __shared__ uint32_t s_recs[NT * kRecStride];
+  __shared__ uint32_t s_count[GW];
+  __shared__ uint32_t s_flag[3];
+  __shared__ uint32_t s_view;
+
+  const uint32_t tid = threadIdx.x;
+  const int warp = (int)(tid >> 5), lane = (int)(tid & 31u);
+  const RcpTable rt{p.rcp, p.rcpShift};
+  Target T;
+  T.width = p.width; T.height = p.height; T.blocksX = p.width >> 3; T.blocksY = p.height >> 3;
+  const uint32_t blocks = T.blocksX * T.blocksY;
+  const bool useGate = (p.flags & ORZ_BATCH_NO_GATE) == 0u;
+  const bool forceClip = (p.flags & ORZ_BATCH_FORCE_CLIPPED) != 0u;
+
+  for (;;) {
+    if (tid == 0) s_view = atomicAdd(p.viewCounter, 1u);
+    __syncthreads();
+    const uint32_t view = s_view;
+    if (view >= p.nViews) break;
+    const size_t slot = p.perViewTarget ? (size_t)view : (size_t)blockIdx.x;
+    T.depth = p.depth + slot * p.depthStride;
+    T.hiz = p.hiz + slot * p.hizStride;
+
+    // ---- clear (Rasterizer.cpp:107-121; depth zeroed too = fresh state) + setMVP (Rasterizer.cpp:76-105)
+    {
+      uint4* d4 = reinterpret_cast<uint4*>(T.depth);
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      for (uint32_t i = tid; i < blocks * 8u; i += NT) d4[i] = z;
+      for (uint32_t i = tid; i < blocks; i += NT) T.hiz[i] = 1;
+      if (tid == 0) {
+        bake_view_matrices(p.mvps + 16 * (size_t)view, p.width, p.height, s_vm);
+        s_flag[0] = s_flag[1] = s_flag[2] = 0u;
+      }
+    }
+    // ---- front-to-back order (Main.cpp:185-190) when the caller did not supply one
+    const uint32_t* order = p.orders ? p.orders + (size_t)view * p.nOcc : nullptr;
+    if (!order) {
+      uint32_t* mine = p.orderScratch + (size_t)blockIdx.x * p.nOcc;
+      const float cx = p.camPos[3 * (size_t)view + 0], cy = p.camPos[3 * (size_t)view + 1], cz = p.camPos[3 * (size_t)view + 2];
+      for (uint32_t i = tid; i < p.nOcc; i += NT) {  // rank sort, stable by index
+        const float* ci = p.occ[i].center;
+        const float dxi = ci[0] - cx, dyi = ci[1] - cy, dzi = ci[2] - cz;
+        const float ki = (dxi * dxi + dyi * dyi) + dzi * dzi;  // dpps 0x7f
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < p.nOcc; ++j) {
+          const float* cj = p.occ[j].center;
+          const float dxj = cj[0] - cx, dyj = cj[1] - cy, dzj = cj[2] - cz;
+          const float kj = (dxj * dxj + dyj * dyj) + dzj * dzj;
+          rank += (kj < ki || (kj == ki && j < i)) ? 1u : 0u;
+        }
+        mine[rank] = i;
+      }
+      order = mine;
+    }
+    __syncthreads();
+
+    uint32_t gateIdx = 0, quadsSubmitted = 0;
+    for (uint32_t wbase = 0; wbase < p.nOcc; wbase += kWindow) {
+      const uint32_t wn = min((uint32_t)kWindow, p.nOcc - wbase);
+      // ---- state-independent part for a window of occluders: query front half + call matrix
+      for (uint32_t i = tid; i < wn; i += NT) {
+        const OccMeta& om = p.occ[order[wbase + i]];
+        BoxFront f;
+        if (useGate) {
+          f = box_front_half(s_vm, om.boundsMin, om.boundsMax, p.width, p.height, rt);
+        } else {
+          f.status = kBoxNearClip; f.minX = f.maxX = f.minY = f.maxY = f.maxZ = 0;
+        }
+        s_front[i][0] = f.status; s_front[i][1] = f.minX; s_front[i][2] = f.maxX;
+        s_front[i][3] = f.minY; s_front[i][4] = f.maxY; s_front[i][5] = f.maxZ;
+        CallMatrix cm;
+        prepare_call(s_vm.baked, om.refMin, om.refMax, cm);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s_cm[i][k] = cm.rx[k]; s_cm[i][4 + k] = cm.ry[k]; s_cm[i][8 + k] = cm.rw[k]; }
+        s_cm[i][12] = cm.c0; s_cm[i][13] = cm.c1;
+      }
+      __syncthreads();
+
+      for (uint32_t wi = 0; wi < wn; ++wi) {
+        const uint32_t status = s_front[wi][0];
+        bool visible = false, clipped = false;
+        if (status == kBoxNearClip) {
+          visible = true;
+          clipped = useGate ? true : forceClip;
+        } else if (status == kBoxRect) {
+          // ---- gate: query2D on the buffers as built so far (Main.cpp:195)
+          volatile uint32_t* flag = &s_flag[gateIdx % 3u];
+          if (tid == 0) s_flag[(gateIdx + 1u) % 3u] = 0u;
+          query2d_coop(T, s_front[wi][1], s_front[wi][2], s_front[wi][3], s_front[wi][4], s_front[wi][5], tid, NT, flag);
+          __syncthreads();
+          visible = *flag != 0u;
+          ++gateIdx;
+        }
+        if (p.gate && tid == 0) p.gate[(size_t)view * p.nOcc + wbase + wi] = (uint8_t)((visible ? 1 : 0) | (clipped && useGate ? 2 : 0));
+        if (!visible) continue;
+
+        // ---- rasterize<clipped>(occluder): setup chunk -> records -> traversal of my rows
+        const OccMeta& om = p.occ[order[wbase + wi]];
+        const uint4* quads = p.quads + om.quadOffset;
+        const uint32_t nq = om.quadCount;
+        quadsSubmitted += nq;
+        CallMatrix cm;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { cm.rx[k] = s_cm[wi][k]; cm.ry[k] = s_cm[wi][4 + k]; cm.rw[k] = s_cm[wi][8 + k]; }
+        cm.c0 = s_cm[wi][12]; cm.c1 = s_cm[wi][13];
+        for (uint32_t q0 = 0; q0 < nq; q0 += NT) {
+          setup_chunk(quads, q0, nq, clipped, cm, rt, T, warp, lane, s_recs, s_count);
+          __syncthreads();
+#pragma unroll 1
+          for (int w2 = 0; w2 < GW; ++w2) {
+            const uint32_t cnt = s_count[w2];
+            for (uint32_t i = 0; i < cnt; ++i)
+              raster_prim<GW>(s_recs + ((uint32_t)w2 * 32u + i) * kRecStride, lane, (uint32_t)warp, GW, T, p.lut);
+          }
+          __syncthreads();  // records consumed; depth/HiZ of this chunk visible to the whole group
+        }
+      }
+      __syncthreads();  // window tables are rewritten next
+    }
+    if (p.quadsSubmitted && tid == 0) p.quadsSubmitted[view] = quadsSubmitted;
+
+    // ---- occludee queries on the finished buffers (Rasterizer.cpp:123-349), one thread per box
+    if (p.visBits || p.clipBits) {
+      for (uint32_t base = 0; base < p.nBoxes; base += NT) {
+        const uint32_t i = base + tid;
+        bool vis = false, clip = false;
+        if (i < p.nBoxes) {
+          const float4 mn = p.boxes[2 * (size_t)i], mx = p.boxes[2 * (size_t)i + 1];
+          const float bmn[4] = {mn.x, mn.y, mn.z, mn.w}, bmx[4] = {mx.x, mx.y, mx.z, mx.w};
+          const BoxFront f = box_front_half(s_vm, bmn, bmx, p.width, p.height, rt);
+          if (f.status == kBoxNearClip) { vis = true; clip = true; }
+          else if (f.status == kBoxRect) vis = query2d_serial(T, f.minX, f.maxX, f.minY, f.maxY, f.maxZ);
+        }
+        const uint32_t vb = __ballot_sync(kFull, vis), cb = __ballot_sync(kFull, clip);
+        if (lane == 0) {
+          const size_t w = (size_t)view * p.bitWords + (base >> 5) + (uint32_t)warp;
+          if (p.visBits) p.visBits[w] = vb;
+          if (p.clipBits) p.clipBits[w] = cb;
+        }
+      }
+    }
+    __syncthreads();  // s_view / s_vm are rewritten by the next view
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-view kernels behind the per-call API (Rasterizer.h:13-26)
+__global__ void k_clear(uint16_t* depth, uint16_t* hiz, uint32_t blocks) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, n = gridDim.x * blockDim.x;
+  uint4* d4 = reinterpret_cast<uint4*>(depth);
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (uint32_t k = i; k < blocks * 8u; k += n) d4[k] = z;
+  for (uint32_t k = i; k < blocks; k += n) hiz[k] = 1;
+}
+
+// rasterize<clipped>(occluder) for one view: every CTA sets up all quads of the batch (cheap,
+// <= 504 quads) and traverses only the block rows its warps own, so no inter-CTA ordering is needed.
+template <int GW>
+__global__ void __launch_bounds__(GW * 32) k_rasterize_single(const ViewMatrices vm, const uint4* quads, uint32_t nq,
+                                                               const float4 refMin, const float4 refMax, int clipped, Target T,
+                                                               const uint32_t* rcp, int rcpShift, const uint2* lut) {
+  constexpr uint32_t NT = GW * 32;
+  __shared__ uint32_t s_recs[NT * kRecStride];
+  __shared__ uint32_t s_count[GW];
+  const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
+  const RcpTable rt{rcp, rcpShift};
+  CallMatrix cm;
+  const float rmn[4] = {refMin.x, refMin.y, refMin.z, refMin.w}, rmx[4] = {refMax.x, refMax.y, refMax.z, refMax.w};
+  prepare_call(vm.baked, rmn, rmx, cm);
+  const uint32_t rowStride = gridDim.x * GW, rowPhase = blockIdx.x * GW + (uint32_t)warp;
+  for (uint32_t q0 = 0; q0 < nq; q0 += NT) {
+    setup_chunk(quads, q0, nq, clipped != 0, cm, rt, T, warp, lane, s_recs, s_count);
+    __syncthreads();
+#pragma unroll 1
+    for (int w2 = 0; w2 < GW; ++w2) {
+      const uint32_t cnt = s_count[w2];
+      for (uint32_t i = 0; i < cnt; ++i)
+        raster_prim<0>(s_recs + ((uint32_t)w2 * 32u + i) * kRecStride, lane, rowPhase, rowStride, T, lut);
+    }
+    __syncthreads();
+  }
+}
+
+// setup records of every quad, uncompacted (parity tests of the setup stage)
+__global__ void k_debug_setup(const ViewMatrices vm, const uint4* quads, uint32_t nq, const float4 refMin, const float4 refMax,
+                              int clipped, Target T, const uint32_t* rcp, int rcpShift, orz_prim_record* out) {
+  const uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  const RcpTable rt{rcp, rcpShift};
+  CallMatrix cm;
+  const float rmn[4] = {refMin.x, refMin.y, refMin.z, refMin.w}, rmx[4] = {refMax.x, refMax.y, refMax.z, refMax.w};
+  prepare_call(vm.baked, rmn, rmx, cm);
+  const uint4 v = quads[qi];
+  const uint32_t word[4] = {v.x, v.y, v.z, v.w};
+  Prim P;
+  const bool ok = clipped ? setup_quad<true>(word, cm, rt, c_modeNibbles, (int32_t)T.blocksX, (int32_t)T.blocksY, P)
+                          : setup_quad<false>(word, cm, rt, c_modeNibbles, (int32_t)T.blocksX, (int32_t)T.blocksY, P);
+  orz_prim_record r;
+  memset(&r, 0, sizeof r);
+  if (ok) {
+    r.mode = P.mode; r.minX = P.minX; r.minY = P.minY; r.rangeX = P.rangeX; r.rangeY = P.rangeY; r.maxZ = P.maxZ;
+    r.dzdx = P.dzdx; r.dzdy = P.dzdy; r.plane0 = P.plane0;
+    for (int e = 0; e < 4; ++e) { r.nx[e] = P.nx[e]; r.ny[e] = P.ny[e]; r.off[e] = P.off[e]; r.slope[e] = P.slope[e]; }
+  }
+  out[qi] = r;
+}
+
+// queryVisibility for n boxes, one thread each; out[i] bit0 visible, bit1 needsClipping
+__global__ void k_query_boxes(const ViewMatrices vm, const float4* boxes, uint32_t n, Target T, const uint32_t* rcp, int rcpShift,
+                              uint8_t* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const RcpTable rt{rcp, rcpShift};
+  const float4 mn = boxes[2 * (size_t)i], mx = boxes[2 * (size_t)i + 1];
+  const float bmn[4] = {mn.x, mn.y, mn.z, mn.w}, bmx[4] = {mx.x, mx.y, mx.z, mx.w};
+  const BoxFront f = box_front_half(vm, bmn, bmx, T.width, T.height, rt);
+  uint8_t r = 0;
+  if (f.status == kBoxNearClip) r = 3;
+  else if (f.status == kBoxRect) r = query2d_serial(T, f.minX, f.maxX, f.minY, f.maxY, f.maxZ) ? 1 : 0;
+  out[i] = r;
+}
+
+__global__ void k_query2d(Target T, uint32_t minX, uint32_t maxX, uint32_t minY, uint32_t maxY, uint32_t maxZ, uint32_t* out) {
+  __shared__ uint32_t s_flag;
+  if (threadIdx.x == 0) s_flag = 0u;
+  __syncthreads();
+  query2d_coop(T, minX, maxX, minY, maxY, maxZ, threadIdx.x, blockDim.x, &s_flag);
+  __syncthreads();
+  if (threadIdx.x == 0) *out = s_flag;
+}
+
+// readBackDepth, Rasterizer.cpp:351-399: one thread per pixel, BGRA8 row-major
+__global__ void k_readback(Target T, uint8_t* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T.width * T.height) return;
+  const uint32_t x = i % T.width, y = i / T.width;
+  const uint32_t b = (y >> 3) * T.blocksX + (x >> 3);
+  uchar4 px = make_uchar4(0, 0, 0, 0);
+  if (T.hiz[b] != 1) {
+    const float bias = 3.9623753e+28f;
+    const float depth = u2f((uint32_t)T.depth[(size_t)b * 64u + (y & 7u) * 8u + (x & 7u)] << 12) * bias;
+    const float lin = (2 * 0.25f) / ((0.25f + 1000.0f) - (1.0f - depth) * (1000.0f - 0.25f));
+    const uint32_t d = (uint32_t)(100 * 256 * lin);
+    px = make_uchar4((uint8_t)(d / 100u), (uint8_t)(d % 256u), 0, 255);
+  }
+  reinterpret_cast<uchar4*>(out)[i] = px;
+}
+
+// canonical export: cleared blocks (HiZ == 1) read as zero -- already true by construction since
+// clear zeroes depth; kept as a copy kernel so downloads never expose garbage after a natural HiZ==1
+__global__ void k_canonical_depth(const uint16_t* depth, const uint16_t* hiz, uint32_t blocks, uint4* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= blocks * 8u) return;
+  const uint4 v = reinterpret_cast<const uint4*>(depth)[i];
+  out[i] = hiz[i >> 3] == 1 ? make_uint4(0u, 0u, 0u, 0u) : v;
+}
+
+}  // namespace orz
+
+// =================================================================================================
+// C ABI
+using namespace orz;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define ORZ_CUDA(x)                                                                                   \
+  do {                                                                                                \
+    cudaError_t _e = (x);                                                                             \
+    if (_e != cudaSuccess) return fail(ORZ_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+struct orz_context {
+  int device = 0;
+  int numSMs = 0;
+  cudaStream_t stream = nullptr;
+  uint2* d_lut = nullptr;
+  uint32_t* d_rcp = nullptr;
+  int rcpBits = 0;
+  bool rcpExact = true;
+  std::vector<uint32_t> h_rcp;
+  uint64_t launches = 0;
+  int groupWarps = 0;
+  // grow-only device scratch
+  uint32_t* d_counter = nullptr;
+  void* d_scratch[8] = {nullptr};
+  size_t scratchBytes[8] = {0};
+  uint32_t* h_pinned = nullptr;  // small pinned mailbox for scalar results
+};
+struct orz_occluder {
+  orz_context* ctx;
+  uint4* d_quads;
+  uint32_t nQuads;
+  float refMin[4], refMax[4];
+};
+struct orz_rasterizer {
+  orz_context* ctx;
+  Target T;
+  ViewMatrices vm;
+  uint8_t* d_boxOut = nullptr;
+};
+struct orz_scene {
+  orz_context* ctx;
+  uint4* d_quads = nullptr;
+  OccMeta* d_occ = nullptr;
+  uint32_t nOcc = 0, totalQuads = 0;
+  float4* d_boxes = nullptr;
+  uint32_t nBoxes = 0;
+};
+
+extern "C" const char* orz_last_error(void) { return g_err.c_str(); }
+extern "C" int orz_version(void) { return 100; }
+
+static int ensure_scratch(orz_context* ctx, int idx, size_t bytes) {
+  if (ctx->scratchBytes[idx] >= bytes) return ORZ_OK;
+  if (ctx->d_scratch[idx]) cudaFree(ctx->d_scratch[idx]);
+  ctx->d_scratch[idx] = nullptr;
+  ctx->scratchBytes[idx] = 0;
+  ORZ_CUDA(cudaMalloc(&ctx->d_scratch[idx], bytes));
+  ctx->scratchBytes[idx] = bytes;
+  return ORZ_OK;
+}
+
+extern "C" int orz_context_create(int device, orz_context** out) {
+  if (!out) return fail(ORZ_ERR_ARG, "orz_context_create: out is NULL");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return fail(ORZ_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
+  if (device < 0 || device >= n) return fail(ORZ_ERR_ARG, "orz_context_create: bad device index");
+  ORZ_CUDA(cudaSetDevice(device));
+  orz_context* ctx = new orz_context();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  ORZ_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->numSMs = prop.multiProcessorCount;
+  ORZ_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ORZ_CUDA(cudaMalloc(&ctx->d_lut, 4096 * sizeof(uint2)));
+  ORZ_CUDA(cudaMemcpy(ctx->d_lut, edge_mask_table(), 4096 * sizeof(uint2), cudaMemcpyHostToDevice));
+  probe_host_rcp(ctx->h_rcp, ctx->rcpBits, ctx->rcpExact);
+  ORZ_CUDA(cudaMalloc(&ctx->d_rcp, ctx->h_rcp.size() * 4));
+  ORZ_CUDA(cudaMemcpy(ctx->d_rcp, ctx->h_rcp.data(), ctx->h_rcp.size() * 4, cudaMemcpyHostToDevice));
+  ORZ_CUDA(cudaMalloc(&ctx->d_counter, 64));
+  ORZ_CUDA(cudaHostAlloc(&ctx->h_pinned, 64, cudaHostAllocDefault));
+  *out = ctx;
+  return ORZ_OK;
+}
+extern "C" void orz_context_destroy(orz_context* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& p : ctx->d_scratch) if (p) cudaFree(p);
+  cudaFree(ctx->d_lut); cudaFree(ctx->d_rcp); cudaFree(ctx->d_counter);
+  cudaFreeHost(ctx->h_pinned);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+extern "C" int orz_context_synchronize(orz_context* ctx) {
+  ORZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return ORZ_OK;
+}
+extern "C" void* orz_context_stream(orz_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" uint64_t orz_context_launch_count(orz_context* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int orz_context_set_group_warps(orz_context* ctx, int warps) {
+  if (warps != 0 && warps != 1 && warps != 2 && warps != 4 && warps != 8) return fail(ORZ_ERR_ARG, "group warps must be 0, 1, 2, 4 or 8");
+  ctx->groupWarps = warps;
+  return ORZ_OK;
+}
+extern "C" int orz_context_set_rcp_table(orz_context* ctx, const uint32_t* table, int bits) {
+  if (!ctx || !table || bits < 1 || bits > 23) return fail(ORZ_ERR_ARG, "orz_context_set_rcp_table: bad arguments");
+  ORZ_CUDA(cudaSetDevice(ctx->device));
+  ORZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->h_rcp.assign(table, table + (size_t(1) << bits));
+  ctx->rcpBits = bits;
+  cudaFree(ctx->d_rcp);
+  ORZ_CUDA(cudaMalloc(&ctx->d_rcp, ctx->h_rcp.size() * 4));
+  ORZ_CUDA(cudaMemcpy(ctx->d_rcp, ctx->h_rcp.data(), ctx->h_rcp.size() * 4, cudaMemcpyHostToDevice));
+  return ORZ_OK;
+}
+extern "C" int orz_context_get_rcp_table(orz_context* ctx, uint32_t* table, int* bits) {
+  if (!ctx) return fail(ORZ_ERR_ARG, "null context");
+  if (bits) *bits = ctx->rcpBits;
+  if (table) memcpy(table, ctx->h_rcp.data(), ctx->h_rcp.size() * 4);
+  return ORZ_OK;
+}
+extern "C" int orz_context_get_lut(orz_context* ctx, int64_t* lut4096) {
+  if (!ctx || !lut4096) return fail(ORZ_ERR_ARG, "bad arguments");
+  memcpy(lut4096, edge_mask_table(), 4096 * 8);
+  return ORZ_OK;
+}
+
+// reference packet layout (Occluder.cpp:146-156) -> one uint4 (v0..v3) per quad
+static void relayout_packets(const uint32_t* packets, uint32_t packetCount, uint4* out) {
+  const uint32_t nQuads = packetCount * 2;
+  for (uint32_t q = 0; q < nQuads; ++q) {
+    const uint32_t g = q >> 3, l = q & 7;
+    const uint32_t* base = packets + (size_t)g * 32 + l;
+    out[q] = make_uint4(base[0], base[8], base[16], base[24]);
+  }
+}
+
+extern "C" int orz_occluder_create(orz_context* ctx, const uint32_t* packets, uint32_t packetCount, const float* refMin4,
+                                   const float* refMax4, orz_occluder** out) {
+  if (!ctx || !packets || !out || packetCount % 4 != 0) return fail(ORZ_ERR_ARG, "orz_occluder_create: bad arguments");
+  ORZ_CUDA(cudaSetDevice(ctx->device));
+  orz_occluder* o = new orz_occluder();
+  o->ctx = ctx;
+  o->nQuads = packetCount * 2;
+  memcpy(o->refMin, refMin4, 16);
+  memcpy(o->refMax, refMax4, 16);
+  std::vector<uint4> tmp(o->nQuads);
+  relayout_packets(packets, packetCount, tmp.data());
+  o->d_quads = nullptr;
+  if (o->nQuads) {
+    ORZ_CUDA(cudaMalloc(&o->d_quads, tmp.size() * sizeof(uint4)));
+    ORZ_CUDA(cudaMemcpy(o->d_quads, tmp.data(), tmp.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+  }
+  *out = o;
+  return ORZ_OK;
+}
+extern "C" void orz_occluder_destroy(orz_occluder* o) {
+  if (!o) return;
+  cudaSetDevice(o->ctx->device);
+  cudaStreamSynchronize(o->ctx->stream);
+  cudaFree(o->d_quads);
+  delete o;
+}
+
+extern "C" int orz_rasterizer_create(orz_context* ctx, uint32_t width, uint32_t height, orz_rasterizer** out) {
+  if (!ctx || !out || width == 0 || height == 0 || width % 8 || height % 8 || width > 65535u * 8u || height > 65535u * 8u)
+    return fail(ORZ_ERR_ARG, "orz_rasterizer_create: width and height must be positive multiples of 8");  // Rasterizer.cpp:68
+  ORZ_CUDA(cudaSetDevice(ctx->device));
+  orz_rasterizer* r = new orz_rasterizer();
+  r->ctx = ctx;
+  r->T.width = width; r->T.height = height; r->T.blocksX = width / 8; r->T.blocksY = height / 8;
+  const size_t blocks = (size_t)r->T.blocksX * r->T.blocksY;
+  ORZ_CUDA(cudaMalloc(&r->T.depth, blocks * 128));
+  ORZ_CUDA(cudaMalloc(&r->T.hiz, (blocks + 8) * 2));
+  ORZ_CUDA(cudaMemsetAsync(r->T.depth, 0, blocks * 128, ctx->stream));
+  ORZ_CUDA(cudaMemsetAsync(r->T.hiz, 0, (blocks + 8) * 2, ctx->stream));  // Rasterizer.cpp:71: HiZ starts at 0 until clear()
+  memset(&r->vm, 0, sizeof r->vm);
+  *out = r;
+  return ORZ_OK;
+}
+extern "C" void orz_rasterizer_destroy(orz_rasterizer* r) {
+  if (!r) return;
+  cudaSetDevice(r->ctx->device);
+  cudaStreamSynchronize(r->ctx->stream);
+  cudaFree(r->T.depth); cudaFree(r->T.hiz); cudaFree(r->d_boxOut);
+  delete r;
+}
+extern "C" int orz_rasterizer_set_mvp(orz_rasterizer* r, const float* m) {
+  if (!r || !m) return fail(ORZ_ERR_ARG, "orz_rasterizer_set_mvp: bad arguments");
+  bake_view_matrices(m, r->T.width, r->T.height, r->vm);
+  return ORZ_OK;
+}
+extern "C" int orz_rasterizer_clear(orz_rasterizer* r) {
+  if (!r) return fail(ORZ_ERR_ARG, "null rasterizer");
+  ORZ_CUDA(cudaSetDevice(r->ctx->device));
+  const uint32_t blocks = r->T.blocksX * r->T.blocksY;
+  k_clear<<<r->ctx->numSMs * 2, 256, 0, r->ctx->stream>>>(r->T.depth, r->T.hiz, blocks);
+  r->ctx->launches++;
+  ORZ_CUDA(cudaGetLastError());
+  return ORZ_OK;
+}
+extern "C" int orz_rasterizer_rasterize(orz_rasterizer* r, const orz_occluder* occ, int clipped) {
+  if (!r || !occ) return fail(ORZ_ERR_ARG, "orz_rasterizer_rasterize: bad arguments");
+  if (occ->nQuads == 0) return ORZ_OK;
+  ORZ_CUDA(cudaSetDevice(r->ctx->device));
+  constexpr int GW = 4;
+  const uint32_t grid = (r->T.blocksY + GW - 1) / GW;  // one screen block-row per warp
+  const float4 mn = make_float4(occ->refMin[0], occ->refMin[1], occ->refMin[2], occ->refMin[3]);
+  const float4 mx = make_float4(occ->refMax[0], occ->refMax[1], occ->refMax[2], occ->refMax[3]);
+  k_rasterize_single<GW><<<grid, GW * 32, 0, r->ctx->stream>>>(r->vm, occ->d_quads, occ->nQuads, mn, mx, clipped, r->T,
+                                                                 r->ctx->d_rcp, 23 - r->ctx->rcpBits, r->ctx->d_lut);
+  r->ctx->launches++;
+  ORZ_CUDA(cudaGetLastError());
+  return ORZ_OK;
+}
+extern "C" int orz_rasterizer_query2d(orz_rasterizer* r, uint32_t minX, uint32_t maxX, uint32_t minY, uint32_t maxY, uint32_t maxZ,
+                                      int* visible) {
+  if (!r || !visible) return fail(ORZ_ERR_ARG, "orz_rasterizer_query2d: bad arguments");
+  if (maxX >= r->T.width || maxY >= r->T.height || minX > maxX || minY > maxY) return fail(ORZ_ERR_ARG, "orz_rasterizer_query2d: rectangle outside the buffer");
+  ORZ_CUDA(cudaSetDevice(r->ctx->device));
+  k_query2d<<<1, 256, 0, r->ctx->stream>>>(r->T, minX, maxX, minY, maxY, maxZ, r->ctx->d_counter + 8);
+  r->ctx->launches++;
+  ORZ_CUDA(cudaMemcpyAsync(r->ctx->h_pinned, r->ctx->d_counter + 8, 4, cudaMemcpyDeviceToHost, r->ctx->stream));
+  ORZ_CUDA(cudaStreamSynchronize(r->ctx->stream));
+  *visible = r->ctx->h_pinned[0] ? 1 : 0;
+  return ORZ_OK;
+}
+extern "C" int orz_rasterizer_query_visibility(orz_rasterizer* r, const float* bmin, const float* bmax, int* visible, int* needsClipping) {
+  if (!r || !bmin || !bmax || !visible) return fail(ORZ_ERR_ARG, "orz_rasterizer_query_visibility: bad arguments");
+  // the front half is state independent and scalar: evaluate it here with the same core the
+  // kernels use, then ask the GPU only for the rectangle test (Rasterizer.cpp:275)
+  const RcpTable rt{r->ctx->h_rcp.data(), 23 - r->ctx->rcpBits};
+  const BoxFront f = box_front_half(r->vm, bmin, bmax, r->T.width, r->T.height, rt);
+  if (f.status == kBoxCulled) { *visible = 0; return ORZ_OK; }  // needsClipping untouched, as in the reference
+  if (f.status == kBoxNearClip) { *visible = 1; if (needsClipping) *needsClipping = 1; return ORZ_OK; }
+  if (needsClipping) *needsClipping = 0;
+  return orz_rasterizer_query2d(r, f.minX, f.maxX, f.minY, f.maxY, f.maxZ, visible);
+}
+extern "C" int orz_rasterizer_query_boxes(orz_rasterizer* r, const float* boxes, uint32_t n, uint8_t* out) {
+  if (!r || (n && (!boxes || !out))) return fail(ORZ_ERR_ARG, "orz_rasterizer_query_boxes: bad arguments");
+  if (n == 0) return ORZ_OK;
+  orz_context* ctx = r->ctx;
+  ORZ_CUDA(cudaSetDevice(ctx->device));
+  if (int e = ensure_scratch(ctx, 0, (size_t)n * 32)) return e;
+  if (int e = ensure_scratch(ctx, 1, n)) return e;
+  ORZ_CUDA(cudaMemcpyAsync(ctx->d_scratch[0], boxes, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  k_query_boxes<<<(n + 127) / 128, 128, 0, ctx->stream>>>(r->vm, (const float4*)ctx->d_scratch[0], n, r->T, ctx->d_rcp, 23 - ctx->rcpBits,
+                                                          (uint8_t*)ctx->d_scratch[1]);
+  ctx->launches++;
+  ORZ_CUDA(cudaGetLastError());
+  ORZ_CUDA(cudaMemcpyAsync(out, ctx->d_scratch[1], n, cudaMemcpyDeviceToHost, ctx->stream));
+  ORZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return ORZ_OK;
+}
+extern "C" int orz_rasterizer_readback_depth(orz_rasterizer* r, void* target) {
+  if (!r || !target) return fail(ORZ_ERR_ARG, "orz_rasterizer_readback_depth: bad arguments");
+  orz_context* ctx = r->ctx;
+  ORZ_CUDA(cudaSetDevice(ctx->device));
+  const size_t px = (size_t)r->T.width * r->T.height;
+  if (int e = ensure_scratch(ctx, 2, px * 4)) return e;
+  k_readback<<<(uint32_t)((px + 255) / 256), 256, 0, ctx->stream>>>(r->T, (uint8_t*)ctx->d_scratch[2]);
+  ctx->launches++;
+  ORZ_CUDA(cudaGetLastError());
+  ORZ_CUDA(cudaMemcpyAsync(target, ctx->d_scratch[2], px * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  ORZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return ORZ_OK;
+}
+extern "C" int orz_rasterizer_download(orz_rasterizer* r, uint16_t* depth, uint16_t* hiz) {
+  if (!r) return fail(ORZ_ERR_ARG, "null rasterizer");
+  orz_context* ctx = r->ctx;
+  ORZ_CUDA(cudaSetDevice(ctx->device));
+  const uint32_t blocks = r->T.blocksX * r->T.blocksY;
+  if (depth) {
+    if (int e = ensure_scratch(ctx, 2, (size_t)blocks * 128)) return e;
+    k_canonical_depth<<<(blocks * 8 + 255) / 256, 256, 0, ctx->stream>>>(r->T.depth, r->T.hiz, blocks, (uint4*)ctx->d_scratch[2]);
+    ctx->launches++;
+    ORZ_CUDA(cudaGetLastError());
+    ORZ_CUDA(cudaMemcpyAsync(depth, ctx->d_scratch[2], (size_t)blocks * 128, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (hiz) ORZ_CUDA(cudaMemcpyAsync(hiz, r->T.hiz, (size_t)blocks * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  ORZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return ORZ_OK;
+}
+extern "C" int orz_rasterizer_debug_setup(orz_rasterizer* r, const orz_occluder* occ, int clipped, orz_prim_record* out) {
+  if (!r || !occ || !out) return fail(ORZ_ERR_ARG, "orz_rasterizer_debug_setup: bad arguments");
+  orz_context* ctx = r->ctx;
+  ORZ_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)occ->nQuads * sizeof(orz_prim_record);
+  if (int e = ensure_scratch(ctx, 3, bytes)) return e;
+  const float4 mn = make_float4(occ->refMin[0], occ->refMin[1], occ->refMin[2], occ->refMin[3]);
+  const float4 mx = make_float4(occ->refMax[0], occ->refMax[1], occ->refMax[2], occ->refMax[3]);
+  k_debug_setup<<<(occ->nQuads + 127) / 128, 128, 0, ctx->stream>>>(r->vm, occ->d_quads, occ->nQuads, mn, mx, clipped, r->T, ctx->d_rcp,
+                                                                    23 - ctx->rcpBits, (orz_prim_record*)ctx->d_scratch[3]);
+  ctx->launches++;
+  ORZ_CUDA(cudaGetLastError());
+  ORZ_CUDA(cudaMemcpyAsync(out, ctx->d_scratch[3], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  ORZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return ORZ_OK;
+}
+
+// ---- scenes + view batches ---------------------------------------------------------------------
+extern "C" int orz_scene_create(orz_context* ctx, const uint32_t* packets, const uint32_t* packetCounts, uint32_t nOcc,
+                                const float* refMin, const float* refMax, const float* boundsMin, const float* boundsMax,
+                                const float* centers, orz_scene** out) {
+  if (!ctx || !packets || !packetCounts || !refMin || !refMax || !boundsMin || !boundsMax || !centers || !out || nOcc == 0)
+    return fail(ORZ_ERR_ARG, "orz_scene_create: bad arguments");
+  ORZ_CUDA(cudaSetDevice(ctx->device));
+  orz_scene* s = new orz_scene();
+  s->ctx = ctx;
+  s->nOcc = nOcc;
+  std::vector<OccMeta> meta(nOcc);
+  size_t totalPackets = 0;
+  for (uint32_t i = 0; i < nOcc; ++i) {
+    if (packetCounts[i] % 4 != 0) { delete s; return fail(ORZ_ERR_ARG, "orz_scene_create: packet counts must be multiples of 4"); }
+    meta[i].quadOffset = (uint32_t)(totalPackets * 2);
+    meta[i].quadCount = packetCounts[i] * 2;
+    meta[i].pad0 = meta[i].pad1 = 0;
+    memcpy(meta[i].refMin, refMin + 4 * i, 16); memcpy(meta[i].refMax, refMax + 4 * i, 16);
+    memcpy(meta[i].boundsMin, boundsMin + 4 * i, 16); memcpy(meta[i].boundsMax, boundsMax + 4 * i, 16);
+    memcpy(meta[i].center, centers + 4 * i, 16);
+    totalPackets += packetCounts[i];
+  }
+  s->totalQuads = (uint32_t)(totalPackets * 2);
+  std::vector<uint4> quads(s->totalQuads);
+  size_t pofs = 0;
+  for (uint32_t i = 0; i < nOcc; ++i) {
+    relayout_packets(packets + pofs * 8, packetCounts[i], quads.data() + meta[i].quadOffset);
+    pofs += packetCounts[i];
+  }
+  ORZ_CUDA(cudaMalloc(&s->d_quads, std::max<size_t>(quads.size(), 1) * sizeof(uint4)));
+  ORZ_CUDA(cudaMemcpy(s->d_quads, quads.data(), quads.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+  ORZ_CUDA(cudaMalloc(&s->d_occ, meta.size() * sizeof(OccMeta)));
+  ORZ_CUDA(cudaMemcpy(s->d_occ, meta.data(), meta.size() * sizeof(OccMeta), cudaMemcpyHostToDevice));
+  *out = s;
+  return ORZ_OK;
+}
+extern "C" int orz_scene_set_occludees(orz_scene* s, const float* boxes, uint32_t n) {
+  if (!s || (n && !boxes)) return fail(ORZ_ERR_ARG, "orz_scene_set_occludees: bad arguments");
+  ORZ_CUDA(cudaSetDevice(s->ctx->device));
+  ORZ_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  cudaFree(s->d_boxes);
+  s->d_boxes = nullptr;
+  s->nBoxes = n;
+  if (n) {
+    ORZ_CUDA(cudaMalloc(&s->d_boxes, (size_t)n * 32));
+    ORZ_CUDA(cudaMemcpy(s->d_boxes, boxes, (size_t)n * 32, cudaMemcpyHostToDevice));
+  }
+  return ORZ_OK;
+}
+extern "C" void orz_scene_destroy(orz_scene* s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  cudaFree(s->d_quads); cudaFree(s->d_occ); cudaFree(s->d_boxes);
+  delete s;
+}
+
+template <int GW>
+static int launch_views(orz_context* ctx, const FrameParams& p, uint32_t grid) {
+  k_render_views<GW><<<grid, GW * 32, 0, ctx->stream>>>(p);
+  ctx->launches++;
+  ORZ_CUDA(cudaGetLastError());
+  return ORZ_OK;
+}
+template <int GW>
+static int occupancy_views(int* perSM) {
+  ORZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(perSM, k_render_views<GW>, GW * 32, 0));
+  return ORZ_OK;
+}
+
+extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const orz_view_batch* b) {
+  if (!ctx || !scene || !b || !b->mvps || (!b->orders && !b->camPos)) return fail(ORZ_ERR_ARG, "orz_render_views_device: bad arguments");
+  if (b->width == 0 || b->height == 0 || b->width % 8 || b->height % 8) return fail(ORZ_ERR_ARG, "width and height must be positive multiples of 8");
+  if (b->nViews == 0) return ORZ_OK;
+  ORZ_CUDA(cudaSetDevice(ctx->device));
+  const int GW = ctx->groupWarps ? ctx->groupWarps : 4;
+  int perSM = 0;
+  int e = GW == 1 ? occupancy_views<1>(&perSM) : GW == 2 ? occupancy_views<2>(&perSM) : GW == 4 ? occupancy_views<4>(&perSM) : occupancy_views<8>(&perSM);
+  if (e) return e;
+  if (perSM < 1) perSM = 1;
+  const uint32_t grid = std::min<uint32_t>(b->nViews, (uint32_t)(ctx->numSMs * perSM));
+  const size_t blocks = (size_t)(b->width / 8) * (b->height / 8);
+
+  FrameParams p;
+  memset(&p, 0, sizeof p);
+  p.quads = scene->d_quads; p.occ = scene->d_occ; p.nOcc = scene->nOcc;
+  p.boxes = scene->d_boxes; p.nBoxes = scene->nBoxes;
+  p.rcp = ctx->d_rcp; p.rcpShift = 23 - ctx->rcpBits; p.lut = ctx->d_lut;
+  p.width = b->width; p.height = b->height; p.nViews = b->nViews; p.flags = b->flags;
+  p.mvps = b->mvps; p.orders = b->orders; p.camPos = b->camPos;
+  p.bitWords = (scene->nBoxes + 31) / 32;
+  p.visBits = scene->nBoxes ? b->visBits : nullptr;
+  p.clipBits = scene->nBoxes ? b->clipBits : nullptr;
+  p.gate = b->gate; p.quadsSubmitted = b->quadsSubmitted;
+  // depth + HiZ: per view when both are outputs, else one scratch target per CTA
+  const size_t hizStride = (blocks + 7) & ~size_t(7);
+  if (b->depth && b->hiz) {
+    p.depth = b->depth; p.hiz = b->hiz; p.depthStride = blocks * 64; p.hizStride = blocks; p.perViewTarget = 1;
+    if (blocks % 8 != 0) return fail(ORZ_ERR_ARG, "per-view depth output needs (w/8)*(h/8) to be a multiple of 8");
+  } else if (!b->depth && !b->hiz) {
+    if ((e = ensure_scratch(ctx, 4, (size_t)grid * blocks * 128))) return e;
+    if ((e = ensure_scratch(ctx, 5, (size_t)grid * hizStride * 2))) return e;
+    p.depth = (uint16_t*)ctx->d_scratch[4]; p.hiz = (uint16_t*)ctx->d_scratch[5];
+    p.depthStride = blocks * 64; p.hizStride = hizStride; p.perViewTarget = 0;
+  } else {
+    return fail(ORZ_ERR_ARG, "depth and hiz outputs must be requested together");
+  }
+  if (!b->orders) {
+    if ((e = ensure_scratch(ctx, 6, (size_t)grid * scene->nOcc * 4))) return e;
+    p.orderScratch = (uint32_t*)ctx->d_scratch[6];
+  }
+  p.viewCounter = ctx->d_counter;
+  ORZ_CUDA(cudaMemsetAsync(ctx->d_counter, 0, 4, ctx->stream));
+  return GW == 1 ? launch_views<1>(ctx, p, grid) : GW == 2 ? launch_views<2>(ctx, p, grid) : GW == 4 ? launch_views<4>(ctx, p, grid) : launch_views<8>(ctx, p, grid);
+}
+
+// Host-pointer variant: stage inputs to HBM, render, bring the requested outputs back.
+extern "C" int orz_render_views(orz_context* ctx, orz_scene* scene, const orz_view_batch* hb) {
+  if (!ctx || !scene || !hb || !hb->mvps || (!hb->orders && !hb->camPos)) return fail(ORZ_ERR_ARG, "orz_render_views: bad arguments");
+  if (hb->nViews == 0) return ORZ_OK;
+  ORZ_CUDA(cudaSetDevice(ctx->device));
+  const size_t nV = hb->nViews, nOcc = scene->nOcc, blocks = (size_t)(hb->width / 8) * (hb->height / 8);
+  const size_t bitWords = (scene->nBoxes + 31) / 32;
+  // one staging arena: [mvps | orders/camPos | visBits | clipBits | gate | quads] + separate depth/hiz
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+  const size_t oMvp = take(nV * 64);
+  const size_t oOrd = take(hb->orders ? nV * nOcc * 4 : nV * 12);
+  const size_t oVis = take(hb->visBits ? nV * bitWords * 4 : 0);
+  const size_t oClip = take(hb->clipBits ? nV * bitWords * 4 : 0);
+  const size_t oGate = take(hb->gate ? nV * nOcc : 0);
+  const size_t oQuads = take(hb->quadsSubmitted ? nV * 4 : 0);
+  int e;
+  if ((e = ensure_scratch(ctx, 7, off))) return e;
+  uint8_t* arena = (uint8_t*)ctx->d_scratch[7];
+  orz_view_batch db = *hb;
+  db.mvps = (const float*)(arena + oMvp);
+  ORZ_CUDA(cudaMemcpyAsync(arena + oMvp, hb->mvps, nV * 64, cudaMemcpyHostToDevice, ctx->stream));
+  if (hb->orders) {
+    db.orders = (const uint32_t*)(arena + oOrd);
+    ORZ_CUDA(cudaMemcpyAsync(arena + oOrd, hb->orders, nV * nOcc * 4, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    db.camPos = (const float*)(arena + oOrd);
+    ORZ_CUDA(cudaMemcpyAsync(arena + oOrd, hb->camPos, nV * 12, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  db.visBits = hb->visBits ? (uint32_t*)(arena + oVis) : nullptr;
+  db.clipBits = hb->clipBits ? (uint32_t*)(arena + oClip) : nullptr;
+  db.gate = hb->gate ? (arena + oGate) : nullptr;
+  db.quadsSubmitted = hb->quadsSubmitted ? (uint32_t*)(arena + oQuads) : nullptr;
+  if (hb->depth || hb->hiz) {
+    if (!hb->depth || !hb->hiz) return fail(ORZ_ERR_ARG, "depth and hiz outputs must be requested together");
+    if ((e = ensure_scratch(ctx, 2, nV * blocks * 128))) return e;
+    if ((e = ensure_scratch(ctx, 3, nV * blocks * 2))) return e;
+    db.depth = (uint16_t*)ctx->d_scratch[2];
+    db.hiz = (uint16_t*)ctx->d_scratch[3];
+  }
+  if ((e = orz_render_views_device(ctx, scene, &db))) return e;
+  if (hb->visBits) ORZ_CUDA(cudaMemcpyAsync(hb->visBits, db.visBits, nV * bitWords * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (hb->clipBits) ORZ_CUDA(cudaMemcpyAsync(hb->clipBits, db.clipBits, nV * bitWords * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (hb->gate) ORZ_CUDA(cudaMemcpyAsync(hb->gate, db.gate, nV * nOcc, cudaMemcpyDeviceToHost, ctx->stream));
+  if (hb->quadsSubmitted) ORZ_CUDA(cudaMemcpyAsync(hb->quadsSubmitted, db.quadsSubmitted, nV * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (hb->depth) {
+    ORZ_CUDA(cudaMemcpyAsync(hb->depth, db.depth, nV * blocks * 128, cudaMemcpyDeviceToHost, ctx->stream));
+    ORZ_CUDA(cudaMemcpyAsync(hb->hiz, db.hiz, nV * blocks * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  ORZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return ORZ_OK;
+}

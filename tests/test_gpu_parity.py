@@ -1,0 +1,234 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (rasterizer_b200.api ->
+librasterizer_b200.so), against the oracle on the same seeded inputs.  Bit-exact: depth, HiZ,
+gate decisions, occludee visibility / needsClipping bits, setup records, read-back image.
+Run on the B200 box: python -m pytest tests -m gpu -x -q"""
+import numpy as np
+import pytest
+
+from oracle import port_oracle as po
+from oracle import ref_oracle as ro
+from rasterizer_b200 import api
+from rasterizer_b200 import camera as cam
+from rasterizer_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context(0)
+    # oracle and GPU must model the same rcpps: the one of the CPU this test runs on
+    po.set_tables()
+    assert np.array_equal(c.rcp_table(), po.probe_host_rcp(int(np.log2(c.rcp_table().size))))
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def lut(ctx):
+    t = ctx.lut()
+    assert np.array_equal(t, po.build_lut())
+    return t
+
+
+class Bundle:
+    """Prepared scene + its baked batches (host bake through the C ABI)."""
+
+    def __init__(self, name):
+        self.ps = wl.load_scene(name) if name == "city" or wl.have_scene(name) else None
+        if self.ps is None:
+            pytest.skip(f"prepared scene {name} not available")
+        baked = [api.bake(b, self.ps.ref_min, self.ps.ref_max) for b in self.ps.batches]
+        self.packed = [b[0] for b in baked]
+        self.centers = np.stack([b[1] for b in baked])
+        self.bmin = np.stack([b[2] for b in baked])
+        self.bmax = np.stack([b[3] for b in baked])
+        self.boxes = self.ps.quad_boxes()
+
+    def scene(self, ctx, boxes=None):
+        return api.Scene(ctx, self.packed, self.ps.ref_min, self.ps.ref_max, self.bmin, self.bmax, self.centers,
+                         self.boxes if boxes is None else boxes)
+
+    def default_view(self, w, h):
+        c = self.ps.camera
+        return cam.view_projection(c["pos"], c["dir"], c["up"], c["fov"], w, h), np.array(c["pos"], np.float32)
+
+
+_bundles = {}
+
+
+def bundle(name):
+    if name not in _bundles:
+        _bundles[name] = Bundle(name)
+    return _bundles[name]
+
+
+def port_frame(B, port, mvp, order, boxes):
+    gate, quads = port.frame(B.packed, B.bmin, B.bmax, B.ps.ref_min, B.ps.ref_max, mvp, order)
+    q = port.query_boxes(boxes) if boxes is not None and len(boxes) else np.zeros(0, np.uint8)
+    return gate, quads, port.depth(), port.hiz(), q
+
+
+@pytest.mark.parametrize("name", ["city", "castle"])
+def test_setup_records(ctx, name):
+    B = bundle(name)
+    w, h = 1920, 1080
+    mvp, _ = B.default_view(w, h)
+    r = api.Rasterizer(ctx, w, h)
+    r.setModelViewProjection(mvp)
+    port = po.PortRasterizer(w, h, np.zeros(4096, np.int64))
+    port.set_mvp(mvp)
+    n_valid = 0
+    for bi in range(0, len(B.packed), max(1, len(B.packed) // 10)):
+        occ = api.Occluder(ctx, B.packed[bi], B.ps.ref_min, B.ps.ref_max)
+        for clipped in (False, True):
+            recs = r.debug_setup(occ, clipped)
+            pk = B.packed[bi]
+            for q in range(len(recs)):
+                g, l = divmod(q, 8)
+                words = np.array([pk[(4 * g + j) * 8 + l] for j in range(4)], np.uint32)
+                want = port.setup_quad(words, B.ps.ref_min, B.ps.ref_max, clipped)
+                assert bytes(recs[q]) == bytes(want), (name, bi, q, clipped)
+                n_valid += int(want.mode != 0)
+        occ.close()
+    assert n_valid > 100
+    r.close(); port.close()
+
+
+@pytest.mark.parametrize("name,size", [("city", (640, 360)), ("castle", (1920, 1080))])
+def test_per_call_api_frame(ctx, lut, name, size):
+    """The reference's own call sequence (Main.cpp:181-206) through the drop-in per-call API."""
+    B = bundle(name)
+    w, h = size
+    mvp, pos = B.default_view(w, h)
+    order = cam.front_to_back_order(B.centers, pos)
+    port = po.PortRasterizer(w, h, lut)
+    boxes = B.boxes[:: max(1, len(B.boxes) // 4000)]
+    gate, quads, depth, hiz, qv = port_frame(B, port, mvp, order, boxes)
+
+    occs = [api.Occluder(ctx, p, B.ps.ref_min, B.ps.ref_max) for p in B.packed]
+    r = api.Rasterizer(ctx, w, h)
+    r.clear()
+    r.setModelViewProjection(mvp)
+    for slot, o in enumerate(order):
+        vis, clip = r.queryVisibility(B.bmin[o], B.bmax[o])
+        assert (int(vis) | (int(clip) << 1)) == gate[slot], (slot, o)
+        if vis:
+            r.rasterize(occs[o], clip)
+    d, hz = r.download()
+    assert np.array_equal(hz, hiz)
+    assert np.array_equal(d, depth)
+    assert np.array_equal(r.query_boxes(boxes), qv)
+    assert np.array_equal(r.readBackDepth(), port.readback())
+    # query2D directly (Rasterizer.cpp:283-349)
+    rng = np.random.default_rng(3)
+    for _ in range(40):
+        x0, x1 = sorted(rng.integers(0, w, 2)); y0, y1 = sorted(rng.integers(0, h, 2)); z = int(rng.integers(0, 65536))
+        assert r.query2D(int(x0), int(x1), int(y0), int(y1), z) == port.query2d(int(x0), int(x1), int(y0), int(y1), z)
+    for o in occs:
+        o.close()
+    r.close(); port.close()
+
+
+@pytest.mark.parametrize("gw", [1, 2, 4, 8])
+@pytest.mark.parametrize("name,size,nviews", [("city", (640, 360), 6), ("castle", (1920, 1080), 5), ("castle", (512, 256), 12)])
+def test_view_batch(ctx, lut, name, size, nviews, gw):
+    B = bundle(name)
+    w, h = size
+    ctx.set_group_warps(gw)
+    mvps, poss = wl.camera_path(B.ps, nviews - 1, w, h) if size[0] >= 640 else wl.probe_views(B.ps, nviews - 1, w, h)
+    m0, p0 = B.default_view(w, h)
+    mvps = np.concatenate([m0[None], mvps]); poss = np.concatenate([p0[None], poss])
+    orders = wl.orders_for(B.centers, poss)
+    boxes = B.boxes[:: max(1, len(B.boxes) // 3000)]
+    sc = B.scene(ctx, boxes)
+    out = sc.render_views(w, h, mvps, orders=orders, want=("vis", "clip", "gate", "depth", "hiz", "quads"))
+    vis = api.unpack_bits(out["vis"], len(boxes)); clip = api.unpack_bits(out["clip"], len(boxes))
+    port = po.PortRasterizer(w, h, lut)
+    for v in range(nviews):
+        gate, quads, depth, hiz, qv = port_frame(B, port, mvps[v], orders[v], boxes)
+        assert np.array_equal(out["gate"][v], gate), v
+        assert out["quads"][v] == quads
+        assert np.array_equal(out["hiz"][v], hiz), v
+        assert np.array_equal(out["depth"][v], depth), v
+        assert np.array_equal(vis[v], (qv & 1).astype(bool)), v
+        assert np.array_equal(clip[v], (qv & 2).astype(bool)), v
+    # bits-only call (scratch depth per CTA) and GPU-side ordering must give the same bits
+    out2 = sc.render_views(w, h, mvps, cam_pos=poss, want=("vis", "gate"))
+    assert np.array_equal(out2["vis"], out["vis"])
+    assert np.array_equal(out2["gate"], out["gate"])
+    ctx.set_group_warps(0)
+    sc.close(); port.close()
+
+
+@pytest.mark.parametrize("size", [(1280, 720), (3840, 2160)])
+def test_no_gate_forced_clip_and_4k_wrap(ctx, lut, size):
+    """Config-4 shape: every batch through rasterize<true>, no gate; 3840x2160 also exercises the
+    16-bit wrap of the first-block index (Rasterizer.cpp:1054)."""
+    B = bundle("castle" if wl.have_scene("castle") else "city")
+    w, h = size
+    mvps, poss = wl.camera_path(B.ps, 2, w, h)
+    orders = wl.orders_for(B.centers, poss)
+    sc = B.scene(ctx, B.boxes[::7])
+    out = sc.render_views(w, h, mvps, orders=orders, flags=api.BATCH_NO_GATE | api.BATCH_FORCE_CLIPPED, want=("vis", "depth", "hiz"))
+    vis = api.unpack_bits(out["vis"], len(B.boxes[::7]))
+    port = po.PortRasterizer(w, h, lut)
+    for v in range(2):
+        port.clear(); port.set_mvp(mvps[v])
+        for o in orders[v]:
+            port.rasterize(B.packed[o], B.ps.ref_min, B.ps.ref_max, True)
+        assert np.array_equal(out["hiz"][v], port.hiz())
+        assert np.array_equal(out["depth"][v], port.depth())
+        assert np.array_equal(vis[v], (port.query_boxes(B.boxes[::7]) & 1).astype(bool))
+    sc.close(); port.close()
+
+
+def test_soup_near_clipped(ctx, lut):
+    ps = wl.synthetic_soup(8192, cube=60.0)
+    baked = [api.bake(b, ps.ref_min, ps.ref_max) for b in ps.batches]
+    sc = api.Scene(ctx, [b[0] for b in baked], ps.ref_min, ps.ref_max, np.stack([b[2] for b in baked]), np.stack([b[3] for b in baked]),
+                   np.stack([b[1] for b in baked]), ps.quad_boxes()[::5])
+    w, h = 1280, 720
+    c = ps.camera
+    mvps = np.stack([cam.view_projection(c["pos"], d, c["up"], c["fov"], w, h) for d in ((0, 0, 1), (1, 0.2, 0.1), (-0.3, 0.1, -1))])
+    poss = np.zeros((3, 3), np.float32)
+    orders = wl.orders_for(np.stack([b[1] for b in baked]), poss)
+    port = po.PortRasterizer(w, h, lut)
+    for flags in (0, api.BATCH_NO_GATE | api.BATCH_FORCE_CLIPPED):
+        out = sc.render_views(w, h, mvps, orders=orders, flags=flags, want=("vis", "depth", "hiz", "gate"))
+        for v in range(3):
+            if flags:
+                port.clear(); port.set_mvp(mvps[v])
+                for o in orders[v]:
+                    port.rasterize(baked[o][0], ps.ref_min, ps.ref_max, True)
+            else:
+                gate, _ = port.frame([b[0] for b in baked], np.stack([b[2] for b in baked]), np.stack([b[3] for b in baked]),
+                                     ps.ref_min, ps.ref_max, mvps[v], orders[v])
+                assert np.array_equal(out["gate"][v], gate)
+            assert np.array_equal(out["hiz"][v], port.hiz())
+            assert np.array_equal(out["depth"][v], port.depth())
+    sc.close(); port.close()
+
+
+@pytest.mark.skipif(not (ro.available() and ro.scene_available("Castle")), reason="reference build / scene data not shipped")
+def test_against_reference_binary_on_this_host(ctx):
+    """The real reference (unmodified sources, oracle/_ref) run on this box's CPU vs the GPU."""
+    B = bundle("castle")
+    s = ro.RefScene.load("Castle")
+    assert all(np.array_equal(s.packed(i), B.packed[i]) for i in range(s.n_occluders))
+    w, h = 1920, 1080
+    mvps, poss = wl.camera_path(B.ps, 4, w, h)
+    orders = wl.orders_for(B.centers, poss)
+    sc = B.scene(ctx)
+    out = sc.render_views(w, h, mvps, orders=orders, want=("vis", "clip", "gate", "depth", "hiz"))
+    vis = api.unpack_bits(out["vis"], len(B.boxes)); clip = api.unpack_bits(out["clip"], len(B.boxes))
+    r = ro.RefRasterizer(w, h)
+    for v in range(4):
+        gate, _ = r.frame(s, mvps[v], orders[v])
+        assert np.array_equal(out["gate"][v], gate)
+        assert np.array_equal(out["hiz"][v], r.hiz())
+        assert np.array_equal(out["depth"][v], r.depth())
+        q = r.query_boxes(B.boxes)
+        assert np.array_equal(vis[v], (q & 1).astype(bool))
+        assert np.array_equal(clip[v], (q & 2).astype(bool))
+    r.close(); s.close(); sc.close()

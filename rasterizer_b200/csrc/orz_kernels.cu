@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(GW * 32) k_render_views(const FrameParams p) {
           else if (f.status == kBoxRect) vis = query2d_serial(T, f.minX, f.maxX, f.minY, f.maxY, f.maxZ);
         }
         const uint32_t vb = __ballot_sync(kFull, vis), cb = __ballot_sync(kFull, clip);
-        if (lane == 0) {
+        if (lane == 0 && (base >> 5) + (uint32_t)warp < p.bitWords) {
           const size_t w = (size_t)view * p.bitWords + (base >> 5) + (uint32_t)warp;
           if (p.visBits) p.visBits[w] = vb;
           if (p.clipBits) p.clipBits[w] = cb;

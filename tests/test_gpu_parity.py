@@ -69,6 +69,19 @@ def port_frame(B, port, mvp, order, boxes):
     return gate, quads, port.depth(), port.hiz(), q
 
 
+def _same_record(a, b) -> bool:
+    """Bitwise equality, except that any NaN equals any NaN: a zero-length edge (v3 == v0 in the
+    lone-triangle quads) gives 0 * inf, for which x86 produces 0xFFC00000 and the GPU 0x7FFFFFFF;
+    no consumer can tell them apart (comparisons false, cvtt -> 0x80000000 for both)."""
+    wa = np.frombuffer(bytes(a), np.uint32).copy()
+    wb = np.frombuffer(bytes(b), np.uint32).copy()
+    fa, fb = wa[6:21].view(np.float32), wb[6:21].view(np.float32)
+    both_nan = np.isnan(fa) & np.isnan(fb)
+    wa[6:21][both_nan] = 0
+    wb[6:21][both_nan] = 0
+    return bool(np.array_equal(wa, wb))
+
+
 @pytest.mark.parametrize("name", ["city", "castle"])
 def test_setup_records(ctx, name):
     B = bundle(name)
@@ -88,7 +101,7 @@ def test_setup_records(ctx, name):
                 g, l = divmod(q, 8)
                 words = np.array([pk[(4 * g + j) * 8 + l] for j in range(4)], np.uint32)
                 want = port.setup_quad(words, B.ps.ref_min, B.ps.ref_max, clipped)
-                assert bytes(recs[q]) == bytes(want), (name, bi, q, clipped)
+                assert _same_record(recs[q], want), (name, bi, q, clipped)
                 n_valid += int(want.mode != 0)
         occ.close()
     assert n_valid > 100

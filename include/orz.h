@@ -99,7 +99,9 @@ void orz_scene_destroy(orz_scene* scene);
 
 enum {
   ORZ_BATCH_NO_GATE = 1u,      /* submit every occluder, no queryVisibility gate (config 4 shape) */
-  ORZ_BATCH_FORCE_CLIPPED = 2u /* with NO_GATE: use rasterize<true> for every occluder */
+  ORZ_BATCH_FORCE_CLIPPED = 2u, /* with NO_GATE: use rasterize<true> for every occluder */
+  ORZ_BATCH_TARGETS_ON_DEVICE = 4u /* orz_render_views only: depth / hiz are DEVICE pointers (the
+                                      buffers stay resident in HBM; only bits and gates travel) */
 };
 typedef struct {
   uint32_t width, height;

@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(HERE, "librasterizer_b200.so")
 
 BATCH_NO_GATE = 1
 BATCH_FORCE_CLIPPED = 2
+BATCH_TARGETS_ON_DEVICE = 4
 
 _lib = None
 

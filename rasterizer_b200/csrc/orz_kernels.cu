@@ -1021,7 +1021,8 @@ extern "C" int orz_render_views(orz_context* ctx, orz_scene* scene, const orz_vi
   db.clipBits = hb->clipBits ? (uint32_t*)(arena + oClip) : nullptr;
   db.gate = hb->gate ? (arena + oGate) : nullptr;
   db.quadsSubmitted = hb->quadsSubmitted ? (uint32_t*)(arena + oQuads) : nullptr;
-  if (hb->depth || hb->hiz) {
+  const bool targetsOnDevice = (hb->flags & ORZ_BATCH_TARGETS_ON_DEVICE) != 0u;
+  if ((hb->depth || hb->hiz) && !targetsOnDevice) {
     if (!hb->depth || !hb->hiz) return fail(ORZ_ERR_ARG, "depth and hiz outputs must be requested together");
     if ((e = ensure_scratch(ctx, 2, nV * blocks * 128))) return e;
     if ((e = ensure_scratch(ctx, 3, nV * blocks * 2))) return e;
@@ -1033,7 +1034,7 @@ extern "C" int orz_render_views(orz_context* ctx, orz_scene* scene, const orz_vi
   if (hb->clipBits) ORZ_CUDA(cudaMemcpyAsync(hb->clipBits, db.clipBits, nV * bitWords * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (hb->gate) ORZ_CUDA(cudaMemcpyAsync(hb->gate, db.gate, nV * nOcc, cudaMemcpyDeviceToHost, ctx->stream));
   if (hb->quadsSubmitted) ORZ_CUDA(cudaMemcpyAsync(hb->quadsSubmitted, db.quadsSubmitted, nV * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (hb->depth) {
+  if (hb->depth && !targetsOnDevice) {
     ORZ_CUDA(cudaMemcpyAsync(hb->depth, db.depth, nV * blocks * 128, cudaMemcpyDeviceToHost, ctx->stream));
     ORZ_CUDA(cudaMemcpyAsync(hb->hiz, db.hiz, nV * blocks * 2, cudaMemcpyDeviceToHost, ctx->stream));
   }

@@ -33,14 +33,16 @@
 #include "orz_core.h"
 #include "orz_host.h"
 
+#ifndef ORZ_THREADS_PER_SM
+#define ORZ_THREADS_PER_SM 1024  // resident threads per SM the view-batch kernel is compiled for (register cap = 65536 / this)
+#endif
+
 namespace orz {
 
 __constant__ uint32_t c_modeNibbles[32] = {ORZ_MODE_NIBBLES};
 
 constexpr uint32_t kFull = 0xffffffffu;
-constexpr int kRecWords = 20;   // words per primitive record
 constexpr int kRecStride = 21;  // odd stride: conflict-free lane-per-record stores
-constexpr int kWindow = 64;     // occluders whose front half is precomputed at a time
 
 struct OccMeta {
   uint32_t quadOffset, quadCount, pad0, pad1;
@@ -113,50 +115,60 @@ __device__ __forceinline__ void raster_prim(const uint32_t* __restrict__ rec, co
   const bool upperHalf = (wIdx & 2) != 0;
   const uint32_t sh0 = (uint32_t)(wIdx & 1) * 16u + (rpar ? 0u : 4u) + (uint32_t)k2;  // mask bit of pixel 2w (Rasterizer.cpp:1257-1268)
   const uint32_t sh1 = sh0 + 8u;
+  const bool convex = mode == kConvex;
+  uint32_t* const depthWords = reinterpret_cast<uint32_t*>(T.depth) + lane;
 
+  uint32_t rowMod = r0 % rowStride;  // (r0 + by) % rowStride, kept incrementally
   for (uint32_t by = 0; by < rangeY; ++by) {
-    const uint32_t R = r0 + by;
-    const bool mineA = (R % rowStride) == rowPhase;
-    const bool mineB = crossing && ((R + 1) % rowStride) == rowPhase;
+    const bool mineA = rowMod == rowPhase;
+    rowMod = rowMod + 1u == rowStride ? 0u : rowMod + 1u;
+    const bool mineB = crossing && rowMod == rowPhase;
     if (mineA || mineB) {
+      // The x chain restarts from the row start (Rasterizer.cpp:1136-1137).  Steps are applied
+      // lazily: `owed` counts the adds still to do before the next block that is really visited,
+      // so blocks behind the last HiZ candidate of the row cost nothing.
       float o = lineOff, dA = lineA, dB = lineB;
+      uint32_t owed = 0;
+      bool hitInRow = false, rowDone = false;
       const uint32_t L = fb + by * blocksX;
       uint32_t a = 0;
 #pragma unroll 1
-      for (int piece = 0; piece < 2; ++piece) {
+      for (int piece = 0; piece < 2 && !rowDone; ++piece) {
         const uint32_t b = piece == 0 ? split : rangeX;
         const bool mine = piece == 0 ? mineA : mineB;
-        if (!mine) {
-          if (piece == 0 && mineB)
-            for (uint32_t i = a; i < b; ++i) { o = nxe + o; dA = dzdx + dA; dB = dzdx + dB; }
-          a = b;
-          continue;
-        }
-        // ---- walk blocks [a, b) of this primitive row, 32 HiZ entries at a time
-        for (uint32_t s0 = a; s0 < b; s0 += 32) {
+        if (!mine) { owed += b - a; a = b; continue; }
+#pragma unroll 1
+        for (uint32_t s0 = a; s0 < b && !rowDone; s0 += 32) {
           const uint32_t m = min(32u, b - s0);
           const uint32_t hv = (uint32_t)lane < m ? (uint32_t)T.hiz[L + s0 + lane] : 0xffffu;
           uint32_t cand = __ballot_sync(kFull, hv < maxZ);  // Rasterizer.cpp:1148-1152
+          const uint32_t cleared = __ballot_sync(kFull, hv == 1u);
           uint32_t pos = 0;
           while (cand) {
             const uint32_t j = (uint32_t)__ffs((int)cand) - 1u;
             cand &= cand - 1u;
-            for (; pos < j; ++pos) { o = nxe + o; dA = dzdx + dA; dB = dzdx + dB; }  // Rasterizer.cpp:1145-1146
-            const uint32_t h = __shfl_sync(kFull, hv, (int)j);
+            const uint32_t steps = owed + j - pos;
+#pragma unroll 1
+            for (uint32_t i = 0; i < steps; ++i) { o = nxe + o; dA = dzdx + dA; dB = dzdx + dB; }  // Rasterizer.cpp:1145-1146
+            owed = 0; pos = j;
             const uint32_t blk = L + s0 + j;
             uint2 mk;
-            if (mode == kConvex) {  // Rasterizer.cpp:1155-1187
-              if (__any_sync(kFull, o >= 63.0f)) continue;
-              int q = cvtt_x86(o);
-              q = q < 0 ? 0 : q;
-              uint2 t = lut[(slope | (uint32_t)q) & 4095u];
+            if (convex) {  // Rasterizer.cpp:1155-1187
+              if (__any_sync(kFull, o >= 63.0f)) {
+                if (hitInRow) { rowDone = true; break; }  // convexity: nothing further in this row (:1161-1165)
+                continue;
+              }
+              hitInRow = true;
+              // max(cvtt(o), 0) for o < 63 or NaN: NaN and negatives give 0
+              const uint32_t q = (uint32_t)__float2int_rz(fmaxf(o, 0.0f));
+              uint2 t = lut[slope | q];
               t.x &= __shfl_xor_sync(kFull, t.x, 1); t.y &= __shfl_xor_sync(kFull, t.y, 1);
               t.x &= __shfl_xor_sync(kFull, t.x, 2); t.y &= __shfl_xor_sync(kFull, t.y, 2);
               mk = t;  // no empty-mask test on this path (Rasterizer.cpp:1186)
             } else {  // Rasterizer.cpp:1188-1239
-              int q = cvtt_x86(o);
-              q = q < 0 ? 0 : (q > 63 ? 63 : q);
-              const uint2 t = lut[(slope | (uint32_t)q) & 4095u];
+              // min(max(cvtt(o), 0), 63): NaN and anything >= 2^31 convert to 0x80000000 -> 0
+              const uint32_t q = o < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o, 0.0f), 63.0f)) : 0u;
+              const uint2 t = lut[slope | q];
               const int g = lane & ~3;
               uint2 A, B, C, D;
               A.x = __shfl_sync(kFull, t.x, g + 0); A.y = __shfl_sync(kFull, t.y, g + 0);
@@ -170,6 +182,10 @@ __device__ __forceinline__ void raster_prim(const uint32_t* __restrict__ rec, co
               else { mk.x = (A.x & D.x) & (B.x | C.x); mk.y = (A.y & D.y) & (B.y | C.y); }
               if ((mk.x | mk.y) == 0u) continue;
             }
+            uint32_t* dptr = depthWords + (size_t)blk * 32u;
+            const bool merge = ((cleared >> j) & 1u) == 0u;  // Rasterizer.cpp:1271
+            uint32_t old = 0u;
+            if (merge) old = *dptr;
             // ---- depth of this lane's two pixels, Rasterizer.cpp:1241-1254
             float a0 = dA, b0 = dB;
             if (upperHalf) { a0 = ORZ_FMA(dzdx, 0.5f, a0); b0 = ORZ_FMA(dzdx, 0.5f, b0); }
@@ -184,14 +200,13 @@ __device__ __forceinline__ void raster_prim(const uint32_t* __restrict__ rec, co
             const uint32_t selMask = ((0u - ((mw >> sh0) & 1u)) & 0x0000ffffu) | ((0u - ((mw >> sh1) & 1u)) & 0xffff0000u);
             val &= selMask;
             // ---- merge, store, HiZ; Rasterizer.cpp:1271-1290
-            uint32_t* dptr = reinterpret_cast<uint32_t*>(T.depth) + (size_t)blk * 32u + (uint32_t)lane;
-            if (h != 1u) val = __vmaxu2(val, *dptr);
+            val = __vmaxu2(val, old);
             *dptr = val;
             uint32_t mn = min(val & 0xffffu, val >> 16);
             mn = __reduce_min_sync(kFull, mn);
             if (lane == 0) T.hiz[blk] = (uint16_t)mn;
           }
-          for (; pos < m; ++pos) { o = nxe + o; dA = dzdx + dA; dB = dzdx + dB; }
+          owed += m - pos;
         }
         a = b;
       }
@@ -278,7 +293,14 @@ __device__ __forceinline__ void setup_chunk(const uint4* __restrict__ quads, uin
 }
 
 // ---------------------------------------------------------------------------------------------
-// View-batch kernel: Main.cpp:181-206 for every view, one CTA of GW warps per view at a time.
+// View-batch path: Main.cpp:181-206 for many independent views, three launches per batch:
+//   k_prepare_views  per (view, occluder): everything that does not depend on the depth buffer --
+//                    matrices, front-to-back order, query front half, per-call matrix
+//   k_render_views   one CTA of GW warps per view at a time: clear, then gate -> setup -> traversal
+//                    per occluder in order
+//   k_query_views    one thread per (view, occludee box) on the finished buffers
+constexpr int kFrontWords = 20;  // status, minX, maxX, minY, maxY, maxZ, CallMatrix (14 floats)
+
 struct FrameParams {
   const uint4* quads;
   const OccMeta* occ;
@@ -290,29 +312,101 @@ struct FrameParams {
   const uint2* lut;
   uint32_t width, height, nViews, flags;
   const float* mvps;
-  const uint32_t* orders;
+  const uint32_t* orders;  // caller's order, or NULL: computed from camPos into orderBuf
   const float* camPos;
+  uint32_t* orderBuf;      // nViews x nOcc
+  ViewMatrices* vmBuf;     // nViews
+  uint32_t* frontBuf;      // nViews x nOcc x kFrontWords
   uint16_t* depth;
   uint16_t* hiz;
-  unsigned long long depthStride, hizStride;  // elements between consecutive views (or CTAs when scratch)
-  int perViewTarget;                          // 1: index by view, 0: index by CTA (scratch)
+  unsigned long long depthStride, hizStride;  // elements between consecutive views
   uint32_t* visBits;
   uint32_t* clipBits;
   uint32_t bitWords;
   uint8_t* gate;
   uint32_t* quadsSubmitted;
   uint32_t* viewCounter;
-  uint32_t* orderScratch;  // per CTA nOcc entries, used when the order is computed here
+  uint32_t* viewCost;   // nViews: quads of the occluders that survive the frustum test (scheduling estimate)
+  uint32_t* viewOrder;  // nViews: views sorted by descending cost (longest first), or NULL
 };
 
-template <int GW>
-__global__ void __launch_bounds__(GW * 32) k_render_views(const FrameParams p) {
-  constexpr uint32_t NT = GW * 32;
+__global__ void __launch_bounds__(128) k_prepare_views(const FrameParams p) {
   __shared__ ViewMatrices s_vm;
-  __shared__ uint32_t s_front[kWindow][6];
-  __shared__ float s_cm[kWindow][14];
-  __shared__ uint32_t s_recs[NT * kRecStride];
-  __shared__ uint32_t s_count[GW];
+  const uint32_t view = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+  const RcpTable rt{p.rcp, p.rcpShift};
+  if (tid == 0) {  // setModelViewProjection, Rasterizer.cpp:76-105
+    bake_view_matrices(p.mvps + 16 * (size_t)view, p.width, p.height, s_vm);
+    p.vmBuf[view] = s_vm;
+  }
+  // front-to-back order (Main.cpp:185-190) when the caller did not supply one: rank sort on
+  // dp(c - p, c - p) in the dpps 0x7f sum order, stable by index
+  const uint32_t* order = p.orders ? p.orders + (size_t)view * p.nOcc : nullptr;
+  if (!order) {
+    uint32_t* mine = p.orderBuf + (size_t)view * p.nOcc;
+    const float cx = p.camPos[3 * (size_t)view + 0], cy = p.camPos[3 * (size_t)view + 1], cz = p.camPos[3 * (size_t)view + 2];
+    for (uint32_t i = tid; i < p.nOcc; i += NT) {
+      const float* ci = p.occ[i].center;
+      const float dxi = ci[0] - cx, dyi = ci[1] - cy, dzi = ci[2] - cz;
+      const float ki = (dxi * dxi + dyi * dyi) + dzi * dzi;
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < p.nOcc; ++j) {
+        const float* cj = p.occ[j].center;
+        const float dxj = cj[0] - cx, dyj = cj[1] - cy, dzj = cj[2] - cz;
+        const float kj = (dxj * dxj + dyj * dyj) + dzj * dzj;
+        rank += (kj < ki || (kj == ki && j < i)) ? 1u : 0u;
+      }
+      mine[rank] = i;
+    }
+    order = mine;
+  }
+  __syncthreads();
+  const bool useGate = (p.flags & ORZ_BATCH_NO_GATE) == 0u;
+  uint32_t cost = 0;
+  for (uint32_t slot = tid; slot < p.nOcc; slot += NT) {
+    const OccMeta& om = p.occ[order[slot]];
+    BoxFront f;
+    if (useGate) {
+      f = box_front_half(s_vm, om.boundsMin, om.boundsMax, p.width, p.height, rt);  // Rasterizer.cpp:123-273
+    } else {
+      f.status = kBoxNearClip; f.minX = f.maxX = f.minY = f.maxY = f.maxZ = 0;
+    }
+    CallMatrix cm;
+    prepare_call(s_vm.baked, om.refMin, om.refMax, cm);  // Rasterizer.cpp:616-655
+    uint32_t* out = p.frontBuf + ((size_t)view * p.nOcc + slot) * kFrontWords;
+    out[0] = f.status; out[1] = f.minX; out[2] = f.maxX; out[3] = f.minY; out[4] = f.maxY; out[5] = f.maxZ;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { out[6 + k] = f2u(cm.rx[k]); out[10 + k] = f2u(cm.ry[k]); out[14 + k] = f2u(cm.rw[k]); }
+    out[18] = f2u(cm.c0); out[19] = f2u(cm.c1);
+    if (f.status != kBoxCulled) cost += om.quadCount;
+  }
+  // per-view work estimate for longest-first scheduling of the render kernel
+  __shared__ uint32_t s_cost;
+  if (tid == 0) s_cost = 0u;
+  __syncthreads();
+  cost = __reduce_add_sync(kFull, cost);
+  if ((tid & 31u) == 0 && cost) atomicAdd(&s_cost, cost);
+  __syncthreads();
+  if (tid == 0) p.viewCost[view] = s_cost;
+}
+
+// views by descending cost, ties by index (rank sort; nViews is at most a few thousand per chunk)
+__global__ void __launch_bounds__(256) k_sort_views(const uint32_t* __restrict__ cost, uint32_t n, uint32_t* __restrict__ order) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t ci = cost[i];
+  uint32_t rank = 0;
+  for (uint32_t j = 0; j < n; ++j) {
+    const uint32_t cj = cost[j];
+    rank += (cj > ci || (cj == ci && j < i)) ? 1u : 0u;
+  }
+  order[rank] = i;
+}
+
+template <int GW>
+__global__ void __launch_bounds__(GW * 32, ORZ_THREADS_PER_SM / (GW * 32)) k_render_views(const FrameParams p) {
+  constexpr uint32_t NT = GW * 32;
+  __shared__ uint32_t s_recs[2][NT * kRecStride];
+  __shared__ uint32_t s_count[2][GW];
   __shared__ uint32_t s_flag[3];
   __shared__ uint32_t s_view;
 
@@ -324,135 +418,101 @@ __global__ void __launch_bounds__(GW * 32) k_render_views(const FrameParams p) {
   const uint32_t blocks = T.blocksX * T.blocksY;
   const bool useGate = (p.flags & ORZ_BATCH_NO_GATE) == 0u;
   const bool forceClip = (p.flags & ORZ_BATCH_FORCE_CLIPPED) != 0u;
+  uint32_t buf = 0;
 
   for (;;) {
-    if (tid == 0) s_view = atomicAdd(p.viewCounter, 1u);
+    if (tid == 0) { s_view = atomicAdd(p.viewCounter, 1u); s_flag[0] = s_flag[1] = s_flag[2] = 0u; }
     __syncthreads();
-    const uint32_t view = s_view;
-    if (view >= p.nViews) break;
-    const size_t slot = p.perViewTarget ? (size_t)view : (size_t)blockIdx.x;
-    T.depth = p.depth + slot * p.depthStride;
-    T.hiz = p.hiz + slot * p.hizStride;
+    if (s_view >= p.nViews) break;
+    const uint32_t view = p.viewOrder ? p.viewOrder[s_view] : s_view;
+    T.depth = p.depth + (size_t)view * p.depthStride;
+    T.hiz = p.hiz + (size_t)view * p.hizStride;
+    const uint32_t* order = p.orders ? p.orders + (size_t)view * p.nOcc : p.orderBuf + (size_t)view * p.nOcc;
+    const uint32_t* front = p.frontBuf + (size_t)view * p.nOcc * kFrontWords;
 
-    // ---- clear (Rasterizer.cpp:107-121; depth zeroed too = fresh state) + setMVP (Rasterizer.cpp:76-105)
+    // ---- clear (Rasterizer.cpp:107-121; depth zeroed too = fresh state)
     {
       uint4* d4 = reinterpret_cast<uint4*>(T.depth);
       const uint4 z = make_uint4(0u, 0u, 0u, 0u);
       for (uint32_t i = tid; i < blocks * 8u; i += NT) d4[i] = z;
       for (uint32_t i = tid; i < blocks; i += NT) T.hiz[i] = 1;
-      if (tid == 0) {
-        bake_view_matrices(p.mvps + 16 * (size_t)view, p.width, p.height, s_vm);
-        s_flag[0] = s_flag[1] = s_flag[2] = 0u;
-      }
-    }
-    // ---- front-to-back order (Main.cpp:185-190) when the caller did not supply one
-    const uint32_t* order = p.orders ? p.orders + (size_t)view * p.nOcc : nullptr;
-    if (!order) {
-      uint32_t* mine = p.orderScratch + (size_t)blockIdx.x * p.nOcc;
-      const float cx = p.camPos[3 * (size_t)view + 0], cy = p.camPos[3 * (size_t)view + 1], cz = p.camPos[3 * (size_t)view + 2];
-      for (uint32_t i = tid; i < p.nOcc; i += NT) {  // rank sort, stable by index
-        const float* ci = p.occ[i].center;
-        const float dxi = ci[0] - cx, dyi = ci[1] - cy, dzi = ci[2] - cz;
-        const float ki = (dxi * dxi + dyi * dyi) + dzi * dzi;  // dpps 0x7f
-        uint32_t rank = 0;
-        for (uint32_t j = 0; j < p.nOcc; ++j) {
-          const float* cj = p.occ[j].center;
-          const float dxj = cj[0] - cx, dyj = cj[1] - cy, dzj = cj[2] - cz;
-          const float kj = (dxj * dxj + dyj * dyj) + dzj * dzj;
-          rank += (kj < ki || (kj == ki && j < i)) ? 1u : 0u;
-        }
-        mine[rank] = i;
-      }
-      order = mine;
     }
     __syncthreads();
 
     uint32_t gateIdx = 0, quadsSubmitted = 0;
-    for (uint32_t wbase = 0; wbase < p.nOcc; wbase += kWindow) {
-      const uint32_t wn = min((uint32_t)kWindow, p.nOcc - wbase);
-      // ---- state-independent part for a window of occluders: query front half + call matrix
-      for (uint32_t i = tid; i < wn; i += NT) {
-        const OccMeta& om = p.occ[order[wbase + i]];
-        BoxFront f;
-        if (useGate) {
-          f = box_front_half(s_vm, om.boundsMin, om.boundsMax, p.width, p.height, rt);
-        } else {
-          f.status = kBoxNearClip; f.minX = f.maxX = f.minY = f.maxY = f.maxZ = 0;
-        }
-        s_front[i][0] = f.status; s_front[i][1] = f.minX; s_front[i][2] = f.maxX;
-        s_front[i][3] = f.minY; s_front[i][4] = f.maxY; s_front[i][5] = f.maxZ;
-        CallMatrix cm;
-        prepare_call(s_vm.baked, om.refMin, om.refMax, cm);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { s_cm[i][k] = cm.rx[k]; s_cm[i][4 + k] = cm.ry[k]; s_cm[i][8 + k] = cm.rw[k]; }
-        s_cm[i][12] = cm.c0; s_cm[i][13] = cm.c1;
+    for (uint32_t slot = 0; slot < p.nOcc; ++slot) {
+      const uint32_t* fr = front + (size_t)slot * kFrontWords;
+      const uint32_t status = fr[0];
+      bool visible = false, clipped = false;
+      if (status == kBoxNearClip) {
+        visible = true;
+        clipped = useGate ? true : forceClip;
+      } else if (status == kBoxRect) {
+        // ---- gate: query2D on the buffers as built so far (Main.cpp:195)
+        volatile uint32_t* flag = &s_flag[gateIdx % 3u];
+        if (tid == 0) s_flag[(gateIdx + 1u) % 3u] = 0u;
+        query2d_coop(T, fr[1], fr[2], fr[3], fr[4], fr[5], tid, NT, flag);
+        __syncthreads();
+        visible = *flag != 0u;
+        ++gateIdx;
       }
-      __syncthreads();
+      if (p.gate && tid == 0) p.gate[(size_t)view * p.nOcc + slot] = (uint8_t)((visible ? 1 : 0) | (clipped && useGate ? 2 : 0));
+      if (!visible) continue;
 
-      for (uint32_t wi = 0; wi < wn; ++wi) {
-        const uint32_t status = s_front[wi][0];
-        bool visible = false, clipped = false;
-        if (status == kBoxNearClip) {
-          visible = true;
-          clipped = useGate ? true : forceClip;
-        } else if (status == kBoxRect) {
-          // ---- gate: query2D on the buffers as built so far (Main.cpp:195)
-          volatile uint32_t* flag = &s_flag[gateIdx % 3u];
-          if (tid == 0) s_flag[(gateIdx + 1u) % 3u] = 0u;
-          query2d_coop(T, s_front[wi][1], s_front[wi][2], s_front[wi][3], s_front[wi][4], s_front[wi][5], tid, NT, flag);
-          __syncthreads();
-          visible = *flag != 0u;
-          ++gateIdx;
-        }
-        if (p.gate && tid == 0) p.gate[(size_t)view * p.nOcc + wbase + wi] = (uint8_t)((visible ? 1 : 0) | (clipped && useGate ? 2 : 0));
-        if (!visible) continue;
-
-        // ---- rasterize<clipped>(occluder): setup chunk -> records -> traversal of my rows
-        const OccMeta& om = p.occ[order[wbase + wi]];
-        const uint4* quads = p.quads + om.quadOffset;
-        const uint32_t nq = om.quadCount;
-        quadsSubmitted += nq;
-        CallMatrix cm;
+      // ---- rasterize<clipped>(occluder): setup chunk -> records -> traversal of my rows.
+      // Records are double buffered: one barrier per chunk (after its setup) is enough, because
+      // a warp can only start overwriting buffer b two barriers after the traversal that read it.
+      const OccMeta& om = p.occ[order[slot]];
+      const uint4* quads = p.quads + om.quadOffset;
+      const uint32_t nq = om.quadCount;
+      quadsSubmitted += nq;
+      CallMatrix cm;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { cm.rx[k] = s_cm[wi][k]; cm.ry[k] = s_cm[wi][4 + k]; cm.rw[k] = s_cm[wi][8 + k]; }
-        cm.c0 = s_cm[wi][12]; cm.c1 = s_cm[wi][13];
-        for (uint32_t q0 = 0; q0 < nq; q0 += NT) {
-          setup_chunk(quads, q0, nq, clipped, cm, rt, T, warp, lane, s_recs, s_count);
-          __syncthreads();
+      for (int k = 0; k < 4; ++k) { cm.rx[k] = u2f(fr[6 + k]); cm.ry[k] = u2f(fr[10 + k]); cm.rw[k] = u2f(fr[14 + k]); }
+      cm.c0 = u2f(fr[18]); cm.c1 = u2f(fr[19]);
+      for (uint32_t q0 = 0; q0 < nq; q0 += NT) {
+        setup_chunk(quads, q0, nq, clipped, cm, rt, T, warp, lane, s_recs[buf], s_count[buf]);
+        __syncthreads();
 #pragma unroll 1
-          for (int w2 = 0; w2 < GW; ++w2) {
-            const uint32_t cnt = s_count[w2];
-            for (uint32_t i = 0; i < cnt; ++i)
-              raster_prim<GW>(s_recs + ((uint32_t)w2 * 32u + i) * kRecStride, lane, (uint32_t)warp, GW, T, p.lut);
-          }
-          __syncthreads();  // records consumed; depth/HiZ of this chunk visible to the whole group
+        for (int w2 = 0; w2 < GW; ++w2) {
+          const uint32_t cnt = s_count[buf][w2];
+          for (uint32_t i = 0; i < cnt; ++i)
+            raster_prim<GW>(s_recs[buf] + ((uint32_t)w2 * 32u + i) * kRecStride, lane, (uint32_t)warp, GW, T, p.lut);
         }
+        buf ^= 1u;
       }
-      __syncthreads();  // window tables are rewritten next
+      __syncthreads();  // depth/HiZ of this occluder visible to the whole group before the next gate
     }
     if (p.quadsSubmitted && tid == 0) p.quadsSubmitted[view] = quadsSubmitted;
+    __syncthreads();  // s_view is rewritten by the next view
+  }
+}
 
-    // ---- occludee queries on the finished buffers (Rasterizer.cpp:123-349), one thread per box
-    if (p.visBits || p.clipBits) {
-      for (uint32_t base = 0; base < p.nBoxes; base += NT) {
-        const uint32_t i = base + tid;
-        bool vis = false, clip = false;
-        if (i < p.nBoxes) {
-          const float4 mn = p.boxes[2 * (size_t)i], mx = p.boxes[2 * (size_t)i + 1];
-          const float bmn[4] = {mn.x, mn.y, mn.z, mn.w}, bmx[4] = {mx.x, mx.y, mx.z, mx.w};
-          const BoxFront f = box_front_half(s_vm, bmn, bmx, p.width, p.height, rt);
-          if (f.status == kBoxNearClip) { vis = true; clip = true; }
-          else if (f.status == kBoxRect) vis = query2d_serial(T, f.minX, f.maxX, f.minY, f.maxY, f.maxZ);
-        }
-        const uint32_t vb = __ballot_sync(kFull, vis), cb = __ballot_sync(kFull, clip);
-        if (lane == 0 && (base >> 5) + (uint32_t)warp < p.bitWords) {
-          const size_t w = (size_t)view * p.bitWords + (base >> 5) + (uint32_t)warp;
-          if (p.visBits) p.visBits[w] = vb;
-          if (p.clipBits) p.clipBits[w] = cb;
-        }
-      }
-    }
-    __syncthreads();  // s_view / s_vm are rewritten by the next view
+// queryVisibility for every (view, occludee box) on the finished buffers; Rasterizer.cpp:123-349
+__global__ void __launch_bounds__(256) k_query_views(const FrameParams p) {
+  __shared__ ViewMatrices s_vm;
+  const uint32_t view = blockIdx.y, tid = threadIdx.x;
+  if (tid < 32) reinterpret_cast<float*>(&s_vm)[tid] = reinterpret_cast<const float*>(p.vmBuf + view)[tid];
+  __syncthreads();
+  const RcpTable rt{p.rcp, p.rcpShift};
+  Target T;
+  T.width = p.width; T.height = p.height; T.blocksX = p.width >> 3; T.blocksY = p.height >> 3;
+  T.depth = p.depth + (size_t)view * p.depthStride;
+  T.hiz = p.hiz + (size_t)view * p.hizStride;
+  const uint32_t i = blockIdx.x * blockDim.x + tid;
+  bool vis = false, clip = false;
+  if (i < p.nBoxes) {
+    const float4 mn = p.boxes[2 * (size_t)i], mx = p.boxes[2 * (size_t)i + 1];
+    const float bmn[4] = {mn.x, mn.y, mn.z, mn.w}, bmx[4] = {mx.x, mx.y, mx.z, mx.w};
+    const BoxFront f = box_front_half(s_vm, bmn, bmx, p.width, p.height, rt);
+    if (f.status == kBoxNearClip) { vis = true; clip = true; }
+    else if (f.status == kBoxRect) vis = query2d_serial(T, f.minX, f.maxX, f.minY, f.maxY, f.maxZ);
+  }
+  const uint32_t vb = __ballot_sync(kFull, vis), cb = __ballot_sync(kFull, clip);
+  const uint32_t word = i >> 5;
+  if ((tid & 31u) == 0 && word < p.bitWords) {
+    if (p.visBits) p.visBits[(size_t)view * p.bitWords + word] = vb;
+    if (p.clipBits) p.clipBits[(size_t)view * p.bitWords + word] = cb;
   }
 }
 
@@ -598,6 +658,7 @@ struct orz_context {
   void* d_scratch[8] = {nullptr};
   size_t scratchBytes[8] = {0};
   uint32_t* h_pinned = nullptr;  // small pinned mailbox for scalar results
+  size_t arenaBudget = size_t(8) << 30;  // bytes of internal per-view depth+HiZ targets (views are chunked to fit)
 };
 struct orz_occluder {
   orz_context* ctx;
@@ -644,6 +705,7 @@ extern "C" int orz_context_create(int device, orz_context** out) {
   cudaDeviceProp prop;
   ORZ_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->numSMs = prop.multiProcessorCount;
+  ctx->arenaBudget = std::min<size_t>(size_t(24) << 30, prop.totalGlobalMem / 6);
   ORZ_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ORZ_CUDA(cudaMalloc(&ctx->d_lut, 4096 * sizeof(uint2)));
   ORZ_CUDA(cudaMemcpy(ctx->d_lut, edge_mask_table(), 4096 * sizeof(uint2), cudaMemcpyHostToDevice));
@@ -942,9 +1004,13 @@ static int occupancy_views(int* perSM) {
   return ORZ_OK;
 }
 
+// Device-pointer entry: three launches per chunk of views (prepare, render, query).  When the
+// caller does not ask for depth/HiZ, per-view targets live in an internal arena and the batch is
+// processed in chunks that fit the arena budget.
 extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const orz_view_batch* b) {
   if (!ctx || !scene || !b || !b->mvps || (!b->orders && !b->camPos)) return fail(ORZ_ERR_ARG, "orz_render_views_device: bad arguments");
   if (b->width == 0 || b->height == 0 || b->width % 8 || b->height % 8) return fail(ORZ_ERR_ARG, "width and height must be positive multiples of 8");
+  if ((b->depth != nullptr) != (b->hiz != nullptr)) return fail(ORZ_ERR_ARG, "depth and hiz outputs must be requested together");
   if (b->nViews == 0) return ORZ_OK;
   ORZ_CUDA(cudaSetDevice(ctx->device));
   const int GW = ctx->groupWarps ? ctx->groupWarps : 4;
@@ -952,40 +1018,73 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
   int e = GW == 1 ? occupancy_views<1>(&perSM) : GW == 2 ? occupancy_views<2>(&perSM) : GW == 4 ? occupancy_views<4>(&perSM) : occupancy_views<8>(&perSM);
   if (e) return e;
   if (perSM < 1) perSM = 1;
-  const uint32_t grid = std::min<uint32_t>(b->nViews, (uint32_t)(ctx->numSMs * perSM));
   const size_t blocks = (size_t)(b->width / 8) * (b->height / 8);
-
-  FrameParams p;
-  memset(&p, 0, sizeof p);
-  p.quads = scene->d_quads; p.occ = scene->d_occ; p.nOcc = scene->nOcc;
-  p.boxes = scene->d_boxes; p.nBoxes = scene->nBoxes;
-  p.rcp = ctx->d_rcp; p.rcpShift = 23 - ctx->rcpBits; p.lut = ctx->d_lut;
-  p.width = b->width; p.height = b->height; p.nViews = b->nViews; p.flags = b->flags;
-  p.mvps = b->mvps; p.orders = b->orders; p.camPos = b->camPos;
-  p.bitWords = (scene->nBoxes + 31) / 32;
-  p.visBits = scene->nBoxes ? b->visBits : nullptr;
-  p.clipBits = scene->nBoxes ? b->clipBits : nullptr;
-  p.gate = b->gate; p.quadsSubmitted = b->quadsSubmitted;
-  // depth + HiZ: per view when both are outputs, else one scratch target per CTA
+  const size_t nOcc = scene->nOcc;
   const size_t hizStride = (blocks + 7) & ~size_t(7);
-  if (b->depth && b->hiz) {
-    p.depth = b->depth; p.hiz = b->hiz; p.depthStride = blocks * 64; p.hizStride = blocks; p.perViewTarget = 1;
-    if (blocks % 8 != 0) return fail(ORZ_ERR_ARG, "per-view depth output needs (w/8)*(h/8) to be a multiple of 8");
-  } else if (!b->depth && !b->hiz) {
-    if ((e = ensure_scratch(ctx, 4, (size_t)grid * blocks * 128))) return e;
-    if ((e = ensure_scratch(ctx, 5, (size_t)grid * hizStride * 2))) return e;
-    p.depth = (uint16_t*)ctx->d_scratch[4]; p.hiz = (uint16_t*)ctx->d_scratch[5];
-    p.depthStride = blocks * 64; p.hizStride = hizStride; p.perViewTarget = 0;
-  } else {
-    return fail(ORZ_ERR_ARG, "depth and hiz outputs must be requested together");
+  const bool ownTargets = b->depth == nullptr;
+  if (!ownTargets && blocks % 8 != 0) return fail(ORZ_ERR_ARG, "per-view depth output needs (w/8)*(h/8) to be a multiple of 8");
+
+  // views per chunk: everything when the caller owns the targets, else what fits the arena budget
+  size_t chunk = b->nViews;
+  if (ownTargets) {
+    const size_t perView = blocks * 128 + hizStride * 2;
+    const size_t budget = std::max<size_t>(ctx->arenaBudget, perView);
+    chunk = std::max<size_t>(1, std::min<size_t>(b->nViews, budget / perView));
+    if ((e = ensure_scratch(ctx, 4, chunk * blocks * 128))) return e;
+    if ((e = ensure_scratch(ctx, 5, chunk * hizStride * 2))) return e;
   }
-  if (!b->orders) {
-    if ((e = ensure_scratch(ctx, 6, (size_t)grid * scene->nOcc * 4))) return e;
-    p.orderScratch = (uint32_t*)ctx->d_scratch[6];
+  if ((e = ensure_scratch(ctx, 6, chunk * sizeof(ViewMatrices) + chunk * nOcc * 4 + chunk * nOcc * kFrontWords * 4 + chunk * 8))) return e;
+  uint8_t* prep = (uint8_t*)ctx->d_scratch[6];
+
+  const size_t bitWords = (scene->nBoxes + 31) / 32;
+  for (size_t v0 = 0; v0 < b->nViews; v0 += chunk) {
+    const uint32_t nv = (uint32_t)std::min<size_t>(chunk, b->nViews - v0);
+    FrameParams p;
+    memset(&p, 0, sizeof p);
+    p.quads = scene->d_quads; p.occ = scene->d_occ; p.nOcc = scene->nOcc;
+    p.boxes = scene->d_boxes; p.nBoxes = scene->nBoxes;
+    p.rcp = ctx->d_rcp; p.rcpShift = 23 - ctx->rcpBits; p.lut = ctx->d_lut;
+    p.width = b->width; p.height = b->height; p.nViews = nv; p.flags = b->flags;
+    p.mvps = b->mvps + 16 * v0;
+    p.orders = b->orders ? b->orders + v0 * nOcc : nullptr;
+    p.camPos = b->camPos ? b->camPos + 3 * v0 : nullptr;
+    p.vmBuf = (ViewMatrices*)prep;
+    p.orderBuf = (uint32_t*)(prep + chunk * sizeof(ViewMatrices));
+    p.frontBuf = (uint32_t*)(prep + chunk * sizeof(ViewMatrices) + chunk * nOcc * 4);
+    p.bitWords = (uint32_t)bitWords;
+    p.visBits = (scene->nBoxes && b->visBits) ? b->visBits + v0 * bitWords : nullptr;
+    p.clipBits = (scene->nBoxes && b->clipBits) ? b->clipBits + v0 * bitWords : nullptr;
+    p.gate = b->gate ? b->gate + v0 * nOcc : nullptr;
+    p.quadsSubmitted = b->quadsSubmitted ? b->quadsSubmitted + v0 : nullptr;
+    if (ownTargets) {
+      p.depth = (uint16_t*)ctx->d_scratch[4]; p.hiz = (uint16_t*)ctx->d_scratch[5];
+      p.depthStride = blocks * 64; p.hizStride = hizStride;
+    } else {
+      p.depth = b->depth + v0 * blocks * 64; p.hiz = b->hiz + v0 * blocks;
+      p.depthStride = blocks * 64; p.hizStride = blocks;
+    }
+    p.viewCounter = ctx->d_counter;
+    p.viewCost = (uint32_t*)(prep + chunk * sizeof(ViewMatrices) + chunk * nOcc * 4 + chunk * nOcc * kFrontWords * 4);
+    p.viewOrder = nv <= 16384u ? p.viewCost + chunk : nullptr;
+    ORZ_CUDA(cudaMemsetAsync(ctx->d_counter, 0, 4, ctx->stream));
+    k_prepare_views<<<nv, 128, 0, ctx->stream>>>(p);
+    ctx->launches++;
+    ORZ_CUDA(cudaGetLastError());
+    if (p.viewOrder) {
+      k_sort_views<<<(nv + 255) / 256, 256, 0, ctx->stream>>>(p.viewCost, nv, p.viewOrder);
+      ctx->launches++;
+      ORZ_CUDA(cudaGetLastError());
+    }
+    const uint32_t grid = std::min<uint32_t>(nv, (uint32_t)(ctx->numSMs * perSM));
+    e = GW == 1 ? launch_views<1>(ctx, p, grid) : GW == 2 ? launch_views<2>(ctx, p, grid) : GW == 4 ? launch_views<4>(ctx, p, grid) : launch_views<8>(ctx, p, grid);
+    if (e) return e;
+    if (p.visBits || p.clipBits) {
+      k_query_views<<<dim3((scene->nBoxes + 255) / 256, nv), 256, 0, ctx->stream>>>(p);
+      ctx->launches++;
+      ORZ_CUDA(cudaGetLastError());
+    }
   }
-  p.viewCounter = ctx->d_counter;
-  ORZ_CUDA(cudaMemsetAsync(ctx->d_counter, 0, 4, ctx->stream));
-  return GW == 1 ? launch_views<1>(ctx, p, grid) : GW == 2 ? launch_views<2>(ctx, p, grid) : GW == 4 ? launch_views<4>(ctx, p, grid) : launch_views<8>(ctx, p, grid);
+  return ORZ_OK;
 }
 
 // Host-pointer variant: stage inputs to HBM, render, bring the requested outputs back.

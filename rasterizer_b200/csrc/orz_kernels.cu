@@ -243,6 +243,7 @@ __device__ __forceinline__ bool query_block(const Target& T, uint32_t bx, uint32
   const uint32_t b = by * T.blocksX + bx;
   const uint32_t h = T.hiz[b];
   if (maxZ <= h) return false;  // Rasterizer.cpp:310
+  if (h == 1u) return true;     // cleared block: depth reads as 0 < maxZ (fresh state), stored bytes are not valid yet
   const int sX = max((int)minX - (int)(8u * bx), 0), eX = min((int)maxX - (int)(8u * bx), 7);
   const int sY = max((int)minY - (int)(8u * by), 0), eY = min((int)maxY - (int)(8u * by), 7);
   if (sX == 0 && eX == 7 && sY == 0 && eY == 7) return true;  // Rasterizer.cpp:319-325
@@ -328,6 +329,7 @@ struct FrameParams {
   uint32_t* viewCounter;
   uint32_t* viewCost;   // nViews: quads of the occluders that survive the frustum test (scheduling estimate)
   uint32_t* viewOrder;  // nViews: views sorted by descending cost (longest first), or NULL
+  int exportDepth;      // 1: the caller reads depth back -> zero-fill blocks that stayed cleared
 };
 
 __global__ void __launch_bounds__(128) k_prepare_views(const FrameParams p) {
@@ -430,13 +432,11 @@ __global__ void __launch_bounds__(GW * 32, ORZ_THREADS_PER_SM / (GW * 32)) k_ren
     const uint32_t* order = p.orders ? p.orders + (size_t)view * p.nOcc : p.orderBuf + (size_t)view * p.nOcc;
     const uint32_t* front = p.frontBuf + (size_t)view * p.nOcc * kFrontWords;
 
-    // ---- clear (Rasterizer.cpp:107-121; depth zeroed too = fresh state)
-    {
-      uint4* d4 = reinterpret_cast<uint4*>(T.depth);
-      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-      for (uint32_t i = tid; i < blocks * 8u; i += NT) d4[i] = z;
-      for (uint32_t i = tid; i < blocks; i += NT) T.hiz[i] = 1;
-    }
+    // ---- clear (Rasterizer.cpp:107-121): HiZ := 1.  Depth is NOT touched here: a block whose
+    // HiZ is 1 is overwritten by its first update (Rasterizer.cpp:1271) and reads as zero in
+    // queries, so the zero fill of never-touched blocks is deferred to the end of the view and
+    // every depth byte is written to HBM once instead of twice.
+    for (uint32_t i = tid; i < blocks; i += NT) T.hiz[i] = 1;
     __syncthreads();
 
     uint32_t gateIdx = 0, quadsSubmitted = 0;
@@ -484,6 +484,15 @@ __global__ void __launch_bounds__(GW * 32, ORZ_THREADS_PER_SM / (GW * 32)) k_ren
       __syncthreads();  // depth/HiZ of this occluder visible to the whole group before the next gate
     }
     if (p.quadsSubmitted && tid == 0) p.quadsSubmitted[view] = quadsSubmitted;
+    if (p.exportDepth) {  // canonical depth for the caller: cleared blocks read as zero
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      for (uint32_t i = tid; i < blocks; i += NT)
+        if (T.hiz[i] == 1) {
+          uint4* d4 = reinterpret_cast<uint4*>(T.depth) + (size_t)i * 8u;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d4[k] = z;
+        }
+    }
     __syncthreads();  // s_view is rewritten by the next view
   }
 }
@@ -1056,6 +1065,7 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
     p.clipBits = (scene->nBoxes && b->clipBits) ? b->clipBits + v0 * bitWords : nullptr;
     p.gate = b->gate ? b->gate + v0 * nOcc : nullptr;
     p.quadsSubmitted = b->quadsSubmitted ? b->quadsSubmitted + v0 : nullptr;
+    p.exportDepth = ownTargets ? 0 : 1;
     if (ownTargets) {
       p.depth = (uint16_t*)ctx->d_scratch[4]; p.hiz = (uint16_t*)ctx->d_scratch[5];
       p.depthStride = blocks * 64; p.hizStride = hizStride;

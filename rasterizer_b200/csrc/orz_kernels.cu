@@ -116,6 +116,7 @@ __device__ __forceinline__ void raster_prim(const uint32_t* __restrict__ rec, co
   const uint32_t sh0 = (uint32_t)(wIdx & 1) * 16u + (rpar ? 0u : 4u) + (uint32_t)k2;  // mask bit of pixel 2w (Rasterizer.cpp:1257-1268)
   const uint32_t sh1 = sh0 + 8u;
   const bool convex = mode == kConvex;
+  const uint32_t selHi = (k2 & 2) ? 0xffffffffu : 0u, selOdd = (k2 & 1) ? 0xffffffffu : 0u;
   uint32_t* const depthWords = reinterpret_cast<uint32_t*>(T.depth) + lane;
 
   uint32_t rowMod = r0 % rowStride;  // (r0 + by) % rowStride, kept incrementally
@@ -161,10 +162,11 @@ __device__ __forceinline__ void raster_prim(const uint32_t* __restrict__ rec, co
               hitInRow = true;
               // max(cvtt(o), 0) for o < 63 or NaN: NaN and negatives give 0
               const uint32_t q = (uint32_t)__float2int_rz(fmaxf(o, 0.0f));
-              uint2 t = lut[slope | q];
-              t.x &= __shfl_xor_sync(kFull, t.x, 1); t.y &= __shfl_xor_sync(kFull, t.y, 1);
-              t.x &= __shfl_xor_sync(kFull, t.x, 2); t.y &= __shfl_xor_sync(kFull, t.y, 2);
-              mk = t;  // no empty-mask test on this path (Rasterizer.cpp:1186)
+              // A & B & C & D (Rasterizer.cpp:1184): the four edge masks sit in lanes e = 0..3 (replicated
+              // 8x), so a warp-wide AND reduction combines them in two REDUX instructions
+              const uint2 t = lut[slope | q];
+              mk.x = __reduce_and_sync(kFull, t.x);
+              mk.y = __reduce_and_sync(kFull, t.y);  // no empty-mask test on this path (Rasterizer.cpp:1186)
             } else {  // Rasterizer.cpp:1188-1239
               // min(max(cvtt(o), 0), 63): NaN and anything >= 2^31 convert to 0x80000000 -> 0
               const uint32_t q = o < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o, 0.0f), 63.0f)) : 0u;
@@ -183,9 +185,8 @@ __device__ __forceinline__ void raster_prim(const uint32_t* __restrict__ rec, co
               if ((mk.x | mk.y) == 0u) continue;
             }
             uint32_t* dptr = depthWords + (size_t)blk * 32u;
-            const bool merge = ((cleared >> j) & 1u) == 0u;  // Rasterizer.cpp:1271
             uint32_t old = 0u;
-            if (merge) old = *dptr;
+            if (((cleared >> j) & 1u) == 0u) old = *dptr;  // Rasterizer.cpp:1271-1278
             // ---- depth of this lane's two pixels, Rasterizer.cpp:1241-1254
             float a0 = dA, b0 = dB;
             if (upperHalf) { a0 = ORZ_FMA(dzdx, 0.5f, a0); b0 = ORZ_FMA(dzdx, 0.5f, b0); }
@@ -193,8 +194,10 @@ __device__ __forceinline__ void raster_prim(const uint32_t* __restrict__ rec, co
             const uint32_t v0 = pack16(a0) | (pack16(b0) << 16);  // row rpar
             const uint32_t v8 = pack16(a8) | (pack16(b8) << 16);  // row 8 + rpar
             const uint32_t mid = avg_u16x2(v0, v8);               // row 4 + rpar
-            const uint32_t quarter = avg_u16x2((k2 & 2) ? v8 : v0, mid);  // rows 2 + rpar / 6 + rpar
-            uint32_t val = k2 == 0 ? v0 : (k2 == 2 ? mid : quarter);
+            const uint32_t near8 = v0 ^ ((v0 ^ v8) & selHi);      // k2 >= 2 ? v8 : v0
+            const uint32_t quarter = avg_u16x2(near8, mid);       // rows 2 + rpar / 6 + rpar
+            const uint32_t even = v0 ^ ((v0 ^ mid) & selHi);      // k2 == 0 ? v0 : mid   (for even k2)
+            uint32_t val = even ^ ((even ^ quarter) & selOdd);    // odd k2 -> the quarter rows
             // ---- coverage of the two pixels, Rasterizer.cpp:1257-1268
             const uint32_t mw = upperHalf ? mk.y : mk.x;
             const uint32_t selMask = ((0u - ((mw >> sh0) & 1u)) & 0x0000ffffu) | ((0u - ((mw >> sh1) & 1u)) & 0xffff0000u);
@@ -329,6 +332,7 @@ struct FrameParams {
   uint32_t* viewCounter;
   uint32_t* viewCost;   // nViews: quads of the occluders that survive the frustum test (scheduling estimate)
   uint32_t* viewOrder;  // nViews: views sorted by descending cost (longest first), or NULL
+  uint32_t viewBase, groupViews;  // this launch handles sorted ranks [viewBase, viewBase + groupViews)
   int exportDepth;      // 1: the caller reads depth back -> zero-fill blocks that stayed cleared
 };
 
@@ -425,8 +429,8 @@ __global__ void __launch_bounds__(GW * 32, ORZ_THREADS_PER_SM / (GW * 32)) k_ren
   for (;;) {
     if (tid == 0) { s_view = atomicAdd(p.viewCounter, 1u); s_flag[0] = s_flag[1] = s_flag[2] = 0u; }
     __syncthreads();
-    if (s_view >= p.nViews) break;
-    const uint32_t view = p.viewOrder ? p.viewOrder[s_view] : s_view;
+    if (s_view >= p.groupViews) break;
+    const uint32_t view = p.viewOrder ? p.viewOrder[p.viewBase + s_view] : p.viewBase + s_view;
     T.depth = p.depth + (size_t)view * p.depthStride;
     T.hiz = p.hiz + (size_t)view * p.hizStride;
     const uint32_t* order = p.orders ? p.orders + (size_t)view * p.nOcc : p.orderBuf + (size_t)view * p.nOcc;
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(GW * 32, ORZ_THREADS_PER_SM / (GW * 32)) k_ren
 // queryVisibility for every (view, occludee box) on the finished buffers; Rasterizer.cpp:123-349
 __global__ void __launch_bounds__(256) k_query_views(const FrameParams p) {
   __shared__ ViewMatrices s_vm;
-  const uint32_t view = blockIdx.y, tid = threadIdx.x;
+  const uint32_t view = p.viewOrder ? p.viewOrder[p.viewBase + blockIdx.y] : p.viewBase + blockIdx.y, tid = threadIdx.x;
   if (tid < 32) reinterpret_cast<float*>(&s_vm)[tid] = reinterpret_cast<const float*>(p.vmBuf + view)[tid];
   __syncthreads();
   const RcpTable rt{p.rcp, p.rcpShift};
@@ -667,6 +671,9 @@ struct orz_context {
   void* d_scratch[8] = {nullptr};
   size_t scratchBytes[8] = {0};
   uint32_t* h_pinned = nullptr;  // small pinned mailbox for scalar results
+  static constexpr int kGroups = 4;          // sub-batches pipelined on auxiliary streams
+  cudaStream_t aux[kGroups] = {nullptr};
+  cudaEvent_t evFork = nullptr, evJoin[kGroups] = {nullptr};
   size_t arenaBudget = size_t(8) << 30;  // bytes of internal per-view depth+HiZ targets (views are chunked to fit)
 };
 struct orz_occluder {
@@ -716,6 +723,11 @@ extern "C" int orz_context_create(int device, orz_context** out) {
   ctx->numSMs = prop.multiProcessorCount;
   ctx->arenaBudget = std::min<size_t>(size_t(24) << 30, prop.totalGlobalMem / 6);
   ORZ_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ORZ_CUDA(cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
+  for (int g = 0; g < orz_context::kGroups; ++g) {
+    ORZ_CUDA(cudaStreamCreateWithFlags(&ctx->aux[g], cudaStreamNonBlocking));
+    ORZ_CUDA(cudaEventCreateWithFlags(&ctx->evJoin[g], cudaEventDisableTiming));
+  }
   ORZ_CUDA(cudaMalloc(&ctx->d_lut, 4096 * sizeof(uint2)));
   ORZ_CUDA(cudaMemcpy(ctx->d_lut, edge_mask_table(), 4096 * sizeof(uint2), cudaMemcpyHostToDevice));
   probe_host_rcp(ctx->h_rcp, ctx->rcpBits, ctx->rcpExact);
@@ -733,6 +745,8 @@ extern "C" void orz_context_destroy(orz_context* ctx) {
   for (auto& p : ctx->d_scratch) if (p) cudaFree(p);
   cudaFree(ctx->d_lut); cudaFree(ctx->d_rcp); cudaFree(ctx->d_counter);
   cudaFreeHost(ctx->h_pinned);
+  for (int g = 0; g < orz_context::kGroups; ++g) { cudaStreamSynchronize(ctx->aux[g]); cudaStreamDestroy(ctx->aux[g]); cudaEventDestroy(ctx->evJoin[g]); }
+  cudaEventDestroy(ctx->evFork);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1001,8 +1015,8 @@ extern "C" void orz_scene_destroy(orz_scene* s) {
 }
 
 template <int GW>
-static int launch_views(orz_context* ctx, const FrameParams& p, uint32_t grid) {
-  k_render_views<GW><<<grid, GW * 32, 0, ctx->stream>>>(p);
+static int launch_views(orz_context* ctx, const FrameParams& p, uint32_t grid, cudaStream_t st) {
+  k_render_views<GW><<<grid, GW * 32, 0, st>>>(p);
   ctx->launches++;
   ORZ_CUDA(cudaGetLastError());
   return ORZ_OK;
@@ -1022,7 +1036,13 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
   if ((b->depth != nullptr) != (b->hiz != nullptr)) return fail(ORZ_ERR_ARG, "depth and hiz outputs must be requested together");
   if (b->nViews == 0) return ORZ_OK;
   ORZ_CUDA(cudaSetDevice(ctx->device));
-  const int GW = ctx->groupWarps ? ctx->groupWarps : 4;
+  // warps per view: enough warps in total to fill the machine (few views -> more warps each)
+  int GW = ctx->groupWarps;
+  if (!GW) {
+    const uint32_t want = (uint32_t)ctx->numSMs * 110u / std::max<uint32_t>(b->nViews, 1u);  // ~16k warps on 148 SMs
+    GW = want >= 8 ? 8 : want >= 4 ? 4 : want >= 2 ? 2 : 1;
+    if (b->height < 512 && GW > 1) GW /= 2;  // few block rows: less row parallelism to hand out
+  }
   int perSM = 0;
   int e = GW == 1 ? occupancy_views<1>(&perSM) : GW == 2 ? occupancy_views<2>(&perSM) : GW == 4 ? occupancy_views<4>(&perSM) : occupancy_views<8>(&perSM);
   if (e) return e;
@@ -1076,7 +1096,6 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
     p.viewCounter = ctx->d_counter;
     p.viewCost = (uint32_t*)(prep + chunk * sizeof(ViewMatrices) + chunk * nOcc * 4 + chunk * nOcc * kFrontWords * 4);
     p.viewOrder = nv <= 16384u ? p.viewCost + chunk : nullptr;
-    ORZ_CUDA(cudaMemsetAsync(ctx->d_counter, 0, 4, ctx->stream));
     k_prepare_views<<<nv, 128, 0, ctx->stream>>>(p);
     ctx->launches++;
     ORZ_CUDA(cudaGetLastError());
@@ -1085,13 +1104,32 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
       ctx->launches++;
       ORZ_CUDA(cudaGetLastError());
     }
-    const uint32_t grid = std::min<uint32_t>(nv, (uint32_t)(ctx->numSMs * perSM));
-    e = GW == 1 ? launch_views<1>(ctx, p, grid) : GW == 2 ? launch_views<2>(ctx, p, grid) : GW == 4 ? launch_views<4>(ctx, p, grid) : launch_views<8>(ctx, p, grid);
-    if (e) return e;
-    if (p.visBits || p.clipBits) {
-      k_query_views<<<dim3((scene->nBoxes + 255) / 256, nv), 256, 0, ctx->stream>>>(p);
-      ctx->launches++;
-      ORZ_CUDA(cudaGetLastError());
+    // Sub-batches (by descending cost) on auxiliary streams: the query kernel of a finished
+    // sub-batch and the CTAs of the next one fill the SMs that the drain of the previous render
+    // kernel leaves idle.  Everything is fenced by events on the context stream.
+    const bool wantQuery = p.visBits || p.clipBits;
+    const int groups = (p.viewOrder && nv >= 64u) ? orz_context::kGroups : 1;
+    ORZ_CUDA(cudaMemsetAsync(ctx->d_counter, 0, 4 * orz_context::kGroups, ctx->stream));
+    if (groups > 1) ORZ_CUDA(cudaEventRecord(ctx->evFork, ctx->stream));
+    for (int g = 0; g < groups; ++g) {
+      cudaStream_t st = groups > 1 ? ctx->aux[g] : ctx->stream;
+      if (groups > 1) ORZ_CUDA(cudaStreamWaitEvent(st, ctx->evFork, 0));
+      FrameParams pg = p;
+      pg.viewBase = (uint32_t)((uint64_t)nv * g / groups);
+      pg.groupViews = (uint32_t)((uint64_t)nv * (g + 1) / groups) - pg.viewBase;
+      pg.viewCounter = ctx->d_counter + g;
+      const uint32_t grid = std::min<uint32_t>(pg.groupViews, (uint32_t)(ctx->numSMs * perSM));
+      e = GW == 1 ? launch_views<1>(ctx, pg, grid, st) : GW == 2 ? launch_views<2>(ctx, pg, grid, st) : GW == 4 ? launch_views<4>(ctx, pg, grid, st) : launch_views<8>(ctx, pg, grid, st);
+      if (e) return e;
+      if (wantQuery) {
+        k_query_views<<<dim3((scene->nBoxes + 255) / 256, pg.groupViews), 256, 0, st>>>(pg);
+        ctx->launches++;
+        ORZ_CUDA(cudaGetLastError());
+      }
+      if (groups > 1) {
+        ORZ_CUDA(cudaEventRecord(ctx->evJoin[g], st));
+        ORZ_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evJoin[g], 0));
+      }
     }
   }
   return ORZ_OK;

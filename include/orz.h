@@ -100,6 +100,8 @@ void orz_scene_destroy(orz_scene* scene);
 enum {
   ORZ_BATCH_NO_GATE = 1u,      /* submit every occluder, no queryVisibility gate (config 4 shape) */
   ORZ_BATCH_FORCE_CLIPPED = 2u, /* with NO_GATE: use rasterize<true> for every occluder */
+  ORZ_BATCH_WIDE = 8u,          /* with NO_GATE: force the one-warp-per-screen-row path that splits ONE view over the
+                                    whole GPU (chosen automatically for <= 8 views over >= 65536 quads) */
   ORZ_BATCH_TARGETS_ON_DEVICE = 4u /* orz_render_views only: depth / hiz are DEVICE pointers (the
                                       buffers stay resident in HBM; only bits and gates travel) */
 };

@@ -21,6 +21,7 @@ LIB_PATH = os.path.join(HERE, "librasterizer_b200.so")
 BATCH_NO_GATE = 1
 BATCH_FORCE_CLIPPED = 2
 BATCH_TARGETS_ON_DEVICE = 4
+BATCH_WIDE = 8
 
 _lib = None
 

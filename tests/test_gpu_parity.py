@@ -245,3 +245,40 @@ def test_against_reference_binary_on_this_host(ctx):
         assert np.array_equal(vis[v], (q & 1).astype(bool))
         assert np.array_equal(clip[v], (q & 2).astype(bool))
     r.close(); s.close(); sc.close()
+
+
+@pytest.mark.parametrize("name,size", [("castle", (1920, 1080)), ("castle", (3840, 2160)), ("soup", (3840, 2160))])
+def test_wide_single_view_path(ctx, lut, name, size):
+    """One view split over the whole GPU (config-4 path: ungated, rasterize<true>, one warp per
+    screen block-row walking globally set-up records) against the oracle."""
+    w, h = size
+    if name == "soup":
+        ps = wl.synthetic_soup(32768, cube=80.0)
+        baked = [api.bake(b, ps.ref_min, ps.ref_max) for b in ps.batches]
+        packed, centers = [b[0] for b in baked], np.stack([b[1] for b in baked])
+        sc = api.Scene(ctx, packed, ps.ref_min, ps.ref_max, np.stack([b[2] for b in baked]), np.stack([b[3] for b in baked]), centers, ps.quad_boxes()[::9])
+        boxes, ref_min, ref_max = ps.quad_boxes()[::9], ps.ref_min, ps.ref_max
+        c = ps.camera
+        mvps = np.stack([cam.view_projection(c["pos"], d, c["up"], c["fov"], w, h) for d in ((0, 0, 1), (0.6, -0.2, 0.7))])
+        poss = np.zeros((2, 3), np.float32)
+    else:
+        B = bundle(name)
+        packed, centers, boxes, ref_min, ref_max = B.packed, B.centers, B.boxes[::7], B.ps.ref_min, B.ps.ref_max
+        sc = B.scene(ctx, boxes)
+        mvps, poss = wl.camera_path(B.ps, 2, w, h)
+    orders = wl.orders_for(centers, poss)
+    flags = api.BATCH_NO_GATE | api.BATCH_FORCE_CLIPPED | api.BATCH_WIDE
+    out = sc.render_views(w, h, mvps, orders=orders, flags=flags, want=("vis", "depth", "hiz", "quads", "gate"))
+    out2 = sc.render_views(w, h, mvps, cam_pos=poss, flags=flags, want=("vis",))
+    vis = api.unpack_bits(out["vis"], len(boxes))
+    port = po.PortRasterizer(w, h, lut)
+    for v in range(2):
+        port.clear(); port.set_mvp(mvps[v])
+        for o in orders[v]:
+            port.rasterize(packed[o], ref_min, ref_max, True)
+        assert np.array_equal(out["hiz"][v], port.hiz())
+        assert np.array_equal(out["depth"][v], port.depth())
+        assert np.array_equal(vis[v], (port.query_boxes(boxes) & 1).astype(bool))
+        assert out["quads"][v] == sum(p.size // 4 for p in packed) and out["gate"][v].all()
+    assert np.array_equal(out2["vis"], out["vis"])
+    sc.close(); port.close()

@@ -33,6 +33,9 @@
 #include "orz_core.h"
 #include "orz_host.h"
 
+#ifndef ORZ_PREFETCH_LEVEL
+#define ORZ_PREFETCH_LEVEL 2  // cache level the depth prefetch targets (0 = off)
+#endif
 #ifndef ORZ_THREADS_PER_SM
 #define ORZ_THREADS_PER_SM 1024  // resident threads per SM the view-batch kernel is compiled for (register cap = 65536 / this)
 #endif
@@ -66,6 +69,14 @@ __device__ __forceinline__ void store_record(uint32_t* rec, const Prim& P) {
   for (int e = 0; e < 4; ++e) { rec[6 + e] = f2u(P.nx[e]); rec[10 + e] = f2u(P.ny[e]); rec[14 + e] = f2u(P.off[e]); }
   rec[18] = (P.slope[0] & 0xfc0u) | ((P.slope[1] & 0xfc0u) << 16);
   rec[19] = (P.slope[2] & 0xfc0u) | ((P.slope[3] & 0xfc0u) << 16);
+}
+
+__device__ __forceinline__ void prefetch_line(const void* p) {
+#if ORZ_PREFETCH_LEVEL == 1
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#elif ORZ_PREFETCH_LEVEL == 2
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
 }
 
 // avg_epu16 on two packed halves: (a + b + 1) >> 1 without overflow
@@ -153,6 +164,11 @@ __device__ __forceinline__ void raster_prim(const uint32_t* __restrict__ rec, co
           const uint32_t hv = (uint32_t)lane < m ? (uint32_t)T.hiz[L + s0 + lane] : 0xffffu;
           uint32_t cand = __ballot_sync(kFull, hv < maxZ);  // Rasterizer.cpp:1148-1152
           const uint32_t cleared = __ballot_sync(kFull, hv == 1u);
+          // One instruction pulls the stored depth of every candidate block of the segment towards
+          // the SM (lane j -> block j): the blocks are then visited one after the other, and
+          // without this each visit would expose a full HBM round trip (memory-level parallelism
+          // per warp would be 1).
+          if (hv < maxZ && hv != 1u) prefetch_line(depthWords + (size_t)(L + s0 + (uint32_t)lane) * 32u - lane);
           uint32_t pos = 0;
           while (cand) {
             const uint32_t j = (uint32_t)__ffs((int)cand) - 1u;
@@ -270,6 +286,41 @@ __device__ bool query2d_serial(const Target& T, uint32_t minX, uint32_t maxX, ui
     for (uint32_t bx = bx0; bx <= bx1; ++bx)
       if (query_block(T, bx, by, minX, maxX, minY, maxY, maxZ)) return true;
   return false;
+}
+
+// One box per lane, whole warp converged: small rectangles are walked by their own lane, large ones
+// (which would leave 31 lanes idle for hundreds of iterations) are taken one at a time by the whole
+// warp, 32 blocks per step with coalesced HiZ reads.  query2D is an OR over blocks, so the visiting
+// order does not matter.  Returns this lane's visibility.
+__device__ __forceinline__ bool query2d_warp(const Target& T, const BoxFront& f, const int lane) {
+  bool vis = false, big = false;
+  if (f.status == kBoxRect) {
+    const uint32_t nb = ((f.maxX >> 3) - (f.minX >> 3) + 1u) * ((f.maxY >> 3) - (f.minY >> 3) + 1u);
+    if (nb <= 6u) vis = query2d_serial(T, f.minX, f.maxX, f.minY, f.maxY, f.maxZ);
+    else big = true;
+  }
+  uint32_t pending = __ballot_sync(kFull, big);
+  while (pending) {
+    const int src = __ffs((int)pending) - 1;
+    pending &= pending - 1u;
+    const uint32_t minX = __shfl_sync(kFull, f.minX, src), maxX = __shfl_sync(kFull, f.maxX, src);
+    const uint32_t minY = __shfl_sync(kFull, f.minY, src), maxY = __shfl_sync(kFull, f.maxY, src);
+    const uint32_t maxZ = __shfl_sync(kFull, f.maxZ, src);
+    const uint32_t bx0 = minX >> 3, by0 = minY >> 3;
+    const uint32_t cols = (maxX >> 3) - bx0 + 1u, n = cols * ((maxY >> 3) - by0 + 1u);
+    bool found = false;
+    for (uint32_t base = 0; base < n; base += 32u) {
+      const uint32_t i = base + (uint32_t)lane;
+      bool hit = false;
+      if (i < n) {
+        const uint32_t ry = i / cols, rx = i - ry * cols;
+        hit = query_block(T, bx0 + rx, by0 + ry, minX, maxX, minY, maxY, maxZ);
+      }
+      if (__any_sync(kFull, hit)) { found = true; break; }
+    }
+    if (lane == src) vis = found;
+  }
+  return vis;
 }
 
 // all threads of a group share one rectangle (occluder gate); `flag` is a shared-memory word that
@@ -523,14 +574,16 @@ __global__ void __launch_bounds__(256) k_query_views(const FrameParams p) {
   T.depth = p.depth + (size_t)view * p.depthStride;
   T.hiz = p.hiz + (size_t)view * p.hizStride;
   const uint32_t i = blockIdx.x * blockDim.x + tid;
-  bool vis = false, clip = false;
+  BoxFront f;
+  f.status = kBoxCulled; f.minX = f.maxX = f.minY = f.maxY = f.maxZ = 0;
   if (i < p.nBoxes) {
     const float4 mn = p.boxes[2 * (size_t)i], mx = p.boxes[2 * (size_t)i + 1];
     const float bmn[4] = {mn.x, mn.y, mn.z, mn.w}, bmx[4] = {mx.x, mx.y, mx.z, mx.w};
-    const BoxFront f = box_front_half(s_vm, bmn, bmx, p.width, p.height, rt);
-    if (f.status == kBoxNearClip) { vis = true; clip = true; }
-    else if (f.status == kBoxRect) vis = query2d_serial(T, f.minX, f.maxX, f.minY, f.maxY, f.maxZ);
+    f = box_front_half(s_vm, bmn, bmx, p.width, p.height, rt);
   }
+  const bool clip = f.status == kBoxNearClip;
+  const bool seen = query2d_warp(T, f, (int)(tid & 31u));  // every lane must take part (warp collectives inside)
+  const bool vis = clip || seen;
   const uint32_t vb = __ballot_sync(kFull, vis), cb = __ballot_sync(kFull, clip);
   const uint32_t word = i >> 5;
   if ((tid & 31u) == 0 && word < p.bitWords) {
@@ -746,15 +799,16 @@ __global__ void k_debug_setup(const ViewMatrices vm, const uint4* quads, uint32_
 __global__ void k_query_boxes(const ViewMatrices vm, const float4* boxes, uint32_t n, Target T, const uint32_t* rcp, int rcpShift,
                               uint8_t* out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
   const RcpTable rt{rcp, rcpShift};
-  const float4 mn = boxes[2 * (size_t)i], mx = boxes[2 * (size_t)i + 1];
-  const float bmn[4] = {mn.x, mn.y, mn.z, mn.w}, bmx[4] = {mx.x, mx.y, mx.z, mx.w};
-  const BoxFront f = box_front_half(vm, bmn, bmx, T.width, T.height, rt);
-  uint8_t r = 0;
-  if (f.status == kBoxNearClip) r = 3;
-  else if (f.status == kBoxRect) r = query2d_serial(T, f.minX, f.maxX, f.minY, f.maxY, f.maxZ) ? 1 : 0;
-  out[i] = r;
+  BoxFront f;
+  f.status = kBoxCulled; f.minX = f.maxX = f.minY = f.maxY = f.maxZ = 0;
+  if (i < n) {
+    const float4 mn = boxes[2 * (size_t)i], mx = boxes[2 * (size_t)i + 1];
+    const float bmn[4] = {mn.x, mn.y, mn.z, mn.w}, bmx[4] = {mx.x, mx.y, mx.z, mx.w};
+    f = box_front_half(vm, bmn, bmx, T.width, T.height, rt);
+  }
+  const bool vis = query2d_warp(T, f, (int)(threadIdx.x & 31u));
+  if (i < n) out[i] = f.status == kBoxNearClip ? 3 : (vis ? 1 : 0);
 }
 
 __global__ void k_query2d(Target T, uint32_t minX, uint32_t maxX, uint32_t minY, uint32_t maxY, uint32_t maxZ, uint32_t* out) {

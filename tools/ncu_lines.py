@@ -28,7 +28,8 @@ for l in dis:
     m = re.match(r'\s*/\*([0-9a-f]{4,})\*/\s+(.*);', l)
     if m:
         line_of[int(m.group(1), 16)] = cur
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+kfilter = os.environ.get("NCU_KERNEL")
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + (["--kernel-name", "regex:" + kfilter] if kfilter else []), capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}

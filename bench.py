@@ -333,7 +333,7 @@ def run_ours(args):
                        "outputs": "depth+HiZ+visibility bits per view (HBM resident)" if with_targets else "visibility bits per view",
                        "l2": f"working set per step {n_views * (2 * w * h + 2 * blocks) / 1e6:.0f} MB of per-view depth+HiZ, larger than the 126 MB L2" if with_targets
                              else "L2 flushed by construction: every view clears and rewrites its scratch target",
-                       "group_warps": args.group_warps or 4, "parallelism": f"views sharded over {world} GPU(s), NCCL all-gather of bitmasks"},
+                       "group_warps": args.group_warps or "auto", "parallelism": f"views sharded over {world} GPU(s), NCCL all-gather of bitmasks"},
             "mquads_per_sec": quads_submitted * world / (kern / 1e3) / 1e6,
             "queries_per_sec": n_boxes * total_views / (kern / 1e3),
             "kernel_ms_per_step": kern, "step_ms": step_ms,
@@ -343,7 +343,11 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg, "kernel": "k_render_views", "note": "issue/latency bound by design (SURVEY 8d): HBM is not the limiter"},
+                         "algorithmic_bytes_per_launch": alg,
+                         "kernel": "one step = k_prepare_views + k_sort_views + 4 x (k_render_views<GW> + k_query_views), the four cost-sorted sub-batches overlapped on four streams; "
+                                   "duration = CUDA events around the step on the context stream",
+                         "traffic_note": (traffic or {}).get("note"),
+                         "note": "issue/latency bound by design (SURVEY 8d): HBM is not the limiter; ncu per-launch counters in profiles/"},
         }
         if not args.no_cpu_baseline and world == 1:
             sample = min(128, n_views)

@@ -148,10 +148,9 @@ def cpu_reference(ps, w, h, mvps, poss, n_threads, seconds, want_kind="reference
         return res
     # reference binary absent: fall back to the scalar port (much slower, single thread)
     from oracle import port_oracle as po
-    from rasterizer_b200 import api
 
     po.set_tables()
-    baked = [api.bake(b, ps.ref_min, ps.ref_max) for b in ps.batches]
+    baked = [po.bake(b, ps.ref_min, ps.ref_max) for b in ps.batches]
     packed = [b[0] for b in baked]
     centers, bmin, bmax = (np.stack([b[i] for b in baked]) for i in (1, 2, 3))
     boxes = ps.quad_boxes()

@@ -323,17 +323,29 @@ __device__ __forceinline__ bool query2d_warp(const Target& T, const BoxFront& f,
   return vis;
 }
 
-// all threads of a group share one rectangle (occluder gate); `flag` is a shared-memory word that
-// any finder sets so the others can stop early
+// all threads of a group share one rectangle (occluder gate): every warp takes 32 blocks per
+// step; `flag` is a shared-memory word a finder sets so the other warps can stop early (read and
+// written with atomics only -- the value is consumed after the group barrier that follows)
 __device__ __forceinline__ void query2d_coop(const Target& T, uint32_t minX, uint32_t maxX, uint32_t minY, uint32_t maxY,
-                                             uint32_t maxZ, uint32_t tid, uint32_t nThreads, volatile uint32_t* flag) {
+                                             uint32_t maxZ, uint32_t tid, uint32_t nThreads, uint32_t* flag) {
+  const uint32_t lane = tid & 31u;
   const uint32_t bx0 = minX >> 3, by0 = minY >> 3;
   const uint32_t cols = (maxX >> 3) - bx0 + 1u, rows = (maxY >> 3) - by0 + 1u;
   const uint32_t n = cols * rows;
-  for (uint32_t i = tid; i < n; i += nThreads) {
-    if (*flag) return;
-    const uint32_t ry = i / cols, rx = i - ry * cols;
-    if (query_block(T, bx0 + rx, by0 + ry, minX, maxX, minY, maxY, maxZ)) { *flag = 1u; return; }
+  for (uint32_t base = tid - lane; base < n; base += nThreads) {
+    uint32_t stop = 0u;
+    if (lane == 0) stop = atomicOr(flag, 0u);
+    if (__shfl_sync(kFull, stop, 0)) return;
+    const uint32_t i = base + lane;
+    bool hit = false;
+    if (i < n) {
+      const uint32_t ry = i / cols, rx = i - ry * cols;
+      hit = query_block(T, bx0 + rx, by0 + ry, minX, maxX, minY, maxY, maxZ);
+    }
+    if (__any_sync(kFull, hit)) {
+      if (lane == 0) atomicExch(flag, 1u);
+      return;
+    }
   }
 }
 
@@ -472,8 +484,9 @@ __global__ void __launch_bounds__(256) k_sort_views(const uint32_t* __restrict__
 template <int GW>
 __global__ void __launch_bounds__(GW * 32, ORZ_THREADS_PER_SM / (GW * 32)) k_render_views(const FrameParams p) {
   constexpr uint32_t NT = GW * 32;
-  __shared__ uint32_t s_recs[2][NT * kRecStride];
-  __shared__ uint32_t s_count[2][GW];
+  constexpr int kBufs = (NT * kRecStride * 4 * 2 > 44000) ? 1 : 2;  // 48 KB static shared memory limit
+  __shared__ uint32_t s_recs[kBufs][NT * kRecStride];
+  __shared__ uint32_t s_count[kBufs][GW];
   __shared__ uint32_t s_flag[3];
   __shared__ uint32_t s_view;
 
@@ -514,11 +527,11 @@ __global__ void __launch_bounds__(GW * 32, ORZ_THREADS_PER_SM / (GW * 32)) k_ren
         clipped = useGate ? true : forceClip;
       } else if (status == kBoxRect) {
         // ---- gate: query2D on the buffers as built so far (Main.cpp:195)
-        volatile uint32_t* flag = &s_flag[gateIdx % 3u];
+        uint32_t* flag = &s_flag[gateIdx % 3u];
         if (tid == 0) s_flag[(gateIdx + 1u) % 3u] = 0u;
         query2d_coop(T, fr[1], fr[2], fr[3], fr[4], fr[5], tid, NT, flag);
         __syncthreads();
-        visible = *flag != 0u;
+        visible = *flag != 0u;  // after the barrier: plain read
         ++gateIdx;
       }
       if (p.gate && tid == 0) p.gate[(size_t)view * p.nOcc + slot] = (uint8_t)((visible ? 1 : 0) | (clipped && useGate ? 2 : 0));
@@ -544,7 +557,8 @@ __global__ void __launch_bounds__(GW * 32, ORZ_THREADS_PER_SM / (GW * 32)) k_ren
           for (uint32_t i = 0; i < cnt; ++i)
             raster_prim<GW>(s_recs[buf] + ((uint32_t)w2 * 32u + i) * kRecStride, lane, (uint32_t)warp, GW, T, p.lut);
         }
-        buf ^= 1u;
+        if (kBufs == 2) buf ^= 1u;
+        else __syncthreads();  // single buffer: records are rewritten by the next chunk
       }
       __syncthreads();  // depth/HiZ of this occluder visible to the whole group before the next gate
     }
@@ -962,7 +976,7 @@ extern "C" int orz_context_synchronize(orz_context* ctx) {
 extern "C" void* orz_context_stream(orz_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" uint64_t orz_context_launch_count(orz_context* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int orz_context_set_group_warps(orz_context* ctx, int warps) {
-  if (warps != 0 && warps != 1 && warps != 2 && warps != 4 && warps != 8) return fail(ORZ_ERR_ARG, "group warps must be 0, 1, 2, 4 or 8");
+  if (warps != 0 && warps != 1 && warps != 2 && warps != 4 && warps != 8 && warps != 16) return fail(ORZ_ERR_ARG, "group warps must be 0, 1, 2, 4, 8 or 16");
   ctx->groupWarps = warps;
   return ORZ_OK;
 }
@@ -1249,7 +1263,7 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
     if (b->height < 512 && GW > 1) GW /= 2;  // few block rows: less row parallelism to hand out
   }
   int perSM = 0;
-  int e = GW == 1 ? occupancy_views<1>(&perSM) : GW == 2 ? occupancy_views<2>(&perSM) : GW == 4 ? occupancy_views<4>(&perSM) : occupancy_views<8>(&perSM);
+  int e = GW == 1 ? occupancy_views<1>(&perSM) : GW == 2 ? occupancy_views<2>(&perSM) : GW == 4 ? occupancy_views<4>(&perSM) : GW == 8 ? occupancy_views<8>(&perSM) : occupancy_views<16>(&perSM);
   if (e) return e;
   if (perSM < 1) perSM = 1;
   const size_t blocks = (size_t)(b->width / 8) * (b->height / 8);
@@ -1361,7 +1375,7 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
       pg.groupViews = (uint32_t)((uint64_t)nv * (g + 1) / groups) - pg.viewBase;
       pg.viewCounter = ctx->d_counter + g;
       const uint32_t grid = std::min<uint32_t>(pg.groupViews, (uint32_t)(ctx->numSMs * perSM));
-      e = GW == 1 ? launch_views<1>(ctx, pg, grid, st) : GW == 2 ? launch_views<2>(ctx, pg, grid, st) : GW == 4 ? launch_views<4>(ctx, pg, grid, st) : launch_views<8>(ctx, pg, grid, st);
+      e = GW == 1 ? launch_views<1>(ctx, pg, grid, st) : GW == 2 ? launch_views<2>(ctx, pg, grid, st) : GW == 4 ? launch_views<4>(ctx, pg, grid, st) : GW == 8 ? launch_views<8>(ctx, pg, grid, st) : launch_views<16>(ctx, pg, grid, st);
       if (e) return e;
       if (wantQuery) {
         k_query_views<<<dim3((scene->nBoxes + 255) / 256, pg.groupViews), 256, 0, st>>>(pg);

@@ -1,0 +1,24 @@
+"""Small workload for compute-sanitizer (memcheck / racecheck / synccheck): a few views of the
+synthetic city through every kernel of the view-batch path and the per-call path."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from rasterizer_b200 import api, workloads as wl, camera as cam
+
+ps = wl.synthetic_city(n_blocks=5)
+ctx = api.Context(0)
+sc = api.Scene.from_prepared(ctx, ps)
+w, h = 320, 184
+mvps, poss = wl.camera_path(ps, 6, w, h)
+for gw in (1, 4, 8):
+    ctx.set_group_warps(gw)
+    out = sc.render_views(w, h, mvps, cam_pos=poss, want=("vis", "clip", "gate", "depth", "hiz", "quads"))
+ctx.set_group_warps(0)
+out = sc.render_views(w, h, mvps[:2], cam_pos=poss[:2], flags=api.BATCH_NO_GATE | api.BATCH_FORCE_CLIPPED | api.BATCH_WIDE, want=("vis", "depth", "hiz"))
+r = api.Rasterizer(ctx, w, h)
+occs = [api.Occluder(ctx, p, ps.ref_min, ps.ref_max) for p in sc.packed_list[:6]]
+r.clear(); r.setModelViewProjection(mvps[0])
+for o in occs:
+    r.rasterize(o, False); r.rasterize(o, True)
+r.queryVisibility(sc.bounds_min[0], sc.bounds_max[0]); r.query_boxes(ps.quad_boxes()[:500]); r.readBackDepth(); r.download()
+print("sanitize workload done", int(out["hiz"].sum()))

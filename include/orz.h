@@ -127,7 +127,10 @@ int orz_render_views(orz_context* ctx, orz_scene* scene, const orz_view_batch* b
 int orz_render_views_device(orz_context* ctx, orz_scene* scene, const orz_view_batch* batch);
 /* kernels launched by the last render / rasterizer call on this context (for launch accounting) */
 uint64_t orz_context_launch_count(orz_context* ctx);
-/* tuning: warps cooperating on one view in the batch kernel (1, 2, 4, 8); 0 = default */
+/* tuning: bytes of the internal arena that holds per-view depth + HiZ when the caller does not ask
+ * for them (default min(24 GB, HBM/6)); larger batches are rendered in chunks of views */
+int orz_context_set_arena_bytes(orz_context* ctx, size_t bytes);
+/* tuning: warps cooperating on one view in the batch kernel (1, 2, 4, 8, 16); 0 = automatic */
 int orz_context_set_group_warps(orz_context* ctx, int warps);
 
 #ifdef __cplusplus

@@ -48,8 +48,12 @@ ORZ_HD float max_x86(float a, float b) { return a > b ? a : b; }
 ORZ_HD int32_t cvtt_x86(float f) {
   return (f >= -2147483648.0f && f < 2147483648.0f) ? (int32_t)f : (int32_t)0x80000000u;
 }
-// packDepthPremultiplied (Rasterizer.cpp:508-525): arithmetic >> 12 then unsigned saturation
+// packDepthPremultiplied (Rasterizer.cpp:508-525): arithmetic >> 12 then unsigned saturation.
+// A NaN depth (inf * 0 from a degenerate depth plane) is the NEGATIVE default NaN on x86 and packs
+// to 0; GPUs produce a positive canonical NaN, so NaN is mapped to -inf first (fmaxf returns the
+// non-NaN operand and leaves every other value unchanged).
 ORZ_HD uint32_t pack16(float f) {
+  f = fmaxf(f, u2f(0xff800000u));
   int32_t v = ((int32_t)f2u(f)) >> 12;
   return v < 0 ? 0u : (v > 65535 ? 65535u : (uint32_t)v);
 }
@@ -302,7 +306,9 @@ ORZ_HD BoxFront box_front_half(const ViewMatrices& vm, const float* mn, const fl
         o[i] = cen[i] + fxor(ext[i], f2u(p[i]) & kSign);
       }
       const float d = (p[0] * o[0] + p[1] * o[1]) + (p[2] * o[2] + p[3] * o[3]);
-      outside = outside || (f2u(d) & kSign);
+      // movemask of the distances (:161-164).  With finite inputs a NaN distance can only be a
+      // generated one (inf - inf, 0 * inf), which x86 creates with the sign bit set.
+      outside = outside || (f2u(d) & kSign) || (d != d);
     }
   if (outside) return out;
 

@@ -980,6 +980,11 @@ extern "C" int orz_context_set_group_warps(orz_context* ctx, int warps) {
   ctx->groupWarps = warps;
   return ORZ_OK;
 }
+extern "C" int orz_context_set_arena_bytes(orz_context* ctx, size_t bytes) {
+  if (!ctx) return fail(ORZ_ERR_ARG, "null context");
+  ctx->arenaBudget = bytes;
+  return ORZ_OK;
+}
 extern "C" int orz_context_set_rcp_table(orz_context* ctx, const uint32_t* table, int bits) {
   if (!ctx || !table || bits < 1 || bits > 23) return fail(ORZ_ERR_ARG, "orz_context_set_rcp_table: bad arguments");
   ORZ_CUDA(cudaSetDevice(ctx->device));

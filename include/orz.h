@@ -130,6 +130,9 @@ uint64_t orz_context_launch_count(orz_context* ctx);
 /* tuning: bytes of the internal arena that holds per-view depth + HiZ when the caller does not ask
  * for them (default min(24 GB, HBM/6)); larger batches are rendered in chunks of views */
 int orz_context_set_arena_bytes(orz_context* ctx, size_t bytes);
+/* tuning: block traversal mapping of the view-batch kernel: 1 = one warp per 8x8 block,
+ * 2 = one lane per block (up to 32 blocks of a primitive in flight per warp) */
+int orz_context_set_traversal(orz_context* ctx, int mapping);
 /* tuning: warps cooperating on one view in the batch kernel (1, 2, 4, 8, 16); 0 = automatic */
 int orz_context_set_group_warps(orz_context* ctx, int warps);
 

@@ -36,6 +36,9 @@
 #ifndef ORZ_PREFETCH_LEVEL
 #define ORZ_PREFETCH_LEVEL 2  // cache level the depth prefetch targets (0 = off)
 #endif
+#ifndef ORZ_THREADS_PER_SM_V2
+#define ORZ_THREADS_PER_SM_V2 512  // same, for the lane-per-block traversal (register cap 128)
+#endif
 #ifndef ORZ_THREADS_PER_SM
 #define ORZ_THREADS_PER_SM 1024  // resident threads per SM the view-batch kernel is compiled for (register cap = 65536 / this)
 #endif
@@ -245,6 +248,188 @@ __device__ __forceinline__ void raster_prim(const uint32_t* __restrict__ rec, co
   // HiZ is written by lane 0 and prefetched by other lanes for the next primitive: order the
   // warp's memory accesses (each block is visited at most once per primitive, so once is enough)
   __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Traversal, second mapping: ONE LANE PER 8x8 BLOCK (Rasterizer.cpp:1098-1292).
+//
+// The warp-per-block mapping above spends ~100 warp instructions per updated block, most of them
+// uniform bookkeeping replicated over 32 lanes, and keeps one block (one HBM round trip) in flight
+// per warp.  Here up to 32 blocks of one primitive are processed at once, one per lane: each lane
+// builds the whole 64-pixel block in registers (packed u16x2 arithmetic) and read-modify-writes its
+// own 128 bytes.  Blocks of one primitive are distinct, so no two lanes touch the same block; order
+// between primitives is kept because a warp finishes one primitive before it starts the next.
+//
+// The 12 iterated add chains still have to be stepped exactly as the reference does (y chain,
+// then x chain restarted at every row start).  Lanes 0-11 each own one chain (one FADD advances
+// all 12) and publish the value at every block position of the chunk through shared memory;
+// afterwards lane j picks up the 12 values of its own block.
+struct BlockWork {
+  uint32_t blk;    // linear block index
+  uint32_t hiz;    // HiZ read for the candidate test
+};
+
+// 64 pixels of one block for one lane: depth rows, coverage, merge, HiZ.  Rasterizer.cpp:1241-1290
+__device__ __forceinline__ void update_block_lane(const Target& T, const uint32_t blk, const bool merge, const uint2 mk,
+                                                  const float* __restrict__ smd /* this lane's 8 depth chain values, stride 32 */,
+                                                  const float dzdx, const float dzdy) {
+  uint32_t r0[2][4], r8[2][4];  // exact rows 0/1 and 8/9 as u16x2 words (pixels 2i, 2i+1)
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    float d[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d[k] = smd[(4 * rr + k) * 32];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a = d[(2 * i) & 3], b = d[(2 * i + 1) & 3];
+      if (i >= 2) { a = ORZ_FMA(dzdx, 0.5f, a); b = ORZ_FMA(dzdx, 0.5f, b); }  // depth1, Rasterizer.cpp:1243
+      r0[rr][i] = pack16(a) | (pack16(b) << 16);
+      r8[rr][i] = pack16(dzdy + a) | (pack16(dzdy + b) << 16);                 // depth8/9, :1244-1245
+    }
+  }
+  uint4* dp = reinterpret_cast<uint4*>(T.depth) + (size_t)blk * 8u;
+  uint32_t mnAcc = 0xffffffffu;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int y = 2 * k + rr;
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t mid = avg_u16x2(r0[rr][i], r8[rr][i]);            // rows 4/5 (:1252)
+        w[i] = k == 0 ? r0[rr][i] : k == 2 ? mid : k == 1 ? avg_u16x2(r0[rr][i], mid) : avg_u16x2(mid, r8[rr][i]);  // :1253-1254
+      }
+      // coverage of row y: pixel px <-> bit 8 px + ky (Rasterizer.cpp:1257-1268)
+      const int ky = (rr ? 0 : 4) + k;
+      const uint32_t lo = ((mk.x >> ky) & 0x01010101u) * 0xffu, hi = ((mk.y >> ky) & 0x01010101u) * 0xffu;
+      w[0] &= __byte_perm(lo, 0u, 0x1100); w[1] &= __byte_perm(lo, 0u, 0x3322);
+      w[2] &= __byte_perm(hi, 0u, 0x1100); w[3] &= __byte_perm(hi, 0u, 0x3322);
+      uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
+      if (merge) {  // Rasterizer.cpp:1271-1278
+        const uint4 old = dp[y];
+        v.x = __vmaxu2(v.x, old.x); v.y = __vmaxu2(v.y, old.y); v.z = __vmaxu2(v.z, old.z); v.w = __vmaxu2(v.w, old.w);
+      }
+      dp[y] = v;
+      mnAcc = __vminu2(mnAcc, __vminu2(__vminu2(v.x, v.y), __vminu2(v.z, v.w)));
+    }
+  T.hiz[blk] = (uint16_t)min(mnAcc & 0xffffu, mnAcc >> 16);  // Rasterizer.cpp:1287-1290
+}
+
+// coverage + update for the (up to 32) blocks whose chain values sit in `sm`; `pass` = HiZ candidate
+__device__ __forceinline__ void process_chunk_lanes(const Target& T, const uint2* __restrict__ lut, const float* __restrict__ sm,
+                                                    const int lane, const bool pass, const uint32_t blk, const uint32_t h,
+                                                    const uint32_t mode, const uint32_t slope01, const uint32_t slope23,
+                                                    const float dzdx, const float dzdy) {
+  bool upd = false;
+  uint2 mk = make_uint2(0u, 0u);
+  if (pass) {
+    const float o0 = sm[0 * 32 + lane], o1 = sm[1 * 32 + lane], o2 = sm[2 * 32 + lane], o3 = sm[3 * 32 + lane];
+    const uint32_t s0 = slope01 & 0xffffu, s1 = slope01 >> 16, s2 = slope23 & 0xffffu, s3 = slope23 >> 16;
+    if (mode == kConvex) {  // Rasterizer.cpp:1155-1187
+      if (!(o0 >= 63.0f || o1 >= 63.0f || o2 >= 63.0f || o3 >= 63.0f)) {
+        const uint2 A = lut[s0 | (uint32_t)__float2int_rz(fmaxf(o0, 0.0f))], B = lut[s1 | (uint32_t)__float2int_rz(fmaxf(o1, 0.0f))];
+        const uint2 C = lut[s2 | (uint32_t)__float2int_rz(fmaxf(o2, 0.0f))], D = lut[s3 | (uint32_t)__float2int_rz(fmaxf(o3, 0.0f))];
+        mk.x = (A.x & B.x) & (C.x & D.x); mk.y = (A.y & B.y) & (C.y & D.y);
+        upd = true;  // no empty-mask test on this path (Rasterizer.cpp:1186)
+      }
+    } else {  // Rasterizer.cpp:1188-1239
+      const uint32_t q0 = o0 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o0, 0.0f), 63.0f)) : 0u;
+      const uint32_t q1 = o1 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o1, 0.0f), 63.0f)) : 0u;
+      const uint32_t q2 = o2 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o2, 0.0f), 63.0f)) : 0u;
+      const uint32_t q3 = o3 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o3, 0.0f), 63.0f)) : 0u;
+      const uint2 A = lut[s0 | q0], B = lut[s1 | q1], C = lut[s2 | q2], D = lut[s3 | q3];
+      if (mode == kTriangle0) { mk.x = A.x & B.x & C.x; mk.y = A.y & B.y & C.y; }
+      else if (mode == kTriangle1) { mk.x = A.x & C.x & D.x; mk.y = A.y & C.y & D.y; }
+      else if (mode == kConcaveRight) { mk.x = (A.x | D.x) & (B.x & C.x); mk.y = (A.y | D.y) & (B.y & C.y); }
+      else if (mode == kConcaveCenter) { mk.x = (A.x & B.x) | (C.x & D.x); mk.y = (A.y & B.y) | (C.y & D.y); }
+      else { mk.x = (A.x & D.x) & (B.x | C.x); mk.y = (A.y & D.y) & (B.y | C.y); }
+      upd = (mk.x | mk.y) != 0u;
+    }
+  }
+  if (upd) update_block_lane(T, blk, h != 1u, mk, sm + 4 * 32 + lane, dzdx, dzdy);
+}
+
+template <int kStride>
+__device__ __forceinline__ void raster_prim_blocks(const uint32_t* __restrict__ rec, const int lane, const uint32_t rowPhase,
+                                                   const Target& T, const uint2* __restrict__ lut, float* __restrict__ sm) {
+  const uint32_t w0 = rec[0], w1 = rec[1], w2 = rec[2];
+  const uint32_t minX = w0 & 0xffffu, minY = w0 >> 16, W = w1 & 0xffffu, rangeY = w1 >> 16;
+  const uint32_t maxZ = w2 & 0xffffu, mode = w2 >> 16;
+  const uint32_t blocksX = T.blocksX;
+  const uint32_t b0 = ((uint32_t)kStride + rowPhase - minY % (uint32_t)kStride) % (uint32_t)kStride;  // first row of mine
+  if (b0 >= rangeY) return;
+  const uint32_t nRows = (rangeY - b0 + (uint32_t)kStride - 1u) / (uint32_t)kStride;
+  const float dzdx = u2f(rec[3]), dzdy = u2f(rec[4]);
+  const uint32_t slope01 = rec[18], slope23 = rec[19];
+
+  // chain lane c: 0-3 edge offsets, 4-11 the eight depth lanes (Rasterizer.cpp:1103-1112)
+  float cur = 0.0f, incX = 0.0f, incY = 0.0f;
+  if (lane < 4) { cur = u2f(rec[14 + lane]); incX = u2f(rec[6 + lane]); incY = u2f(rec[10 + lane]); }
+  else if (lane < 12) {
+    const int l = lane - 4;
+    const float s = -0.5f + 1.0f / 16.0f;
+    cur = ORZ_FMA(dzdx, s + 0.125f * (float)(l & 3), ORZ_FMA(dzdy, (l >> 2) ? s + 0.125f : s, u2f(rec[5])));
+    incX = dzdx; incY = dzdy;
+  }
+  for (uint32_t i = 0; i < b0; ++i) cur = cur + incY;  // Rasterizer.cpp:1130-1131
+
+  if (W <= 32u) {
+    // several rows per chunk: lane -> (row r of the chunk, column c)
+    const uint32_t rpc = 32u / W;
+    const uint32_t r = (uint32_t)lane / W, c = (uint32_t)lane - r * W;
+    for (uint32_t row0 = 0; row0 < nRows; row0 += rpc) {
+      const uint32_t rowsHere = min(rpc, nRows - row0);
+      const bool valid = r < rowsHere;
+      const uint32_t by = b0 + (uint32_t)kStride * (row0 + r);
+      const uint32_t blk = (minY + by) * blocksX + minX + c;
+      const uint32_t h = valid ? (uint32_t)T.hiz[blk] : 0xffffu;
+      const bool pass = h < maxZ;  // Rasterizer.cpp:1148-1152
+      if (!__any_sync(kFull, pass)) {
+        for (uint32_t i = 0; i < rowsHere * (uint32_t)kStride; ++i) cur = cur + incY;
+        continue;
+      }
+      uint32_t j = 0;
+      for (uint32_t rr = 0; rr < rowsHere; ++rr) {
+        float run = cur;  // x chain restarts at the row start (Rasterizer.cpp:1136-1137)
+        for (uint32_t bx = 0; bx < W; ++bx, ++j) {
+          if (lane < 12) sm[lane * 32 + j] = run;
+          run = incX + run;  // Rasterizer.cpp:1145-1146
+        }
+#pragma unroll
+        for (int k = 0; k < kStride; ++k) cur = cur + incY;
+      }
+      __syncwarp();
+      process_chunk_lanes(T, lut, sm, lane, pass, blk, h, mode, slope01, slope23, dzdx, dzdy);
+      __syncwarp();
+    }
+  } else {
+    for (uint32_t row = 0; row < nRows; ++row) {
+      const uint32_t by = b0 + (uint32_t)kStride * row;
+      const uint32_t rowBlk = (minY + by) * blocksX + minX;
+      float run = cur;
+      for (uint32_t s0 = 0; s0 < W; s0 += 32u) {
+        const uint32_t m = min(32u, W - s0);
+        const uint32_t blk = rowBlk + s0 + (uint32_t)lane;
+        const uint32_t h = (uint32_t)lane < m ? (uint32_t)T.hiz[blk] : 0xffffu;
+        const bool pass = h < maxZ;
+        if (!__any_sync(kFull, pass)) {
+          if (s0 + 32u < W) for (uint32_t i = 0; i < 32u; ++i) run = incX + run;
+          continue;
+        }
+        for (uint32_t j = 0; j < m; ++j) {
+          if (lane < 12) sm[lane * 32 + j] = run;
+          run = incX + run;
+        }
+        __syncwarp();
+        process_chunk_lanes(T, lut, sm, lane, pass, blk, h, mode, slope01, slope23, dzdx, dzdy);
+        __syncwarp();
+      }
+#pragma unroll
+      for (int k = 0; k < kStride; ++k) cur = cur + incY;
+    }
+  }
+  __syncwarp();  // order this primitive's depth/HiZ stores before the next primitive's loads (other lanes)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -481,12 +666,16 @@ __global__ void __launch_bounds__(256) k_sort_views(const uint32_t* __restrict__
   order[rank] = i;
 }
 
-template <int GW>
-__global__ void __launch_bounds__(GW * 32, ORZ_THREADS_PER_SM / (GW * 32)) k_render_views(const FrameParams p) {
+// kTrav selects the traversal mapping: 1 = one warp per block (raster_prim), 2 = one lane per block
+// (raster_prim_blocks; needs more registers, so it is compiled for fewer resident threads per SM)
+template <int GW, int kTrav>
+__global__ void __launch_bounds__(GW * 32, (kTrav == 2 ? ORZ_THREADS_PER_SM_V2 : ORZ_THREADS_PER_SM) / (GW * 32)) k_render_views(const FrameParams p) {
   constexpr uint32_t NT = GW * 32;
-  constexpr int kBufs = (NT * kRecStride * 4 * 2 > 44000) ? 1 : 2;  // 48 KB static shared memory limit
+  constexpr int kChainBytes = kTrav == 2 ? GW * 12 * 32 * 4 : 0;
+  constexpr int kBufs = (NT * kRecStride * 4 * 2 + kChainBytes > 44000) ? 1 : 2;  // 48 KB static shared memory limit
   __shared__ uint32_t s_recs[kBufs][NT * kRecStride];
   __shared__ uint32_t s_count[kBufs][GW];
+  __shared__ float s_chain[kTrav == 2 ? GW * 12 * 32 : 1];
   __shared__ uint32_t s_flag[3];
   __shared__ uint32_t s_view;
 
@@ -554,8 +743,11 @@ __global__ void __launch_bounds__(GW * 32, ORZ_THREADS_PER_SM / (GW * 32)) k_ren
 #pragma unroll 1
         for (int w2 = 0; w2 < GW; ++w2) {
           const uint32_t cnt = s_count[buf][w2];
-          for (uint32_t i = 0; i < cnt; ++i)
-            raster_prim<GW>(s_recs[buf] + ((uint32_t)w2 * 32u + i) * kRecStride, lane, (uint32_t)warp, GW, T, p.lut);
+          for (uint32_t i = 0; i < cnt; ++i) {
+            const uint32_t* rec = s_recs[buf] + ((uint32_t)w2 * 32u + i) * kRecStride;
+            if (kTrav == 2 && blocks <= 65536u) raster_prim_blocks<GW>(rec, lane, (uint32_t)warp, T, p.lut, s_chain + warp * (12 * 32));
+            else raster_prim<GW>(rec, lane, (uint32_t)warp, GW, T, p.lut);
+          }
         }
         if (kBufs == 2) buf ^= 1u;
         else __syncthreads();  // single buffer: records are rewritten by the next chunk
@@ -885,6 +1077,7 @@ struct orz_context {
   std::vector<uint32_t> h_rcp;
   uint64_t launches = 0;
   int groupWarps = 0;
+  int traversal = 2;  // 1 = warp per block, 2 = lane per block (default)
   // grow-only device scratch
   uint32_t* d_counter = nullptr;
   void* d_scratch[12] = {nullptr};
@@ -978,6 +1171,11 @@ extern "C" uint64_t orz_context_launch_count(orz_context* ctx) { return ctx ? ct
 extern "C" int orz_context_set_group_warps(orz_context* ctx, int warps) {
   if (warps != 0 && warps != 1 && warps != 2 && warps != 4 && warps != 8 && warps != 16) return fail(ORZ_ERR_ARG, "group warps must be 0, 1, 2, 4, 8 or 16");
   ctx->groupWarps = warps;
+  return ORZ_OK;
+}
+extern "C" int orz_context_set_traversal(orz_context* ctx, int mapping) {
+  if (!ctx || (mapping != 1 && mapping != 2)) return fail(ORZ_ERR_ARG, "traversal mapping must be 1 (warp per block) or 2 (lane per block)");
+  ctx->traversal = mapping;
   return ORZ_OK;
 }
 extern "C" int orz_context_set_arena_bytes(orz_context* ctx, size_t bytes) {
@@ -1238,17 +1436,51 @@ extern "C" void orz_scene_destroy(orz_scene* s) {
   delete s;
 }
 
-template <int GW>
-static int launch_views(orz_context* ctx, const FrameParams& p, uint32_t grid, cudaStream_t st) {
-  k_render_views<GW><<<grid, GW * 32, 0, st>>>(p);
+template <int GW, int kTrav>
+static int launch_views_t(orz_context* ctx, const FrameParams& p, uint32_t grid, cudaStream_t st) {
+  k_render_views<GW, kTrav><<<grid, GW * 32, 0, st>>>(p);
   ctx->launches++;
   ORZ_CUDA(cudaGetLastError());
   return ORZ_OK;
 }
-template <int GW>
-static int occupancy_views(int* perSM) {
-  ORZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(perSM, k_render_views<GW>, GW * 32, 0));
+template <int GW, int kTrav>
+static int occupancy_views_t(int* perSM) {
+  ORZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(perSM, k_render_views<GW, kTrav>, GW * 32, 0));
   return ORZ_OK;
+}
+static int launch_views(orz_context* ctx, int GW, int trav, const FrameParams& p, uint32_t grid, cudaStream_t st) {
+  if (trav == 2) {
+    switch (GW) {
+      case 1: return launch_views_t<1, 2>(ctx, p, grid, st);
+      case 2: return launch_views_t<2, 2>(ctx, p, grid, st);
+      case 4: return launch_views_t<4, 2>(ctx, p, grid, st);
+      default: return launch_views_t<8, 2>(ctx, p, grid, st);
+    }
+  }
+  switch (GW) {
+    case 1: return launch_views_t<1, 1>(ctx, p, grid, st);
+    case 2: return launch_views_t<2, 1>(ctx, p, grid, st);
+    case 4: return launch_views_t<4, 1>(ctx, p, grid, st);
+    case 8: return launch_views_t<8, 1>(ctx, p, grid, st);
+    default: return launch_views_t<16, 1>(ctx, p, grid, st);
+  }
+}
+static int occupancy_views(int GW, int trav, int* perSM) {
+  if (trav == 2) {
+    switch (GW) {
+      case 1: return occupancy_views_t<1, 2>(perSM);
+      case 2: return occupancy_views_t<2, 2>(perSM);
+      case 4: return occupancy_views_t<4, 2>(perSM);
+      default: return occupancy_views_t<8, 2>(perSM);
+    }
+  }
+  switch (GW) {
+    case 1: return occupancy_views_t<1, 1>(perSM);
+    case 2: return occupancy_views_t<2, 1>(perSM);
+    case 4: return occupancy_views_t<4, 1>(perSM);
+    case 8: return occupancy_views_t<8, 1>(perSM);
+    default: return occupancy_views_t<16, 1>(perSM);
+  }
 }
 
 // Device-pointer entry: three launches per chunk of views (prepare, render, query).  When the
@@ -1268,7 +1500,9 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
     if (b->height < 512 && GW > 1) GW /= 2;  // few block rows: less row parallelism to hand out
   }
   int perSM = 0;
-  int e = GW == 1 ? occupancy_views<1>(&perSM) : GW == 2 ? occupancy_views<2>(&perSM) : GW == 4 ? occupancy_views<4>(&perSM) : GW == 8 ? occupancy_views<8>(&perSM) : occupancy_views<16>(&perSM);
+  const int trav = ctx->traversal == 2 ? 2 : 1;
+  if (trav == 2 && GW > 8) GW = 8;
+  int e = occupancy_views(GW, trav, &perSM);
   if (e) return e;
   if (perSM < 1) perSM = 1;
   const size_t blocks = (size_t)(b->width / 8) * (b->height / 8);
@@ -1380,7 +1614,7 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
       pg.groupViews = (uint32_t)((uint64_t)nv * (g + 1) / groups) - pg.viewBase;
       pg.viewCounter = ctx->d_counter + g;
       const uint32_t grid = std::min<uint32_t>(pg.groupViews, (uint32_t)(ctx->numSMs * perSM));
-      e = GW == 1 ? launch_views<1>(ctx, pg, grid, st) : GW == 2 ? launch_views<2>(ctx, pg, grid, st) : GW == 4 ? launch_views<4>(ctx, pg, grid, st) : GW == 8 ? launch_views<8>(ctx, pg, grid, st) : launch_views<16>(ctx, pg, grid, st);
+      e = launch_views(ctx, GW, trav, pg, grid, st);
       if (e) return e;
       if (wantQuery) {
         k_query_views<<<dim3((scene->nBoxes + 255) / 256, pg.groupViews), 256, 0, st>>>(pg);

@@ -143,12 +143,15 @@ def test_per_call_api_frame(ctx, lut, name, size):
     r.close(); port.close()
 
 
+@pytest.mark.parametrize("trav", [1, 2])
 @pytest.mark.parametrize("gw", [1, 2, 4, 8])
 @pytest.mark.parametrize("name,size,nviews", [("city", (640, 360), 6), ("castle", (1920, 1080), 5), ("castle", (512, 256), 12)])
-def test_view_batch(ctx, lut, name, size, nviews, gw):
+def test_view_batch(ctx, lut, name, size, nviews, gw, trav):
+    """Both traversal mappings (1 = warp per block, 2 = lane per block) and every group size."""
     B = bundle(name)
     w, h = size
     ctx.set_group_warps(gw)
+    ctx.set_traversal(trav)
     mvps, poss = wl.camera_path(B.ps, nviews - 1, w, h) if size[0] >= 640 else wl.probe_views(B.ps, nviews - 1, w, h)
     m0, p0 = B.default_view(w, h)
     mvps = np.concatenate([m0[None], mvps]); poss = np.concatenate([p0[None], poss])
@@ -171,6 +174,7 @@ def test_view_batch(ctx, lut, name, size, nviews, gw):
     assert np.array_equal(out2["vis"], out["vis"])
     assert np.array_equal(out2["gate"], out["gate"])
     ctx.set_group_warps(0)
+    ctx.set_traversal(1)
     sc.close(); port.close()
 
 

@@ -39,11 +39,12 @@ def main():
         if targets: b.depth, b.hiz = d_depth.data_ptr(), d_hiz.data_ptr()
         return b
     res = {}
-    for gw in (1, 2, 4, 8):
-        ctx.set_group_warps(gw)
-        res[f"gw{gw}_full"] = timed(ctx, scene, mk(), stream)
-        res[f"gw{gw}_noqueries"] = timed(ctx, scene, mk(vis=False), stream)
-        res[f"gw{gw}_scratch_targets"] = timed(ctx, scene, mk(targets=False), stream)
+    for trav in (1, 2):
+        ctx.set_traversal(trav)
+        for gw in (1, 2, 4, 8):
+            ctx.set_group_warps(gw)
+            res[f"t{trav}_gw{gw}_full"] = timed(ctx, scene, mk(), stream)
+            res[f"t{trav}_gw{gw}_noqueries"] = timed(ctx, scene, mk(vis=False), stream)
     for k, v in res.items():
         print(f"{k:28s} {v:8.3f} ms  {nv / v * 1e3:10.0f} views/s")
     json.dump(res, open("gpurun_out/experiments.json", "w"))

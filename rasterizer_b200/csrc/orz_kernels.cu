@@ -72,6 +72,7 @@ __device__ __forceinline__ void store_record(uint32_t* rec, const Prim& P) {
   for (int e = 0; e < 4; ++e) { rec[6 + e] = f2u(P.nx[e]); rec[10 + e] = f2u(P.ny[e]); rec[14 + e] = f2u(P.off[e]); }
   rec[18] = (P.slope[0] & 0xfc0u) | ((P.slope[1] & 0xfc0u) << 16);
   rec[19] = (P.slope[2] & 0xfc0u) | ((P.slope[3] & 0xfc0u) << 16);
+  rec[20] = (1024u + (uint32_t)P.rangeX - 1u) / (uint32_t)P.rangeX;  // lane / rangeX == (lane * this) >> 10 for lane < 32
 }
 
 __device__ __forceinline__ void prefetch_line(const void* p) {
@@ -269,11 +270,23 @@ struct BlockWork {
   uint32_t hiz;    // HiZ read for the candidate test
 };
 
+// pack16 without the NaN guard: valid when the depth plane is finite (then no chain value can be NaN)
+__device__ __forceinline__ uint32_t pack16_finite(float f) {
+  const int32_t v = ((int32_t)f2u(f)) >> 12;
+  return (uint32_t)min(max(v, 0), 65535);
+}
+
 // 64 pixels of one block for one lane: depth rows, coverage, merge, HiZ.  Rasterizer.cpp:1241-1290
+template <bool kFinite>
 __device__ __forceinline__ void update_block_lane(const Target& T, const uint32_t blk, const bool merge, const uint2 mk,
                                                   const float* __restrict__ smd /* this lane's 8 depth chain values, stride 32 */,
                                                   const float dzdx, const float dzdy) {
-  uint32_t r0[2][4], r8[2][4];  // exact rows 0/1 and 8/9 as u16x2 words (pixels 2i, 2i+1)
+  uint4* dp = reinterpret_cast<uint4*>(T.depth) + (size_t)blk * 8u;
+  uint4 old[8];  // all eight rows are requested before any arithmetic: one HBM round trip per block
+#pragma unroll
+  for (int y = 0; y < 8; ++y) old[y] = merge ? dp[y] : make_uint4(0u, 0u, 0u, 0u);  // Rasterizer.cpp:1271-1278
+
+  uint32_t r0[2][4], r4[2][4], r8[2][4];  // rows 0/1, 4/5, 8/9 as u16x2 words (pixels 2i, 2i+1)
 #pragma unroll
   for (int rr = 0; rr < 2; ++rr) {
     float d[4];
@@ -283,11 +296,12 @@ __device__ __forceinline__ void update_block_lane(const Target& T, const uint32_
     for (int i = 0; i < 4; ++i) {
       float a = d[(2 * i) & 3], b = d[(2 * i + 1) & 3];
       if (i >= 2) { a = ORZ_FMA(dzdx, 0.5f, a); b = ORZ_FMA(dzdx, 0.5f, b); }  // depth1, Rasterizer.cpp:1243
-      r0[rr][i] = pack16(a) | (pack16(b) << 16);
-      r8[rr][i] = pack16(dzdy + a) | (pack16(dzdy + b) << 16);                 // depth8/9, :1244-1245
+      const float a8 = dzdy + a, b8 = dzdy + b;                                // depth8/9, :1244-1245
+      r0[rr][i] = kFinite ? pack16_finite(a) | (pack16_finite(b) << 16) : pack16(a) | (pack16(b) << 16);
+      r8[rr][i] = kFinite ? pack16_finite(a8) | (pack16_finite(b8) << 16) : pack16(a8) | (pack16(b8) << 16);
+      r4[rr][i] = avg_u16x2(r0[rr][i], r8[rr][i]);                             // :1252
     }
   }
-  uint4* dp = reinterpret_cast<uint4*>(T.depth) + (size_t)blk * 8u;
   uint32_t mnAcc = 0xffffffffu;
 #pragma unroll
   for (int k = 0; k < 4; ++k)
@@ -296,20 +310,16 @@ __device__ __forceinline__ void update_block_lane(const Target& T, const uint32_
       const int y = 2 * k + rr;
       uint32_t w[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t mid = avg_u16x2(r0[rr][i], r8[rr][i]);            // rows 4/5 (:1252)
-        w[i] = k == 0 ? r0[rr][i] : k == 2 ? mid : k == 1 ? avg_u16x2(r0[rr][i], mid) : avg_u16x2(mid, r8[rr][i]);  // :1253-1254
-      }
+      for (int i = 0; i < 4; ++i)
+        w[i] = k == 0 ? r0[rr][i] : k == 2 ? r4[rr][i] : k == 1 ? avg_u16x2(r0[rr][i], r4[rr][i]) : avg_u16x2(r4[rr][i], r8[rr][i]);  // :1253-1254
       // coverage of row y: pixel px <-> bit 8 px + ky (Rasterizer.cpp:1257-1268)
       const int ky = (rr ? 0 : 4) + k;
       const uint32_t lo = ((mk.x >> ky) & 0x01010101u) * 0xffu, hi = ((mk.y >> ky) & 0x01010101u) * 0xffu;
-      w[0] &= __byte_perm(lo, 0u, 0x1100); w[1] &= __byte_perm(lo, 0u, 0x3322);
-      w[2] &= __byte_perm(hi, 0u, 0x1100); w[3] &= __byte_perm(hi, 0u, 0x3322);
-      uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
-      if (merge) {  // Rasterizer.cpp:1271-1278
-        const uint4 old = dp[y];
-        v.x = __vmaxu2(v.x, old.x); v.y = __vmaxu2(v.y, old.y); v.z = __vmaxu2(v.z, old.z); v.w = __vmaxu2(v.w, old.w);
-      }
+      uint4 v;
+      v.x = __vmaxu2(w[0] & __byte_perm(lo, 0u, 0x1100), old[y].x);
+      v.y = __vmaxu2(w[1] & __byte_perm(lo, 0u, 0x3322), old[y].y);
+      v.z = __vmaxu2(w[2] & __byte_perm(hi, 0u, 0x1100), old[y].z);
+      v.w = __vmaxu2(w[3] & __byte_perm(hi, 0u, 0x3322), old[y].w);
       dp[y] = v;
       mnAcc = __vminu2(mnAcc, __vminu2(__vminu2(v.x, v.y), __vminu2(v.z, v.w)));
     }
@@ -320,7 +330,7 @@ __device__ __forceinline__ void update_block_lane(const Target& T, const uint32_
 __device__ __forceinline__ void process_chunk_lanes(const Target& T, const uint2* __restrict__ lut, const float* __restrict__ sm,
                                                     const int lane, const bool pass, const uint32_t blk, const uint32_t h,
                                                     const uint32_t mode, const uint32_t slope01, const uint32_t slope23,
-                                                    const float dzdx, const float dzdy) {
+                                                    const float dzdx, const float dzdy, const bool finitePlane) {
   bool upd = false;
   uint2 mk = make_uint2(0u, 0u);
   if (pass) {
@@ -347,7 +357,10 @@ __device__ __forceinline__ void process_chunk_lanes(const Target& T, const uint2
       upd = (mk.x | mk.y) != 0u;
     }
   }
-  if (upd) update_block_lane(T, blk, h != 1u, mk, sm + 4 * 32 + lane, dzdx, dzdy);
+  if (upd) {
+    if (finitePlane) update_block_lane<true>(T, blk, h != 1u, mk, sm + 4 * 32 + lane, dzdx, dzdy);
+    else update_block_lane<false>(T, blk, h != 1u, mk, sm + 4 * 32 + lane, dzdx, dzdy);
+  }
 }
 
 template <int kStride>
@@ -362,6 +375,9 @@ __device__ __forceinline__ void raster_prim_blocks(const uint32_t* __restrict__ 
   const uint32_t nRows = (rangeY - b0 + (uint32_t)kStride - 1u) / (uint32_t)kStride;
   const float dzdx = u2f(rec[3]), dzdy = u2f(rec[4]);
   const uint32_t slope01 = rec[18], slope23 = rec[19];
+  // a finite depth plane cannot produce NaN depths (sums of finite terms overflow to inf at worst)
+  const bool finitePlane = ((rec[3] & 0x7f800000u) != 0x7f800000u) && ((rec[4] & 0x7f800000u) != 0x7f800000u) &&
+                           ((rec[5] & 0x7f800000u) != 0x7f800000u);
 
   // chain lane c: 0-3 edge offsets, 4-11 the eight depth lanes (Rasterizer.cpp:1103-1112)
   float cur = 0.0f, incX = 0.0f, incY = 0.0f;
@@ -376,8 +392,9 @@ __device__ __forceinline__ void raster_prim_blocks(const uint32_t* __restrict__ 
 
   if (W <= 32u) {
     // several rows per chunk: lane -> (row r of the chunk, column c)
-    const uint32_t rpc = 32u / W;
-    const uint32_t r = (uint32_t)lane / W, c = (uint32_t)lane - r * W;
+    const uint32_t magic = rec[20];  // ceil(1024 / W), exact for lane < 32 (stored by store_record)
+    const uint32_t rpc = (32u * magic) >> 10;  // == 32 / W for every W <= 32
+    const uint32_t r = ((uint32_t)lane * magic) >> 10, c = (uint32_t)lane - r * W;
     for (uint32_t row0 = 0; row0 < nRows; row0 += rpc) {
       const uint32_t rowsHere = min(rpc, nRows - row0);
       const bool valid = r < rowsHere;
@@ -392,6 +409,7 @@ __device__ __forceinline__ void raster_prim_blocks(const uint32_t* __restrict__ 
       uint32_t j = 0;
       for (uint32_t rr = 0; rr < rowsHere; ++rr) {
         float run = cur;  // x chain restarts at the row start (Rasterizer.cpp:1136-1137)
+#pragma unroll 4
         for (uint32_t bx = 0; bx < W; ++bx, ++j) {
           if (lane < 12) sm[lane * 32 + j] = run;
           run = incX + run;  // Rasterizer.cpp:1145-1146
@@ -400,7 +418,7 @@ __device__ __forceinline__ void raster_prim_blocks(const uint32_t* __restrict__ 
         for (int k = 0; k < kStride; ++k) cur = cur + incY;
       }
       __syncwarp();
-      process_chunk_lanes(T, lut, sm, lane, pass, blk, h, mode, slope01, slope23, dzdx, dzdy);
+      process_chunk_lanes(T, lut, sm, lane, pass, blk, h, mode, slope01, slope23, dzdx, dzdy, finitePlane);
       __syncwarp();
     }
   } else {
@@ -417,12 +435,13 @@ __device__ __forceinline__ void raster_prim_blocks(const uint32_t* __restrict__ 
           if (s0 + 32u < W) for (uint32_t i = 0; i < 32u; ++i) run = incX + run;
           continue;
         }
+#pragma unroll 4
         for (uint32_t j = 0; j < m; ++j) {
           if (lane < 12) sm[lane * 32 + j] = run;
           run = incX + run;
         }
         __syncwarp();
-        process_chunk_lanes(T, lut, sm, lane, pass, blk, h, mode, slope01, slope23, dzdx, dzdy);
+        process_chunk_lanes(T, lut, sm, lane, pass, blk, h, mode, slope01, slope23, dzdx, dzdy, finitePlane);
         __syncwarp();
       }
 #pragma unroll
@@ -840,7 +859,7 @@ __global__ void __launch_bounds__(1024) k_slot_prefix(const FrameParams p, uint3
   }
 }
 
-constexpr int kWideRecWords = 20;
+constexpr int kWideRecWords = 21;  // same record as store_record writes (20 words + the division magic)
 __global__ void __launch_bounds__(256) k_setup_wide(const FrameParams p, uint32_t view, const uint32_t* __restrict__ slotStart,
                                                      uint32_t totalQuads, uint32_t* __restrict__ recs, uint32_t* __restrict__ chunkCount,
                                                      uint32_t* __restrict__ chunkRows) {
@@ -1495,8 +1514,13 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
   // warps per view: enough warps in total to fill the machine (few views -> more warps each)
   int GW = ctx->groupWarps;
   if (!GW) {
-    const uint32_t want = (uint32_t)ctx->numSMs * 110u / std::max<uint32_t>(b->nViews, 1u);  // ~16k warps on 148 SMs
-    GW = want >= 8 ? 8 : want >= 4 ? 4 : want >= 2 ? 2 : 1;
+    if (ctx->traversal == 2) {  // lane-per-block: fewer, fuller warps (measured on Castle 1080p, 1k-4k views)
+      const uint32_t want = (uint32_t)ctx->numSMs * 60u / std::max<uint32_t>(b->nViews, 1u);
+      GW = want >= 16 ? 8 : want >= 6 ? 4 : want >= 2 ? 2 : 1;
+    } else {
+      const uint32_t want = (uint32_t)ctx->numSMs * 110u / std::max<uint32_t>(b->nViews, 1u);  // ~16k warps on 148 SMs
+      GW = want >= 8 ? 8 : want >= 4 ? 4 : want >= 2 ? 2 : 1;
+    }
     if (b->height < 512 && GW > 1) GW /= 2;  // few block rows: less row parallelism to hand out
   }
   int perSM = 0;

@@ -395,12 +395,15 @@ __device__ __forceinline__ void raster_prim_blocks(const uint32_t* __restrict__ 
     const uint32_t magic = rec[20];  // ceil(1024 / W), exact for lane < 32 (stored by store_record)
     const uint32_t rpc = (32u * magic) >> 10;  // == 32 / W for every W <= 32
     const uint32_t r = ((uint32_t)lane * magic) >> 10, c = (uint32_t)lane - r * W;
+    // HiZ of the next chunk is requested while the current one is processed
+    const uint32_t blk0 = (minY + b0 + (uint32_t)kStride * r) * blocksX + minX + c;
+    const uint32_t blkStep = (uint32_t)kStride * rpc * blocksX;
+    uint32_t hNext = r < min(rpc, nRows) ? (uint32_t)T.hiz[blk0] : 0xffffu;
     for (uint32_t row0 = 0; row0 < nRows; row0 += rpc) {
       const uint32_t rowsHere = min(rpc, nRows - row0);
-      const bool valid = r < rowsHere;
-      const uint32_t by = b0 + (uint32_t)kStride * (row0 + r);
-      const uint32_t blk = (minY + by) * blocksX + minX + c;
-      const uint32_t h = valid ? (uint32_t)T.hiz[blk] : 0xffffu;
+      const uint32_t blk = blk0 + (row0 / rpc) * blkStep;
+      const uint32_t h = hNext;
+      if (row0 + rpc < nRows) hNext = r < min(rpc, nRows - row0 - rpc) ? (uint32_t)T.hiz[blk + blkStep] : 0xffffu;
       const bool pass = h < maxZ;  // Rasterizer.cpp:1148-1152
       if (!__any_sync(kFull, pass)) {
         for (uint32_t i = 0; i < rowsHere * (uint32_t)kStride; ++i) cur = cur + incY;
@@ -512,12 +515,15 @@ __device__ __forceinline__ bool query2d_warp(const Target& T, const BoxFront& f,
     const uint32_t maxZ = __shfl_sync(kFull, f.maxZ, src);
     const uint32_t bx0 = minX >> 3, by0 = minY >> 3;
     const uint32_t cols = (maxX >> 3) - bx0 + 1u, n = cols * ((maxY >> 3) - by0 + 1u);
+    const uint32_t magic = (65536u + cols - 1u) / cols;  // i / cols ~ (i * magic) >> 16, at most one too large (i < 65536)
     bool found = false;
     for (uint32_t base = 0; base < n; base += 32u) {
       const uint32_t i = base + (uint32_t)lane;
       bool hit = false;
       if (i < n) {
-        const uint32_t ry = i / cols, rx = i - ry * cols;
+        uint32_t ry = n <= 65536u ? (i * magic) >> 16 : i / cols;
+        if (ry * cols > i) --ry;
+        const uint32_t rx = i - ry * cols;
         hit = query_block(T, bx0 + rx, by0 + ry, minX, maxX, minY, maxY, maxZ);
       }
       if (__any_sync(kFull, hit)) { found = true; break; }

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from rasterizer_b200 import api, workloads as wl
 
-def timed(ctx, scene, batch, stream, reps=3):
+def timed(ctx, scene, batch, stream, reps=10):
     for _ in range(2):
         scene.render_views_raw(batch, device=True)
     torch.cuda.synchronize()

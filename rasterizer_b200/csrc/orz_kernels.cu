@@ -36,6 +36,9 @@
 #ifndef ORZ_PREFETCH_LEVEL
 #define ORZ_PREFETCH_LEVEL 2  // cache level the depth prefetch targets (0 = off)
 #endif
+#ifndef ORZ_V2_PRELOAD
+#define ORZ_V2_PRELOAD 1  // lane-per-block update: 1 = load all 8 rows up front (32 registers), 0 = L1 prefetch + row-wise loads
+#endif
 #ifndef ORZ_THREADS_PER_SM_V2
 #define ORZ_THREADS_PER_SM_V2 512  // same, for the lane-per-block traversal (register cap 128)
 #endif
@@ -82,6 +85,8 @@ __device__ __forceinline__ void prefetch_line(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 #endif
 }
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // avg_epu16 on two packed halves: (a + b + 1) >> 1 without overflow
 __device__ __forceinline__ uint32_t avg_u16x2(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) >> 1) & 0x7fff7fffu); }
@@ -282,9 +287,11 @@ __device__ __forceinline__ void update_block_lane(const Target& T, const uint32_
                                                   const float* __restrict__ smd /* this lane's 8 depth chain values, stride 32 */,
                                                   const float dzdx, const float dzdy) {
   uint4* dp = reinterpret_cast<uint4*>(T.depth) + (size_t)blk * 8u;
+#if ORZ_V2_PRELOAD
   uint4 old[8];  // all eight rows are requested before any arithmetic: one HBM round trip per block
 #pragma unroll
   for (int y = 0; y < 8; ++y) old[y] = merge ? dp[y] : make_uint4(0u, 0u, 0u, 0u);  // Rasterizer.cpp:1271-1278
+#endif
 
   uint32_t r0[2][4], r4[2][4], r8[2][4];  // rows 0/1, 4/5, 8/9 as u16x2 words (pixels 2i, 2i+1)
 #pragma unroll
@@ -315,11 +322,16 @@ __device__ __forceinline__ void update_block_lane(const Target& T, const uint32_
       // coverage of row y: pixel px <-> bit 8 px + ky (Rasterizer.cpp:1257-1268)
       const int ky = (rr ? 0 : 4) + k;
       const uint32_t lo = ((mk.x >> ky) & 0x01010101u) * 0xffu, hi = ((mk.y >> ky) & 0x01010101u) * 0xffu;
+#if ORZ_V2_PRELOAD
+      const uint4 o = old[y];
+#else
+      const uint4 o = merge ? dp[y] : make_uint4(0u, 0u, 0u, 0u);  // the line was prefetched when the block passed HiZ
+#endif
       uint4 v;
-      v.x = __vmaxu2(w[0] & __byte_perm(lo, 0u, 0x1100), old[y].x);
-      v.y = __vmaxu2(w[1] & __byte_perm(lo, 0u, 0x3322), old[y].y);
-      v.z = __vmaxu2(w[2] & __byte_perm(hi, 0u, 0x1100), old[y].z);
-      v.w = __vmaxu2(w[3] & __byte_perm(hi, 0u, 0x3322), old[y].w);
+      v.x = __vmaxu2(w[0] & __byte_perm(lo, 0u, 0x1100), o.x);
+      v.y = __vmaxu2(w[1] & __byte_perm(lo, 0u, 0x3322), o.y);
+      v.z = __vmaxu2(w[2] & __byte_perm(hi, 0u, 0x1100), o.z);
+      v.w = __vmaxu2(w[3] & __byte_perm(hi, 0u, 0x3322), o.w);
       dp[y] = v;
       mnAcc = __vminu2(mnAcc, __vminu2(__vminu2(v.x, v.y), __vminu2(v.z, v.w)));
     }
@@ -409,6 +421,9 @@ __device__ __forceinline__ void raster_prim_blocks(const uint32_t* __restrict__ 
         for (uint32_t i = 0; i < rowsHere * (uint32_t)kStride; ++i) cur = cur + incY;
         continue;
       }
+#if !ORZ_V2_PRELOAD
+      if (pass && h != 1u) prefetch_l1(T.depth + (size_t)blk * 64u);  // one 128 B line = the whole block
+#endif
       uint32_t j = 0;
       for (uint32_t rr = 0; rr < rowsHere; ++rr) {
         float run = cur;  // x chain restarts at the row start (Rasterizer.cpp:1136-1137)
@@ -438,6 +453,9 @@ __device__ __forceinline__ void raster_prim_blocks(const uint32_t* __restrict__ 
           if (s0 + 32u < W) for (uint32_t i = 0; i < 32u; ++i) run = incX + run;
           continue;
         }
+#if !ORZ_V2_PRELOAD
+        if (pass && h != 1u) prefetch_l1(T.depth + (size_t)blk * 64u);
+#endif
 #pragma unroll 4
         for (uint32_t j = 0; j < m; ++j) {
           if (lane < 12) sm[lane * 32 + j] = run;

@@ -709,16 +709,23 @@ __global__ void __launch_bounds__(256) k_sort_views(const uint32_t* __restrict__
   order[rank] = i;
 }
 
+template <int GW, int kTrav>
+struct FrameSmem {
+  static constexpr int kBufs = GW >= 16 ? 1 : 2;  // record buffers (double buffering saves one barrier per chunk)
+  static constexpr size_t kBytes = (size_t)kBufs * GW * 32 * kRecStride * 4 + (kTrav == 2 ? (size_t)GW * 12 * 32 * 4 : 0);
+};
+
 // kTrav selects the traversal mapping: 1 = one warp per block (raster_prim), 2 = one lane per block
 // (raster_prim_blocks; needs more registers, so it is compiled for fewer resident threads per SM)
 template <int GW, int kTrav>
 __global__ void __launch_bounds__(GW * 32, (kTrav == 2 ? ORZ_THREADS_PER_SM_V2 : ORZ_THREADS_PER_SM) / (GW * 32)) k_render_views(const FrameParams p) {
   constexpr uint32_t NT = GW * 32;
-  constexpr int kChainBytes = kTrav == 2 ? GW * 12 * 32 * 4 : 0;
-  constexpr int kBufs = (NT * kRecStride * 4 * 2 + kChainBytes > 44000) ? 1 : 2;  // 48 KB static shared memory limit
-  __shared__ uint32_t s_recs[kBufs][NT * kRecStride];
+  // dynamic shared memory (may exceed the 48 KB static limit): [2][NT][21] records, then [GW][12][32] chain slots
+  constexpr int kBufs = FrameSmem<GW, kTrav>::kBufs;
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  uint32_t (*s_recs)[NT * kRecStride] = reinterpret_cast<uint32_t (*)[NT * kRecStride]>(s_dyn);
+  float* s_chain = reinterpret_cast<float*>(s_dyn + kBufs * NT * kRecStride);
   __shared__ uint32_t s_count[kBufs][GW];
-  __shared__ float s_chain[kTrav == 2 ? GW * 12 * 32 : 1];
   __shared__ uint32_t s_flag[3];
   __shared__ uint32_t s_view;
 
@@ -1481,14 +1488,20 @@ extern "C" void orz_scene_destroy(orz_scene* s) {
 
 template <int GW, int kTrav>
 static int launch_views_t(orz_context* ctx, const FrameParams& p, uint32_t grid, cudaStream_t st) {
-  k_render_views<GW, kTrav><<<grid, GW * 32, 0, st>>>(p);
+  static bool configured[64] = {false};
+  if (!configured[ctx->device & 63]) {
+    ORZ_CUDA(cudaFuncSetAttribute(k_render_views<GW, kTrav>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FrameSmem<GW, kTrav>::kBytes));
+    configured[ctx->device & 63] = true;
+  }
+  k_render_views<GW, kTrav><<<grid, GW * 32, FrameSmem<GW, kTrav>::kBytes, st>>>(p);
   ctx->launches++;
   ORZ_CUDA(cudaGetLastError());
   return ORZ_OK;
 }
 template <int GW, int kTrav>
 static int occupancy_views_t(int* perSM) {
-  ORZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(perSM, k_render_views<GW, kTrav>, GW * 32, 0));
+  ORZ_CUDA(cudaFuncSetAttribute(k_render_views<GW, kTrav>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FrameSmem<GW, kTrav>::kBytes));
+  ORZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(perSM, k_render_views<GW, kTrav>, GW * 32, FrameSmem<GW, kTrav>::kBytes));
   return ORZ_OK;
 }
 static int launch_views(orz_context* ctx, int GW, int trav, const FrameParams& p, uint32_t grid, cudaStream_t st) {

@@ -73,6 +73,24 @@ ORZ_HD float rcp_x86(float x, const RcpTable& t) {
   return re <= 0 ? u2f(s) : u2f(s | ((uint32_t)re << 23) | (b & 0x7fffffu));
 }
 
+// rsqrtps model (VectorMath.h:20-23 uses it in normalize): x = 2^(2k+p) * 1.m ->
+// 2^-k * table[p][m >> shift]; table probed on the host over [1, 4) (orz_host.cpp).  Zero and
+// denormals give +-inf, negative inputs the default NaN.
+struct RsqrtTable {
+  const uint32_t* base;  // [2][1 << bits]
+  int bits;
+};
+ORZ_HD float rsqrt_x86(float x, const RsqrtTable& t) {
+  const uint32_t in = f2u(x), e = (in >> 23) & 0xffu, m = in & 0x7fffffu;
+  if (e == 255) return m ? u2f(in | 0x00400000u) : ((in & kSign) ? u2f(0xffc00000u) : 0.0f);
+  if (e == 0) return u2f((in & kSign) | 0x7f800000u);
+  if (in & kSign) return u2f(0xffc00000u);
+  const int32_t ue = (int32_t)e - 127, p = ue & 1, k = (ue - p) / 2;
+  const uint32_t b = t.base[((uint32_t)p << t.bits) + (m >> (23 - t.bits))];
+  const int32_t re = (int32_t)((b >> 23) & 0xffu) - k;
+  return u2f(((uint32_t)re << 23) | (b & 0x7fffffu));
+}
+
 // Primitive modes, numbering of Rasterizer.cpp:19-28 (ordered by frequency)
 enum : uint32_t { kCulled = 0, kTriangle0, kTriangle1, kConcaveRight, kConcaveLeft, kConcaveCenter, kConvex };
 // modeTable of Rasterizer.cpp:30-64 as nibbles: entry i = nibble (i & 7) of word (i >> 3);

@@ -125,17 +125,56 @@ const int64_t* edge_mask_table() {
 // vectors were made on): x = 2^(2k+p) * 1.m -> 2^-k * table[p][m >> shift].
 static std::vector<uint32_t> g_rsqrtTable;
 static int g_rsqrtBits = 0;
-static float table_rsqrt(float x) {
-  const uint32_t in = f2u(x), e = (in >> 23) & 0xffu, m = in & 0x7fffffu;
-  if (e == 255) return m ? u2f(in | 0x00400000u) : ((in & kSign) ? u2f(0xffc00000u) : 0.0f);
-  if (e == 0) return u2f((in & kSign) | 0x7f800000u);
-  if (in & kSign) return u2f(0xffc00000u);
-  const int32_t ue = int32_t(e) - 127, p = ue & 1, k = (ue - p) / 2;
-  const uint32_t b = g_rsqrtTable[(uint32_t(p) << g_rsqrtBits) + (m >> (23 - g_rsqrtBits))];
-  const int32_t re = int32_t((b >> 23) & 0xffu) - k;
-  return u2f((uint32_t(re) << 23) | (b & 0x7fffffu));
+static inline float rsqrt_x86(float x) {
+  if (!g_rsqrtBits) return host_rsqrt(x);
+  const RsqrtTable t{g_rsqrtTable.data(), g_rsqrtBits};
+  return orz::rsqrt_x86(x, t);
 }
-static inline float rsqrt_x86(float x) { return g_rsqrtBits ? table_rsqrt(x) : host_rsqrt(x); }
+
+// rsqrtps(y) for y in [1, 4): smallest number of leading mantissa bits it depends on (10 on Intel).
+// `exact` = the exponent / special-value model reproduced the instruction on a sample sweep.
+void probe_host_rsqrt(std::vector<uint32_t>& table, int& bits, bool& exact) {
+  const uint32_t N = 1u << 23;
+  std::vector<uint32_t> full(2 * size_t(N));
+  for (uint32_t p = 0; p < 2; ++p)
+    for (uint32_t m = 0; m < N; ++m) full[size_t(p) * N + m] = f2u(host_rsqrt(u2f(((127u + p) << 23) | m)));
+  int k = 0;
+  for (; k < 23; ++k) {
+    const uint32_t group = N >> k;
+    bool ok = true;
+    for (uint32_t p = 0; p < 2 && ok; ++p)
+      for (uint32_t g = 0; g < (1u << k) && ok; ++g) {
+        const uint32_t v = full[size_t(p) * N + size_t(g) * group];
+        for (uint32_t i = 1; i < group; ++i)
+          if (full[size_t(p) * N + size_t(g) * group + i] != v) { ok = false; break; }
+      }
+    if (ok) break;
+  }
+  bits = k;
+  table.resize(size_t(2) << k);
+  for (uint32_t p = 0; p < 2; ++p)
+    for (uint32_t g = 0; g < (1u << k); ++g) table[(size_t(p) << k) + g] = full[size_t(p) * N + (size_t(g) << (23 - k))];
+  const RsqrtTable rt{table.data(), k};
+  exact = true;
+  uint32_t lcg = 777u;
+  const uint32_t exps[] = {0, 1, 2, 3, 64, 125, 126, 127, 128, 129, 200, 251, 252, 253, 254, 255};
+  for (uint32_t e : exps)
+    for (int i = 0; i < 2048; ++i) {
+      lcg = lcg * 1664525u + 1013904223u;
+      uint32_t in = (lcg & 0x807fffffu) | (e << 23);
+      if (i < 4) in = (in & 0x80000000u) | (e << 23) | (i == 1 ? 0x7fffffu : (i == 2 ? 1u : 0u));
+      if (f2u(host_rsqrt(u2f(in))) != f2u(orz::rsqrt_x86(u2f(in), rt))) exact = false;
+    }
+}
+// the table the bake currently uses: the installed one, or this CPU's
+void current_rsqrt_table(std::vector<uint32_t>& table, int& bits) {
+  if (g_rsqrtBits) { table = g_rsqrtTable; bits = g_rsqrtBits; return; }
+  static std::vector<uint32_t> host;
+  static int hostBits = 0;
+  static std::once_flag once;
+  std::call_once(once, [] { bool ex; probe_host_rsqrt(host, hostBits, ex); });
+  table = host; bits = hostBits;
+}
 
 struct V3 { float x, y, z; };
 static inline V3 sub(const float* a, const float* b) { return {a[0] - b[0], a[1] - b[1], a[2] - b[2]}; }

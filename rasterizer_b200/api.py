@@ -56,6 +56,7 @@ EXPORTS = {
     "orz_context_launch_count": (C.c_uint64, [C.c_void_p]),
     "orz_context_set_group_warps": (C.c_int, [C.c_void_p, C.c_int]),
     "orz_context_set_arena_bytes": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "orz_context_set_cluster_views": (C.c_int, [C.c_void_p, C.c_int]),
     "orz_context_set_traversal": (C.c_int, [C.c_void_p, C.c_int]),
     "orz_edge_mask_table": (C.c_int, [C.c_void_p]),
     "orz_probe_host_rcp": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -180,6 +181,9 @@ class Context:
 
     def set_traversal(self, mapping: int):
         _check(lib().orz_context_set_traversal(self.h, mapping))
+
+    def set_cluster_views(self, max_views: int):
+        _check(lib().orz_context_set_cluster_views(self.h, max_views))
 
     def set_arena_bytes(self, nbytes: int):
         _check(lib().orz_context_set_arena_bytes(self.h, nbytes))

@@ -22,6 +22,7 @@
 //     the group on the blocks of one rectangle.
 // No tensor cores: nothing here is a contraction.  Build: -fmad=false (see orz_core.h).
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -47,6 +48,7 @@
 #endif
 
 namespace orz {
+namespace cg = cooperative_groups;
 
 __constant__ uint32_t c_modeNibbles[32] = {ORZ_MODE_NIBBLES};
 
@@ -635,6 +637,7 @@ struct FrameParams {
   uint32_t* viewOrder;  // nViews: views sorted by descending cost (longest first), or NULL
   uint32_t viewBase, groupViews;  // this launch handles sorted ranks [viewBase, viewBase + groupViews)
   int exportDepth;      // 1: the caller reads depth back -> zero-fill blocks that stayed cleared
+  uint32_t clusterK;    // cluster kernel: tiles per warp
 };
 
 __global__ void __launch_bounds__(128) k_prepare_views(const FrameParams p) {
@@ -815,6 +818,383 @@ __global__ void __launch_bounds__(GW * 32, (kTrav == 2 ? ORZ_THREADS_PER_SM_V2 :
         }
     }
     __syncthreads();  // s_view is rewritten by the next view
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Few views (BASELINE configs 1 and 2 are ONE view): a thread-block CLUSTER of C CTAs x 16 warps
+// per view instead of one CTA.  A single view is a chain of dependent gate -> setup -> traversal
+// phases (Main.cpp:192-206) and, inside one occluder, primitives stack on the same blocks (Castle,
+// default camera: up to ~300 in-order updates of one block per frame), so what counts is the
+// latency of the serial chain, not throughput:
+//   * the screen is cut into TILES of 8x4 blocks; tile t belongs to warp t mod (16 C) of the
+//     cluster for the whole view, lane <-> block.  A tile is only ever read or written by its
+//     owner (gate included): no cross-SM traffic on depth / HiZ, no atomics, order preserved;
+//   * TILE-MAJOR traversal: for each of its tiles a warp walks the occluder's primitives in order
+//     with the tile's depth held in REGISTERS (one 8x8 block = 8 x uint4 per lane) and its HiZ in
+//     a register + shared-memory mirror: a stacked primitive costs shared-memory and ALU latency
+//     only; the L2 round trip (load at first touch, store at the end) is paid once per
+//     (occluder, tile) instead of once per (primitive, block);
+//   * every CTA sets up the whole occluder redundantly (<= 504 quads = one quad per lane, one
+//     pass) but keeps only the primitives that touch one of ITS tiles, compacted in order;
+//   * the gate (queryVisibility of the occluder's box, Main.cpp:195) is evaluated tile-locally
+//     right after the traversal for a WINDOW of the next kGateWindow undecided occluders; a warp
+//     that finds a visible pixel raises that candidate's flag in the shared memory of every CTA
+//     of the cluster (DSMEM stores).  After ONE hardware cluster barrier all CTAs agree on the
+//     first visible candidate: the candidates before it were tested against exactly the buffers
+//     they would have seen sequentially (nothing was rasterised in between), so their "invisible"
+//     is final; the ones after it are tested again in the next window;
+//   * the edge-mask table (32 KB) and the rcpps table (8 KB) live in shared memory.
+constexpr int kClusterGW = 16;
+constexpr int kGateWindow = 4;
+constexpr uint32_t kClusterRcpWords = 2048;  // rcpps tables up to 11 mantissa bits are staged in shared memory
+constexpr uint32_t kTileW = 8, kTileH = 4;   // blocks per tile: lane = 8 * (row in tile) + column in tile
+
+struct ClusterSmem {
+  static constexpr uint32_t NT = kClusterGW * 32;
+  static constexpr uint32_t kLutWords = 4096 * 2;
+  static constexpr uint32_t kRecWords = NT * kRecStride;
+  static constexpr uint32_t kChainWords = kClusterGW * 12 * 32;
+  static constexpr uint32_t kFixedWords = kLutWords + kRecWords + kChainWords + kClusterRcpWords;
+  static size_t bytes(uint32_t tilesPerWarp) { return (size_t)kFixedWords * 4 + (size_t)kClusterGW * tilesPerWarp * 32 * 2; }
+};
+
+// one block of query2D (Rasterizer.cpp:305-343) with the block's HiZ already at hand
+__device__ __forceinline__ bool query_block_h(const Target& T, uint32_t bx, uint32_t by, uint32_t h, uint32_t minX, uint32_t maxX,
+                                              uint32_t minY, uint32_t maxY, uint32_t maxZ) {
+  if (maxZ <= h) return false;  // Rasterizer.cpp:310
+  if (h == 1u) return true;     // cleared block: depth reads as 0 < maxZ (fresh state)
+  const int sX = max((int)minX - (int)(8u * bx), 0), eX = min((int)maxX - (int)(8u * bx), 7);
+  const int sY = max((int)minY - (int)(8u * by), 0), eY = min((int)maxY - (int)(8u * by), 7);
+  if (sX == 0 && eX == 7 && sY == 0 && eY == 7) return true;  // Rasterizer.cpp:319-325
+  return block_fine_test(T.depth, by * T.blocksX + bx, maxZ, sX, eX, sY, eY);
+}
+
+// does the primitive's block rectangle touch a tile owned by CTA `rank` (tile t -> CTA t mod C)?
+template <int C>
+__device__ __forceinline__ bool prim_touches_rank(const Prim& P, uint32_t tilesX, uint32_t rank) {
+  const uint32_t ta = (uint32_t)P.minX / kTileW, tb = (uint32_t)(P.minX + P.rangeX - 1) / kTileW;
+  const uint32_t ua = (uint32_t)P.minY / kTileH, ub = (uint32_t)(P.minY + P.rangeY - 1) / kTileH;
+  const uint32_t n = tb - ta + 1u;
+  if (n >= (uint32_t)C) return true;
+  for (uint32_t u = ua; u <= ub; ++u)
+    if (((rank - (u * tilesX + ta)) & (uint32_t)(C - 1)) < n) return true;
+  return false;
+}
+
+// One primitive on the tile a warp has open (Rasterizer.cpp:1098-1292 restricted to the tile's
+// blocks).  d[8] / h are the lane's block and its HiZ, kept in registers between primitives.
+__device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, const int lane, const uint32_t x0, const uint32_t y0,
+                                          const uint32_t x1, const uint32_t y1, const uint2* __restrict__ lut, float* __restrict__ sm,
+                                          uint4 (&d)[8], uint32_t& h, bool& dirty) {
+  const uint32_t w0 = rec[0], w1 = rec[1], w2 = rec[2];
+  const uint32_t minX = w0 & 0xffffu, minY = w0 >> 16, maxZ = w2 & 0xffffu, mode = w2 >> 16;
+  const uint32_t xa = max(minX, x0), xb = min(minX + (w1 & 0xffffu), x1), ya = max(minY, y0), yb = min(minY + (w1 >> 16), y1);
+  const uint32_t bx = x0 + ((uint32_t)lane & 7u), by = y0 + ((uint32_t)lane >> 3);
+  const bool pass = bx >= xa && bx < xb && by >= ya && by < yb && h < maxZ;  // Rasterizer.cpp:1148-1152
+  const uint32_t passMask = __ballot_sync(kFull, pass);
+  if (!passMask) return;  // the whole tile is behind its HiZ: no chain has to be stepped at all
+
+  // ---- the 12 iterated add chains (4 edge offsets, 8 depth lanes), one per lane 0-11, stepped
+  // exactly as the reference does: y chain from the primitive's first row (Rasterizer.cpp:1130),
+  // x chain restarted at every row start (:1136, :1145); values are published for the blocks that
+  // passed, up to the last one of each tile row
+  const float dzdx = u2f(rec[3]), dzdy = u2f(rec[4]);
+  float cur = 0.0f, incX = 0.0f, incY = 0.0f;
+  if (lane < 4) { cur = u2f(rec[14 + lane]); incX = u2f(rec[6 + lane]); incY = u2f(rec[10 + lane]); }
+  else if (lane < 12) {
+    const int l = lane - 4;
+    const float s = -0.5f + 1.0f / 16.0f;
+    cur = ORZ_FMA(dzdx, s + 0.125f * (float)(l & 3), ORZ_FMA(dzdy, (l >> 2) ? s + 0.125f : s, u2f(rec[5])));
+    incX = dzdx; incY = dzdy;
+  }
+  for (uint32_t i = minY; i < ya; ++i) cur = cur + incY;
+  const uint32_t rLast = (31u - (uint32_t)__clz((int)passMask)) >> 3;
+  for (uint32_t r = ya - y0; r <= rLast; ++r) {
+    const uint32_t rowBits = (passMask >> (8u * r)) & 0xffu;
+    if (rowBits) {
+      const uint32_t cFirst = (uint32_t)__ffs((int)rowBits) - 1u, cLast = 31u - (uint32_t)__clz((int)rowBits);
+      float run = cur;
+      for (uint32_t i = minX; i < x0 + cFirst; ++i) run = incX + run;
+      for (uint32_t c = cFirst; c <= cLast; ++c) {
+        if (lane < 12) sm[lane * 32 + (int)(r * 8u + c)] = run;
+        run = incX + run;
+      }
+    }
+    cur = cur + incY;
+  }
+  __syncwarp();
+
+  // ---- coverage (Rasterizer.cpp:1155-1239)
+  bool upd = false;
+  uint2 mk = make_uint2(0u, 0u);
+  if (pass) {
+    const float o0 = sm[0 * 32 + lane], o1 = sm[1 * 32 + lane], o2 = sm[2 * 32 + lane], o3 = sm[3 * 32 + lane];
+    const uint32_t slope01 = rec[18], slope23 = rec[19];
+    const uint32_t s0 = slope01 & 0xffffu, s1 = slope01 >> 16, s2 = slope23 & 0xffffu, s3 = slope23 >> 16;
+    if (mode == kConvex) {
+      if (!(o0 >= 63.0f || o1 >= 63.0f || o2 >= 63.0f || o3 >= 63.0f)) {
+        const uint2 A = lut[s0 | (uint32_t)__float2int_rz(fmaxf(o0, 0.0f))], B = lut[s1 | (uint32_t)__float2int_rz(fmaxf(o1, 0.0f))];
+        const uint2 C2 = lut[s2 | (uint32_t)__float2int_rz(fmaxf(o2, 0.0f))], D = lut[s3 | (uint32_t)__float2int_rz(fmaxf(o3, 0.0f))];
+        mk.x = (A.x & B.x) & (C2.x & D.x); mk.y = (A.y & B.y) & (C2.y & D.y);
+        upd = true;  // no empty-mask test on this path (Rasterizer.cpp:1186)
+      }
+    } else {
+      const uint32_t q0 = o0 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o0, 0.0f), 63.0f)) : 0u;
+      const uint32_t q1 = o1 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o1, 0.0f), 63.0f)) : 0u;
+      const uint32_t q2 = o2 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o2, 0.0f), 63.0f)) : 0u;
+      const uint32_t q3 = o3 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o3, 0.0f), 63.0f)) : 0u;
+      const uint2 A = lut[s0 | q0], B = lut[s1 | q1], C2 = lut[s2 | q2], D = lut[s3 | q3];
+      if (mode == kTriangle0) { mk.x = A.x & B.x & C2.x; mk.y = A.y & B.y & C2.y; }
+      else if (mode == kTriangle1) { mk.x = A.x & C2.x & D.x; mk.y = A.y & C2.y & D.y; }
+      else if (mode == kConcaveRight) { mk.x = (A.x | D.x) & (B.x & C2.x); mk.y = (A.y | D.y) & (B.y & C2.y); }
+      else if (mode == kConcaveCenter) { mk.x = (A.x & B.x) | (C2.x & D.x); mk.y = (A.y & B.y) | (C2.y & D.y); }
+      else { mk.x = (A.x & D.x) & (B.x | C2.x); mk.y = (A.y & D.y) & (B.y | C2.y); }
+      upd = (mk.x | mk.y) != 0u;
+    }
+  }
+  // ---- depth rows, merge into the registers, HiZ (Rasterizer.cpp:1241-1290)
+  if (upd) {
+    const float* smd = sm + 4 * 32 + lane;
+    const uint32_t keep = h != 1u ? 0xffffffffu : 0u;  // a cleared block is overwritten (:1271-1278)
+    uint32_t r0[2][4], r4[2][4], r8[2][4];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      float dv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dv[k] = smd[(4 * rr + k) * 32];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a = dv[(2 * i) & 3], b = dv[(2 * i + 1) & 3];
+        if (i >= 2) { a = ORZ_FMA(dzdx, 0.5f, a); b = ORZ_FMA(dzdx, 0.5f, b); }  // depth1, :1243
+        const float a8 = dzdy + a, b8 = dzdy + b;                                // depth8/9, :1244-1245
+        r0[rr][i] = pack16(a) | (pack16(b) << 16);
+        r8[rr][i] = pack16(a8) | (pack16(b8) << 16);
+        r4[rr][i] = avg_u16x2(r0[rr][i], r8[rr][i]);                             // :1252
+      }
+    }
+    uint32_t mnAcc = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int y = 2 * k + rr;
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          w[i] = k == 0 ? r0[rr][i] : k == 2 ? r4[rr][i] : k == 1 ? avg_u16x2(r0[rr][i], r4[rr][i]) : avg_u16x2(r4[rr][i], r8[rr][i]);  // :1253-1254
+        const int ky = (rr ? 0 : 4) + k;  // pixel px of row y <-> bit 8 px + ky (:1257-1268)
+        const uint32_t lo = ((mk.x >> ky) & 0x01010101u) * 0xffu, hi = ((mk.y >> ky) & 0x01010101u) * 0xffu;
+        uint4 v;
+        v.x = __vmaxu2(w[0] & __byte_perm(lo, 0u, 0x1100), d[y].x & keep);
+        v.y = __vmaxu2(w[1] & __byte_perm(lo, 0u, 0x3322), d[y].y & keep);
+        v.z = __vmaxu2(w[2] & __byte_perm(hi, 0u, 0x1100), d[y].z & keep);
+        v.w = __vmaxu2(w[3] & __byte_perm(hi, 0u, 0x3322), d[y].w & keep);
+        d[y] = v;
+        mnAcc = __vminu2(mnAcc, __vminu2(__vminu2(v.x, v.y), __vminu2(v.z, v.w)));
+      }
+    h = min(mnAcc & 0xffffu, mnAcc >> 16);  // Rasterizer.cpp:1287-1290
+    dirty = true;
+  }
+  __syncwarp();  // chain slots are rewritten by the next primitive
+}
+
+template <int C>
+__global__ void __launch_bounds__(kClusterGW * 32, 1) k_render_views_cluster(const FrameParams p) {
+  constexpr uint32_t GW = kClusterGW, NT = GW * 32, kWarps = C * GW;
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  uint2* s_lut = reinterpret_cast<uint2*>(s_dyn);
+  uint32_t* s_recs = s_dyn + ClusterSmem::kLutWords;
+  float* s_chain = reinterpret_cast<float*>(s_dyn + ClusterSmem::kLutWords + ClusterSmem::kRecWords);
+  uint32_t* s_rcp = s_dyn + ClusterSmem::kLutWords + ClusterSmem::kRecWords + ClusterSmem::kChainWords;
+  uint16_t* s_hiz = reinterpret_cast<uint16_t*>(s_dyn + ClusterSmem::kFixedWords);  // [GW][K][32]: HiZ of the tiles my warps own
+  __shared__ uint32_t s_count[GW];
+  __shared__ uint32_t s_flag[3][kGateWindow];
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const uint32_t rank = cluster.block_rank();
+  const uint32_t view = p.viewBase + blockIdx.x / (uint32_t)C;
+  const uint32_t tid = threadIdx.x;
+  const int warp = (int)(tid >> 5), lane = (int)(tid & 31u);
+  const uint32_t gw = (uint32_t)warp * (uint32_t)C + rank;  // my tiles: t % kWarps == gw  (so tile t -> CTA t % C)
+  const uint32_t K = p.clusterK;
+
+  for (uint32_t i = tid; i < 4096u; i += NT) s_lut[i] = p.lut[i];
+  const uint32_t rcpWords = 1u << (23 - p.rcpShift);
+  const bool rcpStaged = rcpWords <= kClusterRcpWords;
+  if (rcpStaged) for (uint32_t i = tid; i < rcpWords; i += NT) s_rcp[i] = p.rcp[i];
+  const RcpTable rt{rcpStaged ? s_rcp : p.rcp, p.rcpShift};
+  if (tid < 3u * kGateWindow) (&s_flag[0][0])[tid] = 0u;
+
+  Target T;
+  T.width = p.width; T.height = p.height; T.blocksX = p.width >> 3; T.blocksY = p.height >> 3;
+  T.depth = p.depth + (size_t)view * p.depthStride;
+  T.hiz = p.hiz + (size_t)view * p.hizStride;
+  const uint32_t tilesX = (T.blocksX + kTileW - 1u) / kTileW, tilesY = (T.blocksY + kTileH - 1u) / kTileH, nTiles = tilesX * tilesY;
+  const bool useGate = (p.flags & ORZ_BATCH_NO_GATE) == 0u;
+  const bool forceClip = (p.flags & ORZ_BATCH_FORCE_CLIPPED) != 0u;
+  const uint32_t* order = p.orders ? p.orders + (size_t)view * p.nOcc : p.orderBuf + (size_t)view * p.nOcc;
+  const uint32_t* front = p.frontBuf + (size_t)view * p.nOcc * kFrontWords;
+  uint16_t* myHiz = s_hiz + (size_t)warp * K * 32u + lane;  // + 32 k
+  float* myChain = s_chain + warp * (12 * 32);
+  const uint32_t lx = (uint32_t)lane & 7u, ly = (uint32_t)lane >> 3;
+
+  // clear (Rasterizer.cpp:107-121): HiZ := 1 on my tiles; depth is overwritten by the first update
+  for (uint32_t k = 0, t = gw; k < K && t < nTiles; ++k, t += kWarps) {
+    const uint32_t ty = t / tilesX, tx = t - ty * tilesX;
+    const uint32_t bx = tx * kTileW + lx, by = ty * kTileH + ly;
+    myHiz[32u * k] = 1;
+    if (bx < T.blocksX && by < T.blocksY) T.hiz[by * T.blocksX + bx] = 1;
+  }
+  __syncwarp();
+  cluster.sync();  // tables staged, flags zero in every CTA before the first remote store
+
+  uint32_t slot = 0, phase = 0, quadsSubmitted = 0;
+  while (slot < p.nOcc) {
+    // ---- window: the next undecided occluders up to the first one that needs no test
+    uint32_t cand[kGateWindow];
+    uint32_t n = 0, end = slot;
+    bool stopNearClip = false;
+#pragma unroll 1
+    while (end < p.nOcc && n < (uint32_t)kGateWindow) {
+      const uint32_t st = front[(size_t)end * kFrontWords];
+      if (st == kBoxNearClip) { stopNearClip = true; break; }
+      if (st == kBoxRect) {
+#pragma unroll
+        for (int j = 0; j < kGateWindow; ++j) if ((uint32_t)j == n) cand[j] = end;
+        ++n;
+      }
+      ++end;
+    }
+    uint32_t target = 0xffffffffu;
+    bool clipped = false;
+    if (n > 0) {
+      uint32_t* flags = s_flag[phase % 3u];
+      if (tid < (uint32_t)kGateWindow) s_flag[(phase + 1u) % 3u][tid] = 0u;  // last read two barriers ago
+      bool earlier = false;
+#pragma unroll
+      for (int j = 0; j < kGateWindow; ++j)
+        if ((uint32_t)j < n && !earlier) {
+          // query2D (Rasterizer.cpp:283-349) of candidate j restricted to my tiles
+          const uint32_t* fr = front + (size_t)cand[j] * kFrontWords;
+          const uint32_t minX = fr[1], maxX = fr[2], minY = fr[3], maxY = fr[4], maxZ = fr[5];
+          const uint32_t bx0 = minX >> 3, bx1 = maxX >> 3, by0 = minY >> 3, by1 = maxY >> 3;
+          uint32_t* flagLocal = flags + j;
+          for (uint32_t k = 0, t = gw; k < K && t < nTiles; ++k, t += kWarps) {
+            const uint32_t ty = t / tilesX, tx = t - ty * tilesX;
+            const uint32_t x0 = tx * kTileW, y0 = ty * kTileH;
+            if (x0 > bx1 || x0 + kTileW <= bx0 || y0 > by1 || y0 + kTileH <= by0) continue;
+            if (*reinterpret_cast<volatile uint32_t*>(flagLocal)) break;  // another warp already found a visible pixel
+            const uint32_t bx = x0 + lx, by = y0 + ly;
+            const bool hit = bx >= bx0 && bx <= bx1 && by >= by0 && by <= by1 && bx < T.blocksX && by < T.blocksY &&
+                             query_block_h(T, bx, by, (uint32_t)myHiz[32u * k], minX, maxX, minY, maxY, maxZ);
+            if (__any_sync(kFull, hit)) {
+              if (lane < C) *cluster.map_shared_rank(flagLocal, (unsigned)lane) = 1u;
+              break;
+            }
+          }
+          earlier = *reinterpret_cast<volatile uint32_t*>(flagLocal) != 0u;  // a later candidate's answer would be discarded
+        }
+      cluster.sync();
+      ++phase;
+#pragma unroll
+      for (int j = kGateWindow - 1; j >= 0; --j)
+        if ((uint32_t)j < n && flags[j]) target = cand[j];
+    }
+    if (target == 0xffffffffu && stopNearClip) { target = end; clipped = useGate ? true : forceClip; }
+    const uint32_t decided = target == 0xffffffffu ? end : target + 1u;  // slots [slot, decided) now have their answer
+    if (p.gate && rank == 0u)
+      for (uint32_t s = slot + tid; s < decided; s += NT)
+        p.gate[(size_t)view * p.nOcc + s] = s == target ? (uint8_t)(1 | (clipped && useGate ? 2 : 0)) : (uint8_t)0;
+    slot = decided;
+    if (target == 0xffffffffu) continue;
+
+    // ---- rasterize<clipped>(occluder)
+    const uint32_t* fr = front + (size_t)target * kFrontWords;
+    const OccMeta& om = p.occ[order[target]];
+    const uint4* quads = p.quads + om.quadOffset;
+    const uint32_t nq = om.quadCount;
+    quadsSubmitted += nq;
+    CallMatrix cm;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { cm.rx[k] = u2f(fr[6 + k]); cm.ry[k] = u2f(fr[10 + k]); cm.rw[k] = u2f(fr[14 + k]); }
+    cm.c0 = u2f(fr[18]); cm.c1 = u2f(fr[19]);
+    for (uint32_t q0 = 0; q0 < nq; q0 += NT) {
+      // setup (Rasterizer.cpp:657-1086): one quad per lane; keep what touches a tile of this CTA
+      const uint32_t qi = q0 + tid;
+      bool ok = false;
+      Prim P;
+      if (qi < nq) {
+        const uint4 v = quads[qi];
+        const uint32_t word[4] = {v.x, v.y, v.z, v.w};
+        ok = clipped ? setup_quad<true>(word, cm, rt, c_modeNibbles, (int32_t)T.blocksX, (int32_t)T.blocksY, P)
+                     : setup_quad<false>(word, cm, rt, c_modeNibbles, (int32_t)T.blocksX, (int32_t)T.blocksY, P);
+        if (ok) ok = prim_touches_rank<C>(P, tilesX, rank);
+      }
+      const uint32_t valid = __ballot_sync(kFull, ok);
+      if (lane == 0) s_count[warp] = (uint32_t)__popc(valid);
+      __syncthreads();  // also: every warp is done with the previous chunk's records
+      uint32_t base = 0, total = 0;
+#pragma unroll
+      for (int w2 = 0; w2 < (int)GW; ++w2) { const uint32_t c = s_count[w2]; base += w2 < warp ? c : 0u; total += c; }
+      if (ok) store_record(s_recs + (base + (uint32_t)__popc(valid & ((1u << lane) - 1u))) * kRecStride, P);  // in order
+      __syncthreads();
+
+      // ---- tile-major traversal: my tiles, each with the primitives that touch it, in order
+      if (total)
+        for (uint32_t k = 0, t = gw; k < K && t < nTiles; ++k, t += kWarps) {
+          const uint32_t ty = t / tilesX, tx = t - ty * tilesX;
+          const uint32_t x0 = tx * kTileW, y0 = ty * kTileH;
+          const uint32_t x1 = min(x0 + kTileW, T.blocksX), y1 = min(y0 + kTileH, T.blocksY);
+          const uint32_t bx = x0 + lx, by = y0 + ly;
+          const bool inScreen = bx < x1 && by < y1;
+          uint4* dp = reinterpret_cast<uint4*>(T.depth) + (size_t)(by * T.blocksX + bx) * 8u;
+          uint4 d[8];
+          uint32_t h = 0xffffu;
+          bool open = false, dirty = false;
+          for (uint32_t r0 = 0; r0 < total; r0 += 32u) {
+            bool touches = false;
+            if (r0 + (uint32_t)lane < total) {
+              const uint32_t* rec = s_recs + (r0 + (uint32_t)lane) * kRecStride;
+              const uint32_t a = rec[0], b = rec[1];
+              const uint32_t minX = a & 0xffffu, minY = a >> 16;
+              touches = minX < x1 && minX + (b & 0xffffu) > x0 && minY < y1 && minY + (b >> 16) > y0;
+            }
+            uint32_t hits = __ballot_sync(kFull, touches);
+            while (hits) {
+              const uint32_t i = (uint32_t)__ffs((int)hits) - 1u;
+              hits &= hits - 1u;
+              if (!open) {  // first primitive on this tile: bring the tile into registers
+                open = true;
+                h = inScreen ? (uint32_t)myHiz[32u * k] : 0xffffu;  // off-screen lanes never pass
+                const bool load = inScreen && h != 1u;
+#pragma unroll
+                for (int y = 0; y < 8; ++y) d[y] = load ? dp[y] : make_uint4(0u, 0u, 0u, 0u);
+              }
+              tile_prim(s_recs + (r0 + i) * kRecStride, lane, x0, y0, x1, y1, s_lut, myChain, d, h, dirty);
+            }
+          }
+          if (dirty) {
+#pragma unroll
+            for (int y = 0; y < 8; ++y) dp[y] = d[y];
+            myHiz[32u * k] = (uint16_t)h;
+            T.hiz[by * T.blocksX + bx] = (uint16_t)h;
+          }
+        }
+    }
+  }
+  if (p.quadsSubmitted && rank == 0u && tid == 0u) p.quadsSubmitted[view] = quadsSubmitted;
+  if (p.exportDepth) {  // canonical depth for the caller: blocks that stayed cleared read as zero
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t k = 0, t = gw; k < K && t < nTiles; ++k, t += kWarps) {
+      const uint32_t ty = t / tilesX, tx = t - ty * tilesX;
+      const uint32_t bx = tx * kTileW + lx, by = ty * kTileH + ly;
+      if (bx < T.blocksX && by < T.blocksY && myHiz[32u * k] == 1) {
+        uint4* d4 = reinterpret_cast<uint4*>(T.depth) + (size_t)(by * T.blocksX + bx) * 8u;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) d4[y] = z;
+      }
+    }
   }
 }
 
@@ -1128,6 +1508,7 @@ struct orz_context {
   uint64_t launches = 0;
   int groupWarps = 0;
   int traversal = 2;  // 1 = warp per block, 2 = lane per block (default)
+  int clusterViews = 16;  // batches of at most this many views run one thread-block cluster per view (0 = never)
   // grow-only device scratch
   uint32_t* d_counter = nullptr;
   void* d_scratch[12] = {nullptr};
@@ -1226,6 +1607,11 @@ extern "C" int orz_context_set_group_warps(orz_context* ctx, int warps) {
 extern "C" int orz_context_set_traversal(orz_context* ctx, int mapping) {
   if (!ctx || (mapping != 1 && mapping != 2)) return fail(ORZ_ERR_ARG, "traversal mapping must be 1 (warp per block) or 2 (lane per block)");
   ctx->traversal = mapping;
+  return ORZ_OK;
+}
+extern "C" int orz_context_set_cluster_views(orz_context* ctx, int maxViews) {
+  if (!ctx || maxViews < 0) return fail(ORZ_ERR_ARG, "orz_context_set_cluster_views: bad arguments");
+  ctx->clusterViews = maxViews;
   return ORZ_OK;
 }
 extern "C" int orz_context_set_arena_bytes(orz_context* ctx, size_t bytes) {
@@ -1539,6 +1925,40 @@ static int occupancy_views(int GW, int trav, int* perSM) {
   }
 }
 
+template <int C>
+static int launch_cluster_t(orz_context* ctx, FrameParams p, uint32_t nViews, uint32_t nTiles, cudaStream_t st) {
+  p.clusterK = (nTiles + (uint32_t)(C * kClusterGW) - 1u) / (uint32_t)(C * kClusterGW);
+  const size_t smem = ClusterSmem::bytes(p.clusterK);
+  static size_t configured[64] = {0};
+  if (configured[ctx->device & 63] < smem) {
+    ORZ_CUDA(cudaFuncSetAttribute(k_render_views_cluster<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (C > 8) ORZ_CUDA(cudaFuncSetAttribute(k_render_views_cluster<C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    configured[ctx->device & 63] = smem;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(nViews * (uint32_t)C);
+  cfg.blockDim = dim3(kClusterGW * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  ORZ_CUDA(cudaLaunchKernelEx(&cfg, k_render_views_cluster<C>, p));
+  ctx->launches++;
+  return ORZ_OK;
+}
+// one cluster per view; cluster size from the number of 8x4-block tiles (about 4 tiles per warp, 16 warps per CTA)
+static int launch_cluster(orz_context* ctx, const FrameParams& p, uint32_t nViews, cudaStream_t st) {
+  const uint32_t nTiles = (((p.width >> 3) + kTileW - 1u) / kTileW) * (((p.height >> 3) + kTileH - 1u) / kTileH);
+  if (nTiles > 512u) return launch_cluster_t<16>(ctx, p, nViews, nTiles, st);
+  if (nTiles > 256u) return launch_cluster_t<8>(ctx, p, nViews, nTiles, st);
+  if (nTiles > 128u) return launch_cluster_t<4>(ctx, p, nViews, nTiles, st);
+  return launch_cluster_t<2>(ctx, p, nViews, nTiles, st);
+}
+
 // Device-pointer entry: three launches per chunk of views (prepare, render, query).  When the
 // caller does not ask for depth/HiZ, per-view targets live in an internal arena and the batch is
 // processed in chunks that fit the arena budget.
@@ -1614,7 +2034,10 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
     }
     p.viewCounter = ctx->d_counter;
     p.viewCost = (uint32_t*)(prep + chunk * sizeof(ViewMatrices) + chunk * nOcc * 4 + chunk * nOcc * kFrontWords * 4);
-    p.viewOrder = nv <= 16384u ? p.viewCost + chunk : nullptr;
+    const bool wide = (b->flags & ORZ_BATCH_NO_GATE) && ((b->flags & ORZ_BATCH_WIDE) || (nv <= 8u && scene->totalQuads >= 65536u));
+    // (above 65 536 blocks the reference's 16-bit index wrap needs the linear traversal of the batch kernel)
+    const bool clusterPath = !wide && ctx->clusterViews > 0 && nv <= (uint32_t)ctx->clusterViews && blocks <= 65536u;
+    p.viewOrder = (nv <= 16384u && !clusterPath) ? p.viewCost + chunk : nullptr;
     k_prepare_views<<<nv, 128, 0, ctx->stream>>>(p);
     ctx->launches++;
     ORZ_CUDA(cudaGetLastError());
@@ -1624,7 +2047,6 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
       ORZ_CUDA(cudaGetLastError());
     }
     // Few views over many ungated occluders: split each view over the whole GPU instead
-    const bool wide = (b->flags & ORZ_BATCH_NO_GATE) && ((b->flags & ORZ_BATCH_WIDE) || (nv <= 8u && scene->totalQuads >= 65536u));
     if (wide) {
       const uint32_t total = scene->totalQuads, nChunks = (total + 31u) / 32u;
       if ((e = ensure_scratch(ctx, 8, ((size_t)nOcc + 1) * 4))) return e;
@@ -1655,6 +2077,18 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
         FrameParams pq = p;
         pq.viewOrder = nullptr; pq.viewBase = 0; pq.groupViews = nv;
         k_query_views<<<dim3((scene->nBoxes + 255) / 256, nv), 256, 0, ctx->stream>>>(pq);
+        ctx->launches++;
+        ORZ_CUDA(cudaGetLastError());
+      }
+      continue;
+    }
+    // Few views: one thread-block cluster per view (latency path, BASELINE configs 1 and 2)
+    if (clusterPath) {
+      FrameParams pc = p;
+      pc.viewOrder = nullptr; pc.viewBase = 0; pc.groupViews = nv;
+      if ((e = launch_cluster(ctx, pc, nv, ctx->stream))) return e;
+      if (p.visBits || p.clipBits) {
+        k_query_views<<<dim3((scene->nBoxes + 255) / 256, nv), 256, 0, ctx->stream>>>(pc);
         ctx->launches++;
         ORZ_CUDA(cudaGetLastError());
       }

@@ -152,6 +152,7 @@ def test_view_batch(ctx, lut, name, size, nviews, gw, trav):
     w, h = size
     ctx.set_group_warps(gw)
     ctx.set_traversal(trav)
+    ctx.set_cluster_views(0)  # the one-CTA-per-view batch kernel (few views would take the cluster path)
     mvps, poss = wl.camera_path(B.ps, nviews - 1, w, h) if size[0] >= 640 else wl.probe_views(B.ps, nviews - 1, w, h)
     m0, p0 = B.default_view(w, h)
     mvps = np.concatenate([m0[None], mvps]); poss = np.concatenate([p0[None], poss])
@@ -174,20 +175,63 @@ def test_view_batch(ctx, lut, name, size, nviews, gw, trav):
     assert np.array_equal(out2["vis"], out["vis"])
     assert np.array_equal(out2["gate"], out["gate"])
     ctx.set_group_warps(0)
-    ctx.set_traversal(1)
+    ctx.set_traversal(2)
+    ctx.set_cluster_views(16)
     sc.close(); port.close()
 
 
+@pytest.mark.parametrize("name,size,nviews", [("city", (640, 360), 6), ("castle", (1920, 1080), 5), ("castle", (512, 256), 12),
+                                              ("castle", (1280, 720), 3), ("castle", (2560, 1440), 2), ("sponza", (1920, 1080), 2)])
+def test_view_cluster_path(ctx, lut, name, size, nviews):
+    """Latency path for few views: one thread-block cluster (2-16 CTAs) per view, row-local gates
+    decided per window of candidates with one cluster barrier (k_render_views_cluster)."""
+    B = bundle(name)
+    w, h = size
+    ctx.set_cluster_views(16)
+    mvps, poss = wl.camera_path(B.ps, nviews - 1, w, h) if size[0] >= 640 else wl.probe_views(B.ps, nviews - 1, w, h)
+    m0, p0 = B.default_view(w, h)
+    mvps = np.concatenate([m0[None], mvps]); poss = np.concatenate([p0[None], poss])
+    orders = wl.orders_for(B.centers, poss)
+    boxes = B.boxes[:: max(1, len(B.boxes) // 3000)]
+    sc = B.scene(ctx, boxes)
+    n0 = ctx.launch_count
+    out = sc.render_views(w, h, mvps, orders=orders, want=("vis", "clip", "gate", "depth", "hiz", "quads"))
+    assert ctx.launch_count - n0 == 3  # prepare, cluster render, queries
+    vis = api.unpack_bits(out["vis"], len(boxes)); clip = api.unpack_bits(out["clip"], len(boxes))
+    port = po.PortRasterizer(w, h, lut)
+    for v in range(nviews):
+        gate, quads, depth, hiz, qv = port_frame(B, port, mvps[v], orders[v], boxes)
+        assert np.array_equal(out["gate"][v], gate), v
+        assert out["quads"][v] == quads
+        assert np.array_equal(out["hiz"][v], hiz), v
+        assert np.array_equal(out["depth"][v], depth), v
+        assert np.array_equal(vis[v], (qv & 1).astype(bool)), v
+        assert np.array_equal(clip[v], (qv & 2).astype(bool)), v
+    out2 = sc.render_views(w, h, mvps, cam_pos=poss, want=("vis", "gate"))
+    assert np.array_equal(out2["vis"], out["vis"])
+    assert np.array_equal(out2["gate"], out["gate"])
+    # and the batch kernel gives the same answer
+    ctx.set_cluster_views(0)
+    out3 = sc.render_views(w, h, mvps, orders=orders, want=("vis", "gate", "depth", "hiz"))
+    ctx.set_cluster_views(16)
+    for k in ("vis", "gate", "depth", "hiz"):
+        assert np.array_equal(out3[k], out[k]), k
+    sc.close(); port.close()
+
+
+@pytest.mark.parametrize("cluster", [0, 16])
 @pytest.mark.parametrize("size", [(1280, 720), (3840, 2160)])
-def test_no_gate_forced_clip_and_4k_wrap(ctx, lut, size):
+def test_no_gate_forced_clip_and_4k_wrap(ctx, lut, size, cluster):
     """Config-4 shape: every batch through rasterize<true>, no gate; 3840x2160 also exercises the
     16-bit wrap of the first-block index (Rasterizer.cpp:1054)."""
     B = bundle("castle" if wl.have_scene("castle") else "city")
     w, h = size
+    ctx.set_cluster_views(cluster)
     mvps, poss = wl.camera_path(B.ps, 2, w, h)
     orders = wl.orders_for(B.centers, poss)
     sc = B.scene(ctx, B.boxes[::7])
     out = sc.render_views(w, h, mvps, orders=orders, flags=api.BATCH_NO_GATE | api.BATCH_FORCE_CLIPPED, want=("vis", "depth", "hiz"))
+    ctx.set_cluster_views(16)
     vis = api.unpack_bits(out["vis"], len(B.boxes[::7]))
     port = po.PortRasterizer(w, h, lut)
     for v in range(2):
@@ -200,7 +244,9 @@ def test_no_gate_forced_clip_and_4k_wrap(ctx, lut, size):
     sc.close(); port.close()
 
 
-def test_soup_near_clipped(ctx, lut):
+@pytest.mark.parametrize("cluster", [0, 16])
+def test_soup_near_clipped(ctx, lut, cluster):
+    ctx.set_cluster_views(cluster)
     ps = wl.synthetic_soup(8192, cube=60.0)
     baked = [api.bake(b, ps.ref_min, ps.ref_max) for b in ps.batches]
     sc = api.Scene(ctx, [b[0] for b in baked], ps.ref_min, ps.ref_max, np.stack([b[2] for b in baked]), np.stack([b[3] for b in baked]),
@@ -224,6 +270,7 @@ def test_soup_near_clipped(ctx, lut):
                 assert np.array_equal(out["gate"][v], gate)
             assert np.array_equal(out["hiz"][v], port.hiz())
             assert np.array_equal(out["depth"][v], port.depth())
+    ctx.set_cluster_views(16)
     sc.close(); port.close()
 
 

@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librasterizer_b200.so")
+LIB_PATH = os.environ.get("ORZ_LIB") or os.path.join(HERE, "librasterizer_b200.so")  # ORZ_LIB: profiling builds (tools/)
 
 BATCH_NO_GATE = 1
 BATCH_FORCE_CLIPPED = 2

@@ -638,6 +638,11 @@ struct FrameParams {
   uint32_t viewBase, groupViews;  // this launch handles sorted ranks [viewBase, viewBase + groupViews)
   int exportDepth;      // 1: the caller reads depth back -> zero-fill blocks that stayed cleared
   uint32_t clusterK;    // cluster kernel: tiles per warp
+  // cluster path: speculative setup output per view (k_setup_views)
+  uint32_t* recBuf;     // [nViews][totalQuads][kRecStride] records, each occluder's at its quadOffset
+  uint2* hdrBuf;        // [nViews][totalQuads] bounding boxes of the records
+  uint4* recInfo;       // [nViews][nOcc][2]: {records, quadOffset, quadCount, -}, {block rectangle of all records, half open}
+  uint32_t totalQuads;
 };
 
 __global__ void __launch_bounds__(128) k_prepare_views(const FrameParams p) {
@@ -822,42 +827,121 @@ __global__ void __launch_bounds__(GW * 32, (kTrav == 2 ? ORZ_THREADS_PER_SM_V2 :
 }
 
 // ---------------------------------------------------------------------------------------------
-// Few views (BASELINE configs 1 and 2 are ONE view): a thread-block CLUSTER of C CTAs x 16 warps
-// per view instead of one CTA.  A single view is a chain of dependent gate -> setup -> traversal
-// phases (Main.cpp:192-206) and, inside one occluder, primitives stack on the same blocks (Castle,
-// default camera: up to ~300 in-order updates of one block per frame), so what counts is the
-// latency of the serial chain, not throughput:
-//   * the screen is cut into TILES of 8x4 blocks; tile t belongs to warp t mod (16 C) of the
-//     cluster for the whole view, lane <-> block.  A tile is only ever read or written by its
-//     owner (gate included): no cross-SM traffic on depth / HiZ, no atomics, order preserved;
-//   * TILE-MAJOR traversal: for each of its tiles a warp walks the occluder's primitives in order
-//     with the tile's depth held in REGISTERS (one 8x8 block = 8 x uint4 per lane) and its HiZ in
-//     a register + shared-memory mirror: a stacked primitive costs shared-memory and ALU latency
-//     only; the L2 round trip (load at first touch, store at the end) is paid once per
-//     (occluder, tile) instead of once per (primitive, block);
-//   * every CTA sets up the whole occluder redundantly (<= 504 quads = one quad per lane, one
-//     pass) but keeps only the primitives that touch one of ITS tiles, compacted in order;
-//   * the gate (queryVisibility of the occluder's box, Main.cpp:195) is evaluated tile-locally
-//     right after the traversal for a WINDOW of the next kGateWindow undecided occluders; a warp
-//     that finds a visible pixel raises that candidate's flag in the shared memory of every CTA
-//     of the cluster (DSMEM stores).  After ONE hardware cluster barrier all CTAs agree on the
-//     first visible candidate: the candidates before it were tested against exactly the buffers
-//     they would have seen sequentially (nothing was rasterised in between), so their "invisible"
-//     is final; the ones after it are tested again in the next window;
-//   * the edge-mask table (32 KB) and the rcpps table (8 KB) live in shared memory.
+// Few views (BASELINE configs 1 and 2 are ONE view): the latency path.  A single view is a chain
+// of dependent gate -> setup -> traversal steps (Main.cpp:192-206) and, inside one occluder,
+// primitives stack on the same blocks (Castle, default camera: ~300 in-order updates of one
+// block per frame), so what counts is the length of the dependency chain, not throughput.
+//
+//   k_setup_views           everything that does not depend on the depth buffer, at full width:
+//                           one CTA per (occluder that survives the frustum, view) sets up its
+//                           quads (Rasterizer.cpp:657-1086) and writes the valid primitives in
+//                           order as records + 8-byte bounding-box headers (speculative: the
+//                           gate may still reject the occluder)
+//   k_raster_views_cluster  one thread-block CLUSTER of C CTAs x 16 warps per view, run as a
+//                           DATAFLOW machine with no barrier in its main loop:
+//     * the screen is cut into TILES of 8x4 blocks; tile t belongs to warp t mod (16 C) of the
+//       cluster for the whole view, lane <-> block.  A tile is only ever read or written by its
+//       owner (gate included): no cross-SM traffic on depth / HiZ, order preserved per block;
+//     * every warp walks the occluders front to back at ITS OWN pace.  For a rectangle candidate
+//       it tests the part of the rectangle that lies on its tiles (query2D, Rasterizer.cpp:283-349)
+//       -- at that point it has applied every earlier visible occluder to those tiles, which is
+//       all the test depends on -- and either raises the candidate's `visible` flag in the shared
+//       memory of every CTA (DSMEM stores) or adds itself to the candidate's `done` count
+//       (per-CTA count, forwarded to every CTA by the CTA's last warp).  Warps whose tiles do not
+//       meet the rectangle are counted before the walk starts.  A candidate is visible as soon as
+//       ONE warp says so, invisible when all have said no: fast warps run ahead and only the true
+//       dependencies remain (sum over occluders of the slowest warp -> slowest warp's own total:
+//       660 -> 176 primitive-tile steps on the Castle default view);
+//     * TILE-MAJOR traversal: for each of its tiles a warp walks the occluder's primitives in
+//       order with the tile's depth held in REGISTERS (one 8x8 block = 8 x uint4 per lane) and
+//       its HiZ in a register + shared-memory mirror: a stacked primitive costs shared-memory and
+//       ALU latency only; the L2 round trip (load at first touch, store at the end) is paid once
+//       per (occluder, tile) instead of once per (primitive, block);
+//     * the edge-mask table (32 KB) lives in shared memory; records are gathered from L2 into a
+//       per-warp staging area 32 at a time with all loads in flight together.
 constexpr int kClusterGW = 16;
-constexpr int kGateWindow = 4;
-constexpr uint32_t kClusterRcpWords = 2048;  // rcpps tables up to 11 mantissa bits are staged in shared memory
 constexpr uint32_t kTileW = 8, kTileH = 4;   // blocks per tile: lane = 8 * (row in tile) + column in tile
+constexpr uint32_t kStageCap = 32;           // records a warp stages at a time
+constexpr uint32_t kClusterMaxOcc = 2048;    // occluders per scene the cluster path accepts (shared-memory decision arrays)
+constexpr uint32_t kHeadWords = 6;           // status, minX, maxX, minY, maxY, maxZ of kFrontWords
 
 struct ClusterSmem {
-  static constexpr uint32_t NT = kClusterGW * 32;
   static constexpr uint32_t kLutWords = 4096 * 2;
-  static constexpr uint32_t kRecWords = NT * kRecStride;
+  static constexpr uint32_t kStageWords = kClusterGW * kStageCap * kRecStride;
+  static constexpr uint32_t kIdxWords = kClusterGW * kStageCap;
   static constexpr uint32_t kChainWords = kClusterGW * 12 * 32;
-  static constexpr uint32_t kFixedWords = kLutWords + kRecWords + kChainWords + kClusterRcpWords;
-  static size_t bytes(uint32_t tilesPerWarp) { return (size_t)kFixedWords * 4 + (size_t)kClusterGW * tilesPerWarp * 32 * 2; }
+  static constexpr uint32_t kFixedWords = kLutWords + kStageWords + kIdxWords + kChainWords;
+  // + [nOcc][6] gate heads, 3 x [nOcc] decision words, [GW][K][32] u16 HiZ mirror
+  static size_t bytes(uint32_t tilesPerWarp, uint32_t nOcc) {
+    return (size_t)(kFixedWords + nOcc * (kHeadWords + 3u)) * 4 + (size_t)kClusterGW * tilesPerWarp * 32 * 2;
+  }
 };
+
+// ---- speculative setup of every occluder that survives the frustum, Rasterizer.cpp:657-1086
+__global__ void __launch_bounds__(256) k_setup_views(const FrameParams p) {
+  __shared__ uint32_t s_cnt[8];
+  __shared__ uint32_t s_box[4];
+  const uint32_t slot = blockIdx.x, view = blockIdx.y, tid = threadIdx.x;
+  const int warp = (int)(tid >> 5), lane = (int)(tid & 31u);
+  const uint32_t* fr = p.frontBuf + ((size_t)view * p.nOcc + slot) * kFrontWords;
+  const uint32_t status = fr[0];
+  if (status == kBoxCulled) {
+    if (tid == 0) p.recInfo[((size_t)view * p.nOcc + slot) * 2u] = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  const bool useGate = (p.flags & ORZ_BATCH_NO_GATE) == 0u;
+  const bool clipped = status == kBoxNearClip ? (useGate ? true : (p.flags & ORZ_BATCH_FORCE_CLIPPED) != 0u) : false;
+  const uint32_t* order = p.orders ? p.orders + (size_t)view * p.nOcc : p.orderBuf + (size_t)view * p.nOcc;
+  const OccMeta& om = p.occ[order[slot]];
+  const RcpTable rt{p.rcp, p.rcpShift};
+  CallMatrix cm;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { cm.rx[k] = u2f(fr[6 + k]); cm.ry[k] = u2f(fr[10 + k]); cm.rw[k] = u2f(fr[14 + k]); }
+  cm.c0 = u2f(fr[18]); cm.c1 = u2f(fr[19]);
+  const int32_t blocksX = (int32_t)(p.width >> 3), blocksY = (int32_t)(p.height >> 3);
+  const size_t recBase = (size_t)view * p.totalQuads + om.quadOffset;  // records of this (view, occluder) start here
+  uint32_t* recs = p.recBuf + recBase * kRecStride;
+  uint2* hdrs = p.hdrBuf + recBase;
+  if (tid < 4) s_box[tid] = tid < 2 ? 0xffffffffu : 0u;
+  uint32_t written = 0;
+  uint32_t bx0 = 0xffffffffu, by0 = 0xffffffffu, bx1 = 0u, by1 = 0u;
+  for (uint32_t q0 = 0; q0 < om.quadCount; q0 += 256u) {
+    const uint32_t qi = q0 + tid;
+    bool ok = false;
+    Prim P;
+    if (qi < om.quadCount) {
+      const uint4 v = p.quads[om.quadOffset + qi];  // 128-bit coalesced load: the four packed vertices of this lane's quad
+      const uint32_t word[4] = {v.x, v.y, v.z, v.w};
+      ok = clipped ? setup_quad<true>(word, cm, rt, c_modeNibbles, blocksX, blocksY, P)
+                   : setup_quad<false>(word, cm, rt, c_modeNibbles, blocksX, blocksY, P);
+    }
+    const uint32_t valid = __ballot_sync(kFull, ok);
+    __syncthreads();  // s_cnt of the previous chunk has been read
+    if (lane == 0) s_cnt[warp] = (uint32_t)__popc(valid);
+    __syncthreads();
+    uint32_t base = written, total = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < 8; ++w2) { const uint32_t c = s_cnt[w2]; base += w2 < warp ? c : 0u; total += c; }
+    if (ok) {  // in order: binning by prefix-sum compaction
+      const uint32_t at = base + (uint32_t)__popc(valid & ((1u << lane) - 1u));
+      store_record(recs + (size_t)at * kRecStride, P);
+      hdrs[at] = make_uint2((uint32_t)P.minX | ((uint32_t)P.minY << 16), (uint32_t)P.rangeX | ((uint32_t)P.rangeY << 16));
+      bx0 = min(bx0, (uint32_t)P.minX); by0 = min(by0, (uint32_t)P.minY);
+      bx1 = max(bx1, (uint32_t)(P.minX + P.rangeX)); by1 = max(by1, (uint32_t)(P.minY + P.rangeY));
+    }
+    written += total;
+  }
+  bx0 = __reduce_min_sync(kFull, bx0); by0 = __reduce_min_sync(kFull, by0);
+  bx1 = __reduce_max_sync(kFull, bx1); by1 = __reduce_max_sync(kFull, by1);
+  __syncthreads();
+  if (lane == 0) { atomicMin(&s_box[0], bx0); atomicMin(&s_box[1], by0); atomicMax(&s_box[2], bx1); atomicMax(&s_box[3], by1); }
+  __syncthreads();
+  if (tid == 0) {
+    p.recInfo[((size_t)view * p.nOcc + slot) * 2u] = make_uint4(written, om.quadOffset, om.quadCount, 0u);
+    // block rectangle that holds every primitive of the occluder, half open (lo > hi when there is none)
+    p.recInfo[((size_t)view * p.nOcc + slot) * 2u + 1u] = make_uint4(s_box[0], s_box[1], s_box[2], s_box[3]);
+  }
+}
 
 // one block of query2D (Rasterizer.cpp:305-343) with the block's HiZ already at hand
 __device__ __forceinline__ bool query_block_h(const Target& T, uint32_t bx, uint32_t by, uint32_t h, uint32_t minX, uint32_t maxX,
@@ -868,18 +952,6 @@ __device__ __forceinline__ bool query_block_h(const Target& T, uint32_t bx, uint
   const int sY = max((int)minY - (int)(8u * by), 0), eY = min((int)maxY - (int)(8u * by), 7);
   if (sX == 0 && eX == 7 && sY == 0 && eY == 7) return true;  // Rasterizer.cpp:319-325
   return block_fine_test(T.depth, by * T.blocksX + bx, maxZ, sX, eX, sY, eY);
-}
-
-// does the primitive's block rectangle touch a tile owned by CTA `rank` (tile t -> CTA t mod C)?
-template <int C>
-__device__ __forceinline__ bool prim_touches_rank(const Prim& P, uint32_t tilesX, uint32_t rank) {
-  const uint32_t ta = (uint32_t)P.minX / kTileW, tb = (uint32_t)(P.minX + P.rangeX - 1) / kTileW;
-  const uint32_t ua = (uint32_t)P.minY / kTileH, ub = (uint32_t)(P.minY + P.rangeY - 1) / kTileH;
-  const uint32_t n = tb - ta + 1u;
-  if (n >= (uint32_t)C) return true;
-  for (uint32_t u = ua; u <= ub; ++u)
-    if (((rank - (u * tilesX + ta)) & (uint32_t)(C - 1)) < n) return true;
-  return false;
 }
 
 // One primitive on the tile a warp has open (Rasterizer.cpp:1098-1292 restricted to the tile's
@@ -1000,31 +1072,32 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
 }
 
 template <int C>
-__global__ void __launch_bounds__(kClusterGW * 32, 1) k_render_views_cluster(const FrameParams p) {
+__global__ void __launch_bounds__(kClusterGW * 32, 1) k_raster_views_cluster(const FrameParams p) {
   constexpr uint32_t GW = kClusterGW, NT = GW * 32, kWarps = C * GW;
   extern __shared__ __align__(16) uint32_t s_dyn[];
   uint2* s_lut = reinterpret_cast<uint2*>(s_dyn);
-  uint32_t* s_recs = s_dyn + ClusterSmem::kLutWords;
-  float* s_chain = reinterpret_cast<float*>(s_dyn + ClusterSmem::kLutWords + ClusterSmem::kRecWords);
-  uint32_t* s_rcp = s_dyn + ClusterSmem::kLutWords + ClusterSmem::kRecWords + ClusterSmem::kChainWords;
-  uint16_t* s_hiz = reinterpret_cast<uint16_t*>(s_dyn + ClusterSmem::kFixedWords);  // [GW][K][32]: HiZ of the tiles my warps own
-  __shared__ uint32_t s_count[GW];
-  __shared__ uint32_t s_flag[3][kGateWindow];
+  uint32_t* s_stageAll = s_dyn + ClusterSmem::kLutWords;
+  uint32_t* s_idxAll = s_stageAll + ClusterSmem::kStageWords;
+  float* s_chain = reinterpret_cast<float*>(s_idxAll + ClusterSmem::kIdxWords);
+  uint32_t* s_head = s_dyn + ClusterSmem::kFixedWords;     // [nOcc][6]: status + gate rectangle of every order slot
+  uint32_t* s_vis = s_head + p.nOcc * kHeadWords;          // [nOcc]: some warp saw a visible pixel
+  uint32_t* s_doneLocal = s_vis + p.nOcc;                  // [nOcc]: warps of THIS CTA that answered "not on my tiles"
+  uint32_t* s_doneCta = s_doneLocal + p.nOcc;              // [nOcc]: CTAs of the cluster whose 16 warps all answered
+  uint16_t* s_hiz = reinterpret_cast<uint16_t*>(s_doneCta + p.nOcc);  // [GW][K][32]: HiZ of the tiles my warps own
 
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t rank = cluster.block_rank();
   const uint32_t view = p.viewBase + blockIdx.x / (uint32_t)C;
   const uint32_t tid = threadIdx.x;
   const int warp = (int)(tid >> 5), lane = (int)(tid & 31u);
-  const uint32_t gw = (uint32_t)warp * (uint32_t)C + rank;  // my tiles: t % kWarps == gw  (so tile t -> CTA t % C)
+  const uint32_t gw = (uint32_t)warp * (uint32_t)C + rank;  // my tiles: t % kWarps == gw
   const uint32_t K = p.clusterK;
+  const uint32_t nOcc = p.nOcc;
 
+  const uint32_t* front = p.frontBuf + (size_t)view * nOcc * kFrontWords;
   for (uint32_t i = tid; i < 4096u; i += NT) s_lut[i] = p.lut[i];
-  const uint32_t rcpWords = 1u << (23 - p.rcpShift);
-  const bool rcpStaged = rcpWords <= kClusterRcpWords;
-  if (rcpStaged) for (uint32_t i = tid; i < rcpWords; i += NT) s_rcp[i] = p.rcp[i];
-  const RcpTable rt{rcpStaged ? s_rcp : p.rcp, p.rcpShift};
-  if (tid < 3u * kGateWindow) (&s_flag[0][0])[tid] = 0u;
+  for (uint32_t i = tid; i < nOcc * kHeadWords; i += NT) s_head[i] = front[(size_t)(i / kHeadWords) * kFrontWords + i % kHeadWords];
+  for (uint32_t i = tid; i < nOcc * 3u; i += NT) s_vis[i] = 0u;
 
   Target T;
   T.width = p.width; T.height = p.height; T.blocksX = p.width >> 3; T.blocksY = p.height >> 3;
@@ -1033,162 +1106,177 @@ __global__ void __launch_bounds__(kClusterGW * 32, 1) k_render_views_cluster(con
   const uint32_t tilesX = (T.blocksX + kTileW - 1u) / kTileW, tilesY = (T.blocksY + kTileH - 1u) / kTileH, nTiles = tilesX * tilesY;
   const bool useGate = (p.flags & ORZ_BATCH_NO_GATE) == 0u;
   const bool forceClip = (p.flags & ORZ_BATCH_FORCE_CLIPPED) != 0u;
-  const uint32_t* order = p.orders ? p.orders + (size_t)view * p.nOcc : p.orderBuf + (size_t)view * p.nOcc;
-  const uint32_t* front = p.frontBuf + (size_t)view * p.nOcc * kFrontWords;
+  const uint4* recInfo = p.recInfo + (size_t)view * nOcc * 2u;
   uint16_t* myHiz = s_hiz + (size_t)warp * K * 32u + lane;  // + 32 k
   float* myChain = s_chain + warp * (12 * 32);
+  uint32_t* myStage = s_stageAll + (uint32_t)warp * kStageCap * kRecStride;
+  uint32_t* myIdx = s_idxAll + (uint32_t)warp * kStageCap;
   const uint32_t lx = (uint32_t)lane & 7u, ly = (uint32_t)lane >> 3;
+  const bool reporter = rank == 0u && warp == 0 && lane == 0;  // writes the per-slot outputs of the view
 
+  // lane k keeps the origin (in blocks) of my k-th tile; 0xffff = none
+  uint32_t tileX0 = 0xffffu, tileY0 = 0xffffu;
+  if ((uint32_t)lane < K) {
+    const uint32_t t = gw + (uint32_t)lane * kWarps;
+    if (t < nTiles) { const uint32_t ty = t / tilesX; tileX0 = (t - ty * tilesX) * kTileW; tileY0 = ty * kTileH; }
+  }
+  const uint32_t allTiles = __ballot_sync(kFull, tileX0 != 0xffffu);
   // clear (Rasterizer.cpp:107-121): HiZ := 1 on my tiles; depth is overwritten by the first update
-  for (uint32_t k = 0, t = gw; k < K && t < nTiles; ++k, t += kWarps) {
-    const uint32_t ty = t / tilesX, tx = t - ty * tilesX;
-    const uint32_t bx = tx * kTileW + lx, by = ty * kTileH + ly;
+  for (uint32_t m = allTiles; m; m &= m - 1u) {
+    const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+    const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
     myHiz[32u * k] = 1;
     if (bx < T.blocksX && by < T.blocksY) T.hiz[by * T.blocksX + bx] = 1;
   }
   __syncwarp();
-  cluster.sync();  // tables staged, flags zero in every CTA before the first remote store
+  cluster.sync();  // tables staged, decision words zero in every CTA before the first remote access
 
-  uint32_t slot = 0, phase = 0, quadsSubmitted = 0;
-  while (slot < p.nOcc) {
-    // ---- window: the next undecided occluders up to the first one that needs no test
-    uint32_t cand[kGateWindow];
-    uint32_t n = 0, end = slot;
-    bool stopNearClip = false;
-#pragma unroll 1
-    while (end < p.nOcc && n < (uint32_t)kGateWindow) {
-      const uint32_t st = front[(size_t)end * kFrontWords];
-      if (st == kBoxNearClip) { stopNearClip = true; break; }
-      if (st == kBoxRect) {
-#pragma unroll
-        for (int j = 0; j < kGateWindow; ++j) if ((uint32_t)j == n) cand[j] = end;
-        ++n;
-      }
-      ++end;
-    }
-    uint32_t target = 0xffffffffu;
-    bool clipped = false;
-    if (n > 0) {
-      uint32_t* flags = s_flag[phase % 3u];
-      if (tid < (uint32_t)kGateWindow) s_flag[(phase + 1u) % 3u][tid] = 0u;  // last read two barriers ago
-      bool earlier = false;
-#pragma unroll
-      for (int j = 0; j < kGateWindow; ++j)
-        if ((uint32_t)j < n && !earlier) {
-          // query2D (Rasterizer.cpp:283-349) of candidate j restricted to my tiles
-          const uint32_t* fr = front + (size_t)cand[j] * kFrontWords;
-          const uint32_t minX = fr[1], maxX = fr[2], minY = fr[3], maxY = fr[4], maxZ = fr[5];
-          const uint32_t bx0 = minX >> 3, bx1 = maxX >> 3, by0 = minY >> 3, by1 = maxY >> 3;
-          uint32_t* flagLocal = flags + j;
-          for (uint32_t k = 0, t = gw; k < K && t < nTiles; ++k, t += kWarps) {
-            const uint32_t ty = t / tilesX, tx = t - ty * tilesX;
-            const uint32_t x0 = tx * kTileW, y0 = ty * kTileH;
-            if (x0 > bx1 || x0 + kTileW <= bx0 || y0 > by1 || y0 + kTileH <= by0) continue;
-            if (*reinterpret_cast<volatile uint32_t*>(flagLocal)) break;  // another warp already found a visible pixel
-            const uint32_t bx = x0 + lx, by = y0 + ly;
-            const bool hit = bx >= bx0 && bx <= bx1 && by >= by0 && by <= by1 && bx < T.blocksX && by < T.blocksY &&
-                             query_block_h(T, bx, by, (uint32_t)myHiz[32u * k], minX, maxX, minY, maxY, maxZ);
-            if (__any_sync(kFull, hit)) {
-              if (lane < C) *cluster.map_shared_rank(flagLocal, (unsigned)lane) = 1u;
-              break;
-            }
-          }
-          earlier = *reinterpret_cast<volatile uint32_t*>(flagLocal) != 0u;  // a later candidate's answer would be discarded
-        }
-      cluster.sync();
-      ++phase;
-#pragma unroll
-      for (int j = kGateWindow - 1; j >= 0; --j)
-        if ((uint32_t)j < n && flags[j]) target = cand[j];
-    }
-    if (target == 0xffffffffu && stopNearClip) { target = end; clipped = useGate ? true : forceClip; }
-    const uint32_t decided = target == 0xffffffffu ? end : target + 1u;  // slots [slot, decided) now have their answer
-    if (p.gate && rank == 0u)
-      for (uint32_t s = slot + tid; s < decided; s += NT)
-        p.gate[(size_t)view * p.nOcc + s] = s == target ? (uint8_t)(1 | (clipped && useGate ? 2 : 0)) : (uint8_t)0;
-    slot = decided;
-    if (target == 0xffffffffu) continue;
+  // "no visible pixel on my tiles" for candidate s: per-CTA count, forwarded by the CTA's last warp
+  auto answer_no = [&](uint32_t s) {
+    uint32_t old = 0u;
+    if (lane == 0) old = atomicAdd(&s_doneLocal[s], 1u);
+    old = __shfl_sync(kFull, old, 0);
+    if (old == GW - 1u && lane < C) atomicAdd(cluster.map_shared_rank(&s_doneCta[s], (unsigned)lane), 1u);
+  };
+  // my tiles that meet the block rectangle [bx0, bx1] x [by0, by1] (inclusive), as a mask over k
+  auto tiles_meeting = [&](uint32_t bx0, uint32_t bx1, uint32_t by0, uint32_t by1) -> uint32_t {
+    return __ballot_sync(kFull, tileX0 != 0xffffu && tileX0 <= bx1 && tileX0 + kTileW > bx0 && tileY0 <= by1 && tileY0 + kTileH > by0);
+  };
 
-    // ---- rasterize<clipped>(occluder)
-    const uint32_t* fr = front + (size_t)target * kFrontWords;
-    const OccMeta& om = p.occ[order[target]];
-    const uint4* quads = p.quads + om.quadOffset;
-    const uint32_t nq = om.quadCount;
-    quadsSubmitted += nq;
-    CallMatrix cm;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { cm.rx[k] = u2f(fr[6 + k]); cm.ry[k] = u2f(fr[10 + k]); cm.rw[k] = u2f(fr[14 + k]); }
-    cm.c0 = u2f(fr[18]); cm.c1 = u2f(fr[19]);
-    for (uint32_t q0 = 0; q0 < nq; q0 += NT) {
-      // setup (Rasterizer.cpp:657-1086): one quad per lane; keep what touches a tile of this CTA
-      const uint32_t qi = q0 + tid;
-      bool ok = false;
-      Prim P;
-      if (qi < nq) {
-        const uint4 v = quads[qi];
-        const uint32_t word[4] = {v.x, v.y, v.z, v.w};
-        ok = clipped ? setup_quad<true>(word, cm, rt, c_modeNibbles, (int32_t)T.blocksX, (int32_t)T.blocksY, P)
-                     : setup_quad<false>(word, cm, rt, c_modeNibbles, (int32_t)T.blocksX, (int32_t)T.blocksY, P);
-        if (ok) ok = prim_touches_rank<C>(P, tilesX, rank);
-      }
-      const uint32_t valid = __ballot_sync(kFull, ok);
-      if (lane == 0) s_count[warp] = (uint32_t)__popc(valid);
-      __syncthreads();  // also: every warp is done with the previous chunk's records
-      uint32_t base = 0, total = 0;
-#pragma unroll
-      for (int w2 = 0; w2 < (int)GW; ++w2) { const uint32_t c = s_count[w2]; base += w2 < warp ? c : 0u; total += c; }
-      if (ok) store_record(s_recs + (base + (uint32_t)__popc(valid & ((1u << lane) - 1u))) * kRecStride, P);  // in order
-      __syncthreads();
-
-      // ---- tile-major traversal: my tiles, each with the primitives that touch it, in order
-      if (total)
-        for (uint32_t k = 0, t = gw; k < K && t < nTiles; ++k, t += kWarps) {
-          const uint32_t ty = t / tilesX, tx = t - ty * tilesX;
-          const uint32_t x0 = tx * kTileW, y0 = ty * kTileH;
-          const uint32_t x1 = min(x0 + kTileW, T.blocksX), y1 = min(y0 + kTileH, T.blocksY);
-          const uint32_t bx = x0 + lx, by = y0 + ly;
-          const bool inScreen = bx < x1 && by < y1;
-          uint4* dp = reinterpret_cast<uint4*>(T.depth) + (size_t)(by * T.blocksX + bx) * 8u;
-          uint4 d[8];
-          uint32_t h = 0xffffu;
-          bool open = false, dirty = false;
-          for (uint32_t r0 = 0; r0 < total; r0 += 32u) {
-            bool touches = false;
-            if (r0 + (uint32_t)lane < total) {
-              const uint32_t* rec = s_recs + (r0 + (uint32_t)lane) * kRecStride;
-              const uint32_t a = rec[0], b = rec[1];
-              const uint32_t minX = a & 0xffffu, minY = a >> 16;
-              touches = minX < x1 && minX + (b & 0xffffu) > x0 && minY < y1 && minY + (b >> 16) > y0;
-            }
-            uint32_t hits = __ballot_sync(kFull, touches);
-            while (hits) {
-              const uint32_t i = (uint32_t)__ffs((int)hits) - 1u;
-              hits &= hits - 1u;
-              if (!open) {  // first primitive on this tile: bring the tile into registers
-                open = true;
-                h = inScreen ? (uint32_t)myHiz[32u * k] : 0xffffu;  // off-screen lanes never pass
-                const bool load = inScreen && h != 1u;
-#pragma unroll
-                for (int y = 0; y < 8; ++y) d[y] = load ? dp[y] : make_uint4(0u, 0u, 0u, 0u);
-              }
-              tile_prim(s_recs + (r0 + i) * kRecStride, lane, x0, y0, x1, y1, s_lut, myChain, d, h, dirty);
-            }
-          }
-          if (dirty) {
-#pragma unroll
-            for (int y = 0; y < 8; ++y) dp[y] = d[y];
-            myHiz[32u * k] = (uint16_t)h;
-            T.hiz[by * T.blocksX + bx] = (uint16_t)h;
-          }
-        }
-    }
+  // ---- candidates whose rectangle does not touch my tiles: answered before the walk starts
+  for (uint32_t s = 0; s < nOcc; ++s) {
+    const uint32_t* hd = s_head + s * kHeadWords;
+    if (hd[0] != kBoxRect) continue;
+    if (!tiles_meeting(hd[1] >> 3, hd[2] >> 3, hd[3] >> 3, hd[4] >> 3)) answer_no(s);
   }
-  if (p.quadsSubmitted && rank == 0u && tid == 0u) p.quadsSubmitted[view] = quadsSubmitted;
+
+  uint32_t quadsSubmitted = 0;
+  for (uint32_t s = 0; s < nOcc; ++s) {
+    const uint32_t* hd = s_head + s * kHeadWords;
+    const uint32_t status = hd[0];
+    if (status == kBoxCulled) {
+      if (p.gate && reporter) p.gate[(size_t)view * nOcc + s] = 0;
+      continue;
+    }
+    const uint4 info = recInfo[2u * s], box = recInfo[2u * s + 1u];  // requested now, needed after the gate
+    bool visible = true, clipped = false;
+    if (status == kBoxNearClip) {
+      clipped = useGate ? true : forceClip;
+    } else {
+      // ---- gate: query2D (Rasterizer.cpp:283-349) on the part of the rectangle that lies on my tiles
+      const uint32_t minX = hd[1], maxX = hd[2], minY = hd[3], maxY = hd[4], maxZ = hd[5];
+      const uint32_t bx0 = minX >> 3, bx1 = maxX >> 3, by0 = minY >> 3, by1 = maxY >> 3;
+      volatile uint32_t* vis = s_vis + s;
+      uint32_t tm = tiles_meeting(bx0, bx1, by0, by1);
+      if (tm && !*vis) {
+        bool found = false;
+        for (; tm; tm &= tm - 1u) {
+          const uint32_t k = (uint32_t)__ffs((int)tm) - 1u;
+          const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
+          if (*vis) break;  // another warp already found a visible pixel
+          const bool hit = bx >= bx0 && bx <= bx1 && by >= by0 && by <= by1 && bx < T.blocksX && by < T.blocksY &&
+                           query_block_h(T, bx, by, (uint32_t)myHiz[32u * k], minX, maxX, minY, maxY, maxZ);
+          if (__any_sync(kFull, hit)) { found = true; break; }
+        }
+        if (found) { if (lane < C) *cluster.map_shared_rank(s_vis + s, (unsigned)lane) = 1u; }
+        else if (!*vis) answer_no(s);
+      }
+      // visible as soon as ONE warp says so, invisible when all 16 C warps have said no
+      volatile uint32_t* done = s_doneCta + s;
+      for (;;) {
+        if (*vis) break;
+        if (*done >= (uint32_t)C) { visible = *vis != 0u; break; }
+        __nanosleep(32);
+      }
+    }
+    if (reporter) {
+      if (p.gate) p.gate[(size_t)view * nOcc + s] = (uint8_t)((visible ? 1 : 0) | (clipped && useGate ? 2 : 0));
+      if (visible) quadsSubmitted += info.z;
+    }
+    if (!visible || info.x == 0u) continue;
+
+    // ---- rasterize<clipped>(occluder): the records k_setup_views wrote, on my tiles
+    uint32_t tmOcc = 0u;
+    if (box.x < box.z) tmOcc = tiles_meeting(box.x, box.z - 1u, box.y, box.w - 1u);
+    if (!tmOcc) continue;
+    const uint32_t cnt = info.x;
+    const size_t recBase = (size_t)view * p.totalQuads + info.y;
+    const uint32_t* recs = p.recBuf + recBase * kRecStride;
+    const uint2* hdrs = p.hdrBuf + recBase;
+    if ((uint32_t)lane * 16u < cnt) prefetch_l1(hdrs + (uint32_t)lane * 16u);  // <= 504 headers = 32 lines
+
+    uint32_t nStaged = 0;
+    // staged records -> my tiles, tile-major, each tile's primitives in order
+    auto flush = [&]() {
+      __syncwarp();
+#pragma unroll 8
+      for (uint32_t i = 0; i < nStaged; ++i)
+        if (lane < kRecStride) myStage[i * kRecStride + lane] = recs[(size_t)myIdx[i] * kRecStride + lane];
+      __syncwarp();
+      for (uint32_t m = tmOcc; m; m &= m - 1u) {
+        const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+        const uint32_t x0 = __shfl_sync(kFull, tileX0, (int)k), y0 = __shfl_sync(kFull, tileY0, (int)k);
+        const uint32_t x1 = min(x0 + kTileW, T.blocksX), y1 = min(y0 + kTileH, T.blocksY);
+        bool touches = false;
+        if ((uint32_t)lane < nStaged) {
+          const uint32_t a = myStage[lane * kRecStride], b = myStage[lane * kRecStride + 1];
+          const uint32_t minX = a & 0xffffu, minY = a >> 16;
+          touches = minX < x1 && minX + (b & 0xffffu) > x0 && minY < y1 && minY + (b >> 16) > y0;
+        }
+        uint32_t hits = __ballot_sync(kFull, touches);
+        if (!hits) continue;
+        // bring the tile into registers
+        const uint32_t bx = x0 + lx, by = y0 + ly;
+        const bool inScreen = bx < x1 && by < y1;
+        uint4* dp = reinterpret_cast<uint4*>(T.depth) + (size_t)(by * T.blocksX + bx) * 8u;
+        uint32_t h = inScreen ? (uint32_t)myHiz[32u * k] : 0xffffu;  // off-screen lanes never pass
+        const bool load = inScreen && h != 1u;
+        uint4 d[8];
+#pragma unroll
+        for (int y = 0; y < 8; ++y) d[y] = load ? dp[y] : make_uint4(0u, 0u, 0u, 0u);
+        bool dirty = false;
+        for (; hits; hits &= hits - 1u)
+          tile_prim(myStage + ((uint32_t)__ffs((int)hits) - 1u) * kRecStride, lane, x0, y0, x1, y1, s_lut, myChain, d, h, dirty);
+        if (dirty) {
+#pragma unroll
+          for (int y = 0; y < 8; ++y) dp[y] = d[y];
+          myHiz[32u * k] = (uint16_t)h;
+          T.hiz[by * T.blocksX + bx] = (uint16_t)h;
+        }
+      }
+      __syncwarp();
+      nStaged = 0;
+    };
+    for (uint32_t r0 = 0; r0 < cnt; r0 += 32u) {
+      uint32_t hx0 = 0, hx1 = 0, hy0 = 0, hy1 = 0;  // empty
+      if (r0 + (uint32_t)lane < cnt) {
+        const uint2 hdr = hdrs[r0 + (uint32_t)lane];
+        hx0 = hdr.x & 0xffffu; hy0 = hdr.x >> 16; hx1 = hx0 + (hdr.y & 0xffffu); hy1 = hy0 + (hdr.y >> 16);
+      }
+      bool touches = false;
+      for (uint32_t m = tmOcc; m; m &= m - 1u) {
+        const int k = __ffs((int)m) - 1;
+        const uint32_t x0 = __shfl_sync(kFull, tileX0, k), y0 = __shfl_sync(kFull, tileY0, k);
+        touches = touches || (hx0 < x0 + kTileW && hx1 > x0 && hy0 < y0 + kTileH && hy1 > y0);
+      }
+      uint32_t hits = __ballot_sync(kFull, touches);
+      while (hits) {
+        const uint32_t take = min(kStageCap - nStaged, (uint32_t)__popc(hits));
+        const uint32_t myRank = (uint32_t)__popc(hits & ((1u << lane) - 1u));
+        if (((hits >> lane) & 1u) && myRank < take) myIdx[nStaged + myRank] = r0 + (uint32_t)lane;
+        for (uint32_t i = 0; i < take; ++i) hits &= hits - 1u;
+        nStaged += take;
+        if (nStaged == kStageCap) flush();
+      }
+    }
+    if (nStaged) flush();
+  }
+  if (p.quadsSubmitted && reporter) p.quadsSubmitted[view] = quadsSubmitted;
   if (p.exportDepth) {  // canonical depth for the caller: blocks that stayed cleared read as zero
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    for (uint32_t k = 0, t = gw; k < K && t < nTiles; ++k, t += kWarps) {
-      const uint32_t ty = t / tilesX, tx = t - ty * tilesX;
-      const uint32_t bx = tx * kTileW + lx, by = ty * kTileH + ly;
+    for (uint32_t m = allTiles; m; m &= m - 1u) {
+      const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+      const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
       if (bx < T.blocksX && by < T.blocksY && myHiz[32u * k] == 1) {
         uint4* d4 = reinterpret_cast<uint4*>(T.depth) + (size_t)(by * T.blocksX + bx) * 8u;
 #pragma unroll
@@ -1196,6 +1284,7 @@ __global__ void __launch_bounds__(kClusterGW * 32, 1) k_render_views_cluster(con
       }
     }
   }
+  cluster.sync();  // no CTA may leave while another one can still write its decision words
 }
 
 // queryVisibility for every (view, occludee box) on the finished buffers; Rasterizer.cpp:123-349
@@ -1928,13 +2017,16 @@ static int occupancy_views(int GW, int trav, int* perSM) {
 template <int C>
 static int launch_cluster_t(orz_context* ctx, FrameParams p, uint32_t nViews, uint32_t nTiles, cudaStream_t st) {
   p.clusterK = (nTiles + (uint32_t)(C * kClusterGW) - 1u) / (uint32_t)(C * kClusterGW);
-  const size_t smem = ClusterSmem::bytes(p.clusterK);
+  const size_t smem = ClusterSmem::bytes(p.clusterK, p.nOcc);
   static size_t configured[64] = {0};
   if (configured[ctx->device & 63] < smem) {
-    ORZ_CUDA(cudaFuncSetAttribute(k_render_views_cluster<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (C > 8) ORZ_CUDA(cudaFuncSetAttribute(k_render_views_cluster<C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    ORZ_CUDA(cudaFuncSetAttribute(k_raster_views_cluster<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (C > 8) ORZ_CUDA(cudaFuncSetAttribute(k_raster_views_cluster<C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     configured[ctx->device & 63] = smem;
   }
+  k_setup_views<<<dim3(p.nOcc, nViews), 256, 0, st>>>(p);
+  ctx->launches++;
+  ORZ_CUDA(cudaGetLastError());
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(nViews * (uint32_t)C);
@@ -1946,7 +2038,7 @@ static int launch_cluster_t(orz_context* ctx, FrameParams p, uint32_t nViews, ui
   at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  ORZ_CUDA(cudaLaunchKernelEx(&cfg, k_render_views_cluster<C>, p));
+  ORZ_CUDA(cudaLaunchKernelEx(&cfg, k_raster_views_cluster<C>, p));
   ctx->launches++;
   return ORZ_OK;
 }
@@ -2036,7 +2128,8 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
     p.viewCost = (uint32_t*)(prep + chunk * sizeof(ViewMatrices) + chunk * nOcc * 4 + chunk * nOcc * kFrontWords * 4);
     const bool wide = (b->flags & ORZ_BATCH_NO_GATE) && ((b->flags & ORZ_BATCH_WIDE) || (nv <= 8u && scene->totalQuads >= 65536u));
     // (above 65 536 blocks the reference's 16-bit index wrap needs the linear traversal of the batch kernel)
-    const bool clusterPath = !wide && ctx->clusterViews > 0 && nv <= (uint32_t)ctx->clusterViews && blocks <= 65536u;
+    const bool clusterPath = !wide && ctx->clusterViews > 0 && nv <= (uint32_t)ctx->clusterViews && blocks <= 65536u && nOcc <= kClusterMaxOcc &&
+                             (size_t)nv * scene->totalQuads * (kRecStride * 4 + 8) <= (size_t(2) << 30);
     p.viewOrder = (nv <= 16384u && !clusterPath) ? p.viewCost + chunk : nullptr;
     k_prepare_views<<<nv, 128, 0, ctx->stream>>>(p);
     ctx->launches++;
@@ -2086,6 +2179,12 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
     if (clusterPath) {
       FrameParams pc = p;
       pc.viewOrder = nullptr; pc.viewBase = 0; pc.groupViews = nv;
+      const size_t recBytes = (size_t)nv * scene->totalQuads * kRecStride * 4, hdrBytes = (size_t)nv * scene->totalQuads * 8;
+      if ((e = ensure_scratch(ctx, 11, recBytes + hdrBytes + (size_t)nv * nOcc * 32 + 64))) return e;
+      pc.hdrBuf = (uint2*)ctx->d_scratch[11];
+      pc.recInfo = (uint4*)((uint8_t*)ctx->d_scratch[11] + ((hdrBytes + 15) & ~size_t(15)));
+      pc.recBuf = (uint32_t*)((uint8_t*)pc.recInfo + (size_t)nv * nOcc * 32);
+      pc.totalQuads = scene->totalQuads;
       if ((e = launch_cluster(ctx, pc, nv, ctx->stream))) return e;
       if (p.visBits || p.clipBits) {
         k_query_views<<<dim3((scene->nBoxes + 255) / 256, nv), 256, 0, ctx->stream>>>(pc);

@@ -183,8 +183,8 @@ def test_view_batch(ctx, lut, name, size, nviews, gw, trav):
 @pytest.mark.parametrize("name,size,nviews", [("city", (640, 360), 6), ("castle", (1920, 1080), 5), ("castle", (512, 256), 12),
                                               ("castle", (1280, 720), 3), ("castle", (2560, 1440), 2), ("sponza", (1920, 1080), 2)])
 def test_view_cluster_path(ctx, lut, name, size, nviews):
-    """Latency path for few views: one thread-block cluster (2-16 CTAs) per view, row-local gates
-    decided per window of candidates with one cluster barrier (k_render_views_cluster)."""
+    """Latency path for few views: speculative setup kernel + one thread-block cluster (2-16 CTAs) per
+    view run as a dataflow machine (tile-local gates, DSMEM decision flags, k_raster_views_cluster)."""
     B = bundle(name)
     w, h = size
     ctx.set_cluster_views(16)
@@ -196,7 +196,7 @@ def test_view_cluster_path(ctx, lut, name, size, nviews):
     sc = B.scene(ctx, boxes)
     n0 = ctx.launch_count
     out = sc.render_views(w, h, mvps, orders=orders, want=("vis", "clip", "gate", "depth", "hiz", "quads"))
-    assert ctx.launch_count - n0 == 3  # prepare, cluster render, queries
+    assert ctx.launch_count - n0 == 4  # prepare, speculative setup, cluster raster, queries
     vis = api.unpack_bits(out["vis"], len(boxes)); clip = api.unpack_bits(out["clip"], len(boxes))
     port = po.PortRasterizer(w, h, lut)
     for v in range(nviews):

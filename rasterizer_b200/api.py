@@ -57,6 +57,7 @@ EXPORTS = {
     "orz_context_set_group_warps": (C.c_int, [C.c_void_p, C.c_int]),
     "orz_context_set_arena_bytes": (C.c_int, [C.c_void_p, C.c_size_t]),
     "orz_context_set_cluster_views": (C.c_int, [C.c_void_p, C.c_int]),
+    "orz_context_set_cluster_size": (C.c_int, [C.c_void_p, C.c_int]),
     "orz_context_set_traversal": (C.c_int, [C.c_void_p, C.c_int]),
     "orz_edge_mask_table": (C.c_int, [C.c_void_p]),
     "orz_probe_host_rcp": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -184,6 +185,9 @@ class Context:
 
     def set_cluster_views(self, max_views: int):
         _check(lib().orz_context_set_cluster_views(self.h, max_views))
+
+    def set_cluster_size(self, ctas: int):
+        _check(lib().orz_context_set_cluster_size(self.h, ctas))
 
     def set_arena_bytes(self, nbytes: int):
         _check(lib().orz_context_set_arena_bytes(self.h, nbytes))

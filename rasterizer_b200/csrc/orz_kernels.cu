@@ -954,6 +954,21 @@ __device__ __forceinline__ bool query_block_h(const Target& T, uint32_t bx, uint
   return block_fine_test(T.depth, by * T.blocksX + bx, maxZ, sX, eX, sY, eY);
 }
 
+// One iterated chain for one tile row: `ny` y steps, `nPre` x steps up to tile column cA, then the
+// values at tile columns [cA, cB] go to out[c].  Trip counts are warp uniform (nyMax >= ny); every
+// add is the reference's own (same operands, same order), only lanes differ in what they own.
+__device__ __forceinline__ void step_chain(float cur, const float incX, const float incY, const uint32_t ny, const uint32_t nyMax,
+                                           const uint32_t nPre, const uint32_t cA, const uint32_t cB, const bool active, float* out) {
+#pragma unroll 2
+  for (uint32_t i = 0; i < nyMax; ++i) cur = i < ny ? cur + incY : cur;  // Rasterizer.cpp:1130-1131
+#pragma unroll 4
+  for (uint32_t i = 0; i < nPre; ++i) cur = incX + cur;                    // Rasterizer.cpp:1145-1146
+  for (uint32_t c = cA; c <= cB; ++c) {
+    if (active) out[c] = cur;
+    cur = incX + cur;
+  }
+}
+
 // One primitive on the tile a warp has open (Rasterizer.cpp:1098-1292 restricted to the tile's
 // blocks).  d[8] / h are the lane's block and its HiZ, kept in registers between primitives.
 __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, const int lane, const uint32_t x0, const uint32_t y0,
@@ -967,33 +982,21 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
   const uint32_t passMask = __ballot_sync(kFull, pass);
   if (!passMask) return;  // the whole tile is behind its HiZ: no chain has to be stepped at all
 
-  // ---- the 12 iterated add chains (4 edge offsets, 8 depth lanes), one per lane 0-11, stepped
-  // exactly as the reference does: y chain from the primitive's first row (Rasterizer.cpp:1130),
-  // x chain restarted at every row start (:1136, :1145); values are published for the blocks that
-  // passed, up to the last one of each tile row
+  // ---- the iterated add chains, stepped exactly as the reference does: y chain from the
+  // primitive's first row (Rasterizer.cpp:1130), x chain restarted at every row start (:1136,
+  // :1145).  One lane per (chain, tile row): first the 4 edge offsets x 4 rows (16 lanes); the
+  // 8 depth chains x 4 rows (32 lanes) only when some block is really covered.
   const float dzdx = u2f(rec[3]), dzdy = u2f(rec[4]);
-  float cur = 0.0f, incX = 0.0f, incY = 0.0f;
-  if (lane < 4) { cur = u2f(rec[14 + lane]); incX = u2f(rec[6 + lane]); incY = u2f(rec[10 + lane]); }
-  else if (lane < 12) {
-    const int l = lane - 4;
-    const float s = -0.5f + 1.0f / 16.0f;
-    cur = ORZ_FMA(dzdx, s + 0.125f * (float)(l & 3), ORZ_FMA(dzdy, (l >> 2) ? s + 0.125f : s, u2f(rec[5])));
-    incX = dzdx; incY = dzdy;
-  }
-  for (uint32_t i = minY; i < ya; ++i) cur = cur + incY;
-  const uint32_t rLast = (31u - (uint32_t)__clz((int)passMask)) >> 3;
-  for (uint32_t r = ya - y0; r <= rLast; ++r) {
-    const uint32_t rowBits = (passMask >> (8u * r)) & 0xffu;
-    if (rowBits) {
-      const uint32_t cFirst = (uint32_t)__ffs((int)rowBits) - 1u, cLast = 31u - (uint32_t)__clz((int)rowBits);
-      float run = cur;
-      for (uint32_t i = minX; i < x0 + cFirst; ++i) run = incX + run;
-      for (uint32_t c = cFirst; c <= cLast; ++c) {
-        if (lane < 12) sm[lane * 32 + (int)(r * 8u + c)] = run;
-        run = incX + run;
-      }
-    }
-    cur = cur + incY;
+  const uint32_t rFirst = ya - y0;
+  {
+    const uint32_t rLast = (31u - (uint32_t)__clz((int)passMask)) >> 3;
+    const uint32_t cols = (passMask | (passMask >> 8) | (passMask >> 16) | (passMask >> 24)) & 0xffu;
+    const uint32_t cA = (uint32_t)__ffs((int)cols) - 1u, cB = 31u - (uint32_t)__clz((int)cols);
+    const uint32_t r = (uint32_t)lane >> 2, e = (uint32_t)lane & 3u;
+    const bool active = lane < 16 && r >= rFirst && r <= rLast;
+    float cur = 0.0f, incX = 0.0f, incY = 0.0f;
+    if (active) { cur = u2f(rec[14 + e]); incX = u2f(rec[6 + e]); incY = u2f(rec[10 + e]); }
+    step_chain(cur, incX, incY, y0 + r - minY, y0 + rLast - minY, x0 + cA - minX, cA, cB, active, sm + e * 32u + r * 8u);
   }
   __syncwarp();
 
@@ -1025,6 +1028,19 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
       upd = (mk.x | mk.y) != 0u;
     }
   }
+  const uint32_t updMask = __ballot_sync(kFull, upd);
+  if (!updMask) return;  // every lane has consumed its edge slots: `upd` depends on them
+  {  // the eight depth lanes (Rasterizer.cpp:1103-1112) at the covered blocks
+    const uint32_t rLast = (31u - (uint32_t)__clz((int)updMask)) >> 3, rLo = ((uint32_t)__ffs((int)updMask) - 1u) >> 3;
+    const uint32_t cols = (updMask | (updMask >> 8) | (updMask >> 16) | (updMask >> 24)) & 0xffu;
+    const uint32_t cA = (uint32_t)__ffs((int)cols) - 1u, cB = 31u - (uint32_t)__clz((int)cols);
+    const uint32_t r = (uint32_t)lane >> 3, l = (uint32_t)lane & 7u;
+    const bool active = r >= rLo && r <= rLast;
+    const float s = -0.5f + 1.0f / 16.0f;
+    const float cur = ORZ_FMA(dzdx, s + 0.125f * (float)(l & 3u), ORZ_FMA(dzdy, (l >> 2) ? s + 0.125f : s, u2f(rec[5])));
+    step_chain(cur, dzdx, dzdy, y0 + r - minY, y0 + rLast - minY, x0 + cA - minX, cA, cB, active, sm + (4u + l) * 32u + r * 8u);
+  }
+  __syncwarp();
   // ---- depth rows, merge into the registers, HiZ (Rasterizer.cpp:1241-1290)
   if (upd) {
     const float* smd = sm + 4 * 32 + lane;
@@ -1597,7 +1613,8 @@ struct orz_context {
   uint64_t launches = 0;
   int groupWarps = 0;
   int traversal = 2;  // 1 = warp per block, 2 = lane per block (default)
-  int clusterViews = 16;  // batches of at most this many views run one thread-block cluster per view (0 = never)
+  int clusterViews = 128;  // batches of at most this many views run one thread-block cluster per view (0 = never)
+  int clusterSize = 0;     // CTAs per cluster (2, 4, 8, 16); 0 = automatic
   // grow-only device scratch
   uint32_t* d_counter = nullptr;
   void* d_scratch[12] = {nullptr};
@@ -1701,6 +1718,11 @@ extern "C" int orz_context_set_traversal(orz_context* ctx, int mapping) {
 extern "C" int orz_context_set_cluster_views(orz_context* ctx, int maxViews) {
   if (!ctx || maxViews < 0) return fail(ORZ_ERR_ARG, "orz_context_set_cluster_views: bad arguments");
   ctx->clusterViews = maxViews;
+  return ORZ_OK;
+}
+extern "C" int orz_context_set_cluster_size(orz_context* ctx, int ctas) {
+  if (!ctx || (ctas != 0 && ctas != 2 && ctas != 4 && ctas != 8 && ctas != 16)) return fail(ORZ_ERR_ARG, "cluster size must be 0, 2, 4, 8 or 16");
+  ctx->clusterSize = ctas;
   return ORZ_OK;
 }
 extern "C" int orz_context_set_arena_bytes(orz_context* ctx, size_t bytes) {
@@ -2042,13 +2064,21 @@ static int launch_cluster_t(orz_context* ctx, FrameParams p, uint32_t nViews, ui
   ctx->launches++;
   return ORZ_OK;
 }
-// one cluster per view; cluster size from the number of 8x4-block tiles (about 4 tiles per warp, 16 warps per CTA)
+// one cluster per view.  Cluster size: as many CTAs as the view can use (one tile per warp) while all
+// views of the batch still fit the GPU in one wave; at least enough that a warp owns <= 32 tiles.
 static int launch_cluster(orz_context* ctx, const FrameParams& p, uint32_t nViews, cudaStream_t st) {
   const uint32_t nTiles = (((p.width >> 3) + kTileW - 1u) / kTileW) * (((p.height >> 3) + kTileH - 1u) / kTileH);
-  if (nTiles > 512u) return launch_cluster_t<16>(ctx, p, nViews, nTiles, st);
-  if (nTiles > 256u) return launch_cluster_t<8>(ctx, p, nViews, nTiles, st);
-  if (nTiles > 128u) return launch_cluster_t<4>(ctx, p, nViews, nTiles, st);
-  return launch_cluster_t<2>(ctx, p, nViews, nTiles, st);
+  uint32_t c = 2;
+  while (c < 16u && c * kClusterGW < nTiles && nViews * c * 2u <= (uint32_t)ctx->numSMs) c *= 2u;
+  while (c < 16u && (nTiles + c * kClusterGW - 1u) / (c * kClusterGW) > 32u) c *= 2u;
+  if (ctx->clusterSize) c = (uint32_t)ctx->clusterSize;
+  if ((nTiles + c * kClusterGW - 1u) / (c * kClusterGW) > 32u) return fail(ORZ_ERR_ARG, "cluster path: target too large for this cluster size");
+  switch (c) {
+    case 16: return launch_cluster_t<16>(ctx, p, nViews, nTiles, st);
+    case 8: return launch_cluster_t<8>(ctx, p, nViews, nTiles, st);
+    case 4: return launch_cluster_t<4>(ctx, p, nViews, nTiles, st);
+    default: return launch_cluster_t<2>(ctx, p, nViews, nTiles, st);
+  }
 }
 
 // Device-pointer entry: three launches per chunk of views (prepare, render, query).  When the
@@ -2129,7 +2159,7 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
     const bool wide = (b->flags & ORZ_BATCH_NO_GATE) && ((b->flags & ORZ_BATCH_WIDE) || (nv <= 8u && scene->totalQuads >= 65536u));
     // (above 65 536 blocks the reference's 16-bit index wrap needs the linear traversal of the batch kernel)
     const bool clusterPath = !wide && ctx->clusterViews > 0 && nv <= (uint32_t)ctx->clusterViews && blocks <= 65536u && nOcc <= kClusterMaxOcc &&
-                             (size_t)nv * scene->totalQuads * (kRecStride * 4 + 8) <= (size_t(2) << 30);
+                             (size_t)nv * scene->totalQuads * (kRecStride * 4 + 8) <= (size_t(8) << 30);
     p.viewOrder = (nv <= 16384u && !clusterPath) ? p.viewCost + chunk : nullptr;
     k_prepare_views<<<nv, 128, 0, ctx->stream>>>(p);
     ctx->launches++;

@@ -17,6 +17,8 @@ def main():
     res = {}
     sweep = [int(x) for x in os.environ.get('FEW_VIEWS_NV', '1,2,4,8,16,18,32,36,64,128').split(',')]
     paths = [("cluster", 1 << 20), ("cta", 0)] if not os.environ.get('FEW_VIEWS_ONLY_CLUSTER') else [("cluster", 1 << 20)]
+    if os.environ.get('FEW_VIEWS_CSWEEP'):
+        paths = [("cluster", 1 << 20)] + [(f"c{c}", -c) for c in (2, 4, 8, 16)]
     for nv in sweep:
         mvps, poss = wl.camera_path(ps, nv, w, h)
         d_mvp, d_pos = torch.from_numpy(mvps).to(dev), torch.from_numpy(poss).to(dev)
@@ -27,7 +29,8 @@ def main():
         row = {}
         keep = None
         for label, cv in paths:
-            ctx.set_cluster_views(cv)
+            ctx.set_cluster_size(-cv if cv < 0 else 0)
+            ctx.set_cluster_views(1 << 20 if cv < 0 else cv)
             for _ in range(3): sc.render_views_raw(b, device=True)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -39,6 +42,7 @@ def main():
             got = (d_vis.cpu().numpy().copy(), d_hiz.cpu().numpy().copy())
             if keep is None: keep = got
             else: row["same"] = bool(np.array_equal(keep[0], got[0]) and np.array_equal(keep[1], got[1]))
+        row = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in row.items()}
         row["cluster_views_per_s"] = nv / row["cluster_ms"] * 1e3
         if "cta_ms" in row: row["cta_views_per_s"] = nv / row["cta_ms"] * 1e3
         res[nv] = row

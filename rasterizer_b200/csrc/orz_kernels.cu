@@ -40,6 +40,12 @@
 #ifndef ORZ_V2_PRELOAD
 #define ORZ_V2_PRELOAD 1  // lane-per-block update: 1 = load all 8 rows up front (32 registers), 0 = L1 prefetch + row-wise loads
 #endif
+#ifndef ORZ_VAR_UNROLL
+#define ORZ_VAR_UNROLL 4  // unroll of the chain stepping loops (1, 2, 8 measured: 4 is best)
+#endif
+#ifndef ORZ_SPIN_NAP
+#define ORZ_SPIN_NAP 32  // ns a warp sleeps between two looks at a gate decision (0 = pure spin)
+#endif
 #ifndef ORZ_THREADS_PER_SM_V2
 #define ORZ_THREADS_PER_SM_V2 512  // same, for the lane-per-block traversal (register cap 128)
 #endif
@@ -53,6 +59,7 @@ namespace cg = cooperative_groups;
 __constant__ uint32_t c_modeNibbles[32] = {ORZ_MODE_NIBBLES};
 
 constexpr uint32_t kFull = 0xffffffffu;
+constexpr int kChainUnroll = ORZ_VAR_UNROLL;
 constexpr int kRecStride = 21;  // odd stride: conflict-free lane-per-record stores
 
 struct OccMeta {
@@ -954,15 +961,18 @@ __device__ __forceinline__ bool query_block_h(const Target& T, uint32_t bx, uint
   return block_fine_test(T.depth, by * T.blocksX + bx, maxZ, sX, eX, sY, eY);
 }
 
-// One iterated chain for one tile row: `ny` y steps, `nPre` x steps up to tile column cA, then the
-// values at tile columns [cA, cB] go to out[c].  Trip counts are warp uniform (nyMax >= ny); every
-// add is the reference's own (same operands, same order), only lanes differ in what they own.
-__device__ __forceinline__ void step_chain(float cur, const float incX, const float incY, const uint32_t ny, const uint32_t nyMax,
+// One iterated chain for one tile row: nyCommon + nyExtra y steps, nPre x steps up to tile column
+// cA, then the values at tile columns [cA, cB] go to out[c].  Trip counts are warp uniform except
+// nyExtra (0-3, the row inside the tile); every add is the reference's own (same operands, same
+// order), only lanes differ in what they own.
+__device__ __forceinline__ void step_chain(float cur, const float incX, const float incY, const uint32_t nyCommon, const uint32_t nyExtra,
                                            const uint32_t nPre, const uint32_t cA, const uint32_t cB, const bool active, float* out) {
-#pragma unroll 2
-  for (uint32_t i = 0; i < nyMax; ++i) cur = i < ny ? cur + incY : cur;  // Rasterizer.cpp:1130-1131
-#pragma unroll 4
-  for (uint32_t i = 0; i < nPre; ++i) cur = incX + cur;                    // Rasterizer.cpp:1145-1146
+#pragma unroll kChainUnroll
+  for (uint32_t i = 0; i < nyCommon; ++i) cur = cur + incY;  // Rasterizer.cpp:1130-1131
+#pragma unroll
+  for (uint32_t i = 0; i < kTileH - 1u; ++i) cur = i < nyExtra ? cur + incY : cur;
+#pragma unroll kChainUnroll
+  for (uint32_t i = 0; i < nPre; ++i) cur = incX + cur;      // Rasterizer.cpp:1145-1146
   for (uint32_t c = cA; c <= cB; ++c) {
     if (active) out[c] = cur;
     cur = incX + cur;
@@ -996,7 +1006,7 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
     const bool active = lane < 16 && r >= rFirst && r <= rLast;
     float cur = 0.0f, incX = 0.0f, incY = 0.0f;
     if (active) { cur = u2f(rec[14 + e]); incX = u2f(rec[6 + e]); incY = u2f(rec[10 + e]); }
-    step_chain(cur, incX, incY, y0 + r - minY, y0 + rLast - minY, x0 + cA - minX, cA, cB, active, sm + e * 32u + r * 8u);
+    step_chain(cur, incX, incY, ya - minY, r - rFirst, x0 + cA - minX, cA, cB, active, sm + e * 32u + r * 8u);
   }
   __syncwarp();
 
@@ -1038,7 +1048,7 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
     const bool active = r >= rLo && r <= rLast;
     const float s = -0.5f + 1.0f / 16.0f;
     const float cur = ORZ_FMA(dzdx, s + 0.125f * (float)(l & 3u), ORZ_FMA(dzdy, (l >> 2) ? s + 0.125f : s, u2f(rec[5])));
-    step_chain(cur, dzdx, dzdy, y0 + r - minY, y0 + rLast - minY, x0 + cA - minX, cA, cB, active, sm + (4u + l) * 32u + r * 8u);
+    step_chain(cur, dzdx, dzdy, y0 + rLo - minY, r - rLo, x0 + cA - minX, cA, cB, active, sm + (4u + l) * 32u + r * 8u);
   }
   __syncwarp();
   // ---- depth rows, merge into the registers, HiZ (Rasterizer.cpp:1241-1290)
@@ -1056,7 +1066,7 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
         float a = dv[(2 * i) & 3], b = dv[(2 * i + 1) & 3];
         if (i >= 2) { a = ORZ_FMA(dzdx, 0.5f, a); b = ORZ_FMA(dzdx, 0.5f, b); }  // depth1, :1243
         const float a8 = dzdy + a, b8 = dzdy + b;                                // depth8/9, :1244-1245
-        r0[rr][i] = pack16(a) | (pack16(b) << 16);
+        r0[rr][i] = pack16(a) | (pack16(b) << 16);  // (a run-time "finite plane" shortcut for the NaN guard was measured slower)
         r8[rr][i] = pack16(a8) | (pack16(b8) << 16);
         r4[rr][i] = avg_u16x2(r0[rr][i], r8[rr][i]);                             // :1252
       }
@@ -1103,7 +1113,8 @@ __global__ void __launch_bounds__(kClusterGW * 32, 1) k_raster_views_cluster(con
 
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t rank = cluster.block_rank();
-  const uint32_t view = p.viewBase + blockIdx.x / (uint32_t)C;
+  const uint32_t vrank = p.viewBase + blockIdx.x / (uint32_t)C;
+  const uint32_t view = p.viewOrder ? p.viewOrder[vrank] : vrank;  // longest first: clusters are scheduled in grid order
   const uint32_t tid = threadIdx.x;
   const int warp = (int)(tid >> 5), lane = (int)(tid & 31u);
   const uint32_t gw = (uint32_t)warp * (uint32_t)C + rank;  // my tiles: t % kWarps == gw
@@ -1202,7 +1213,9 @@ __global__ void __launch_bounds__(kClusterGW * 32, 1) k_raster_views_cluster(con
       for (;;) {
         if (*vis) break;
         if (*done >= (uint32_t)C) { visible = *vis != 0u; break; }
-        __nanosleep(32);
+#if ORZ_SPIN_NAP
+        __nanosleep(ORZ_SPIN_NAP);  // (a longer or growing nap was measured slower: the wake-up delay sits on the dependency chain)
+#endif
       }
     }
     if (reporter) {
@@ -1613,7 +1626,7 @@ struct orz_context {
   uint64_t launches = 0;
   int groupWarps = 0;
   int traversal = 2;  // 1 = warp per block, 2 = lane per block (default)
-  int clusterViews = 128;  // batches of at most this many views run one thread-block cluster per view (0 = never)
+  int clusterViews = 1024;  // batches of at most this many views run one thread-block cluster per view (0 = never)
   int clusterSize = 0;     // CTAs per cluster (2, 4, 8, 16); 0 = automatic
   // grow-only device scratch
   uint32_t* d_counter = nullptr;
@@ -2158,9 +2171,11 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
     p.viewCost = (uint32_t*)(prep + chunk * sizeof(ViewMatrices) + chunk * nOcc * 4 + chunk * nOcc * kFrontWords * 4);
     const bool wide = (b->flags & ORZ_BATCH_NO_GATE) && ((b->flags & ORZ_BATCH_WIDE) || (nv <= 8u && scene->totalQuads >= 65536u));
     // (above 65 536 blocks the reference's 16-bit index wrap needs the linear traversal of the batch kernel)
-    const bool clusterPath = !wide && ctx->clusterViews > 0 && nv <= (uint32_t)ctx->clusterViews && blocks <= 65536u && nOcc <= kClusterMaxOcc &&
+    // measured crossover with the batch kernel: ~2000 views at 1920x1080, ~800 at 512x256 (profiles/r1_few_views_*)
+    const uint32_t clusterLimit = blocks >= 8192u ? (uint32_t)ctx->clusterViews : (uint32_t)ctx->clusterViews * 3u / 4u;
+    const bool clusterPath = !wide && ctx->clusterViews > 0 && nv <= clusterLimit && blocks <= 65536u && nOcc <= kClusterMaxOcc &&
                              (size_t)nv * scene->totalQuads * (kRecStride * 4 + 8) <= (size_t(8) << 30);
-    p.viewOrder = (nv <= 16384u && !clusterPath) ? p.viewCost + chunk : nullptr;
+    p.viewOrder = (nv <= 16384u && !(clusterPath && nv * 2u <= (uint32_t)ctx->numSMs)) ? p.viewCost + chunk : nullptr;
     k_prepare_views<<<nv, 128, 0, ctx->stream>>>(p);
     ctx->launches++;
     ORZ_CUDA(cudaGetLastError());
@@ -2208,7 +2223,7 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
     // Few views: one thread-block cluster per view (latency path, BASELINE configs 1 and 2)
     if (clusterPath) {
       FrameParams pc = p;
-      pc.viewOrder = nullptr; pc.viewBase = 0; pc.groupViews = nv;
+      pc.viewBase = 0; pc.groupViews = nv;
       const size_t recBytes = (size_t)nv * scene->totalQuads * kRecStride * 4, hdrBytes = (size_t)nv * scene->totalQuads * 8;
       if ((e = ensure_scratch(ctx, 11, recBytes + hdrBytes + (size_t)nv * nOcc * 32 + 64))) return e;
       pc.hdrBuf = (uint2*)ctx->d_scratch[11];
@@ -2217,6 +2232,7 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
       pc.totalQuads = scene->totalQuads;
       if ((e = launch_cluster(ctx, pc, nv, ctx->stream))) return e;
       if (p.visBits || p.clipBits) {
+        pc.viewOrder = nullptr;
         k_query_views<<<dim3((scene->nBoxes + 255) / 256, nv), 256, 0, ctx->stream>>>(pc);
         ctx->launches++;
         ORZ_CUDA(cudaGetLastError());

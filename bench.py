@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--workload", default="castle_1080p_path", choices=sorted(WORKLOADS))
     ap.add_argument("--views", type=int, default=0, help="views per GPU (default: the workload's)")
     ap.add_argument("--group-warps", type=int, default=0)
+    ap.add_argument("--cluster-views", type=int, default=-1, help="largest batch that takes the cluster-per-view path (0 = batch kernel only; default: library's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -225,6 +226,10 @@ def run_ours(args):
     ctx = api.Context(local)
     if args.group_warps:
         ctx.set_group_warps(args.group_warps)
+    if args.cluster_views >= 0:
+        ctx.set_cluster_views(args.cluster_views)
+    cluster_limit = (args.cluster_views if args.cluster_views >= 0 else 1024) * (4 if blocks >= 8192 else 3) // 4
+    cluster_path = n_views <= cluster_limit and blocks <= 65536
     scene = api.Scene.from_prepared(ctx, ps)
     n_boxes, n_occ, words = scene.n_boxes, scene.n_occluders, (scene.n_boxes + 31) // 32
     mvps_all, poss_all = make_views(ps, kind, n_views * world, w, h)
@@ -343,11 +348,28 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg,
-                         "kernel": "one step = k_prepare_views + k_sort_views + 4 x (k_render_views<GW> + k_query_views), the four cost-sorted sub-batches overlapped on four streams; "
-                                   "duration = CUDA events around the step on the context stream",
+                         "kernel": ("one step = k_prepare_views + k_sort_views + k_setup_views (speculative setup of every occluder in the frustum) + "
+                                    "k_raster_views_cluster (one thread-block cluster per view, dataflow gates, tile-major register-resident depth) + k_query_views; "
+                                    if cluster_path else
+                                    "one step = k_prepare_views + k_sort_views + 4 x (k_render_views<GW> + k_query_views), the four cost-sorted sub-batches overlapped on four streams; ")
+                                   + "duration = CUDA events around the step on the context stream",
                          "traffic_note": (traffic or {}).get("note"),
                          "note": "issue/latency bound by design (SURVEY 8d): HBM is not the limiter; ncu per-launch counters in profiles/"},
         }
+        # BASELINE configs[0]/[1]: ONE view (the scene's default camera) through the host entry point: matrix in, bits out
+        c = ps.camera
+        from rasterizer_b200 import camera as cam
+        one_mvp = cam.view_projection(c["pos"], c["dir"], c["up"], c["fov"], w, h)[None]
+        one_pos = np.array(c["pos"], np.float32)[None]
+        for _ in range(3):
+            scene.render_views(w, h, one_mvp, cam_pos=one_pos, want=("vis",))
+        t0 = time.perf_counter()
+        for _ in range(20):
+            scene.render_views(w, h, one_mvp, cam_pos=one_pos, want=("vis",))
+        line["single_view"] = {"ms": (time.perf_counter() - t0) / 20 * 1e3, "what": "one view, default camera: host matrix in -> frame loop + all occludee queries -> host bits out (wall clock, includes H2D/D2H and launches)"}
+        if not args.no_cpu_baseline and world == 1:
+            cb1 = cpu_reference(ps, w, h, one_mvp, one_pos, 1, 1.0)
+            line["single_view"]["reference_ms_one_core"] = cb1["frame_ms_per_view"] + cb1["query_ms_per_view"]
         if not args.no_cpu_baseline and world == 1:
             sample = min(128, n_views)
             idx = np.linspace(0, n_views - 1, sample).astype(int)

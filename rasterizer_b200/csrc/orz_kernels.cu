@@ -866,7 +866,13 @@ __global__ void __launch_bounds__(GW * 32, (kTrav == 2 ? ORZ_THREADS_PER_SM_V2 :
 //       per (occluder, tile) instead of once per (primitive, block);
 //     * the edge-mask table (32 KB) lives in shared memory; records are gathered from L2 into a
 //       per-warp staging area 32 at a time with all loads in flight together.
-constexpr int kClusterGW = 16;
+#ifndef ORZ_CLUSTER_GW
+#define ORZ_CLUSTER_GW 16
+#endif
+#ifndef ORZ_CLUSTER_REGS
+#define ORZ_CLUSTER_REGS 96  // 16 warps x 96 registers leave room for one CTA of the query kernel on the same SM
+#endif
+constexpr int kClusterGW = ORZ_CLUSTER_GW;  // warps per CTA of the cluster kernel; registers per thread capped so that they fit one SM
 constexpr uint32_t kTileW = 8, kTileH = 4;   // blocks per tile: lane = 8 * (row in tile) + column in tile
 constexpr uint32_t kStageCap = 32;           // records a warp stages at a time
 constexpr uint32_t kClusterMaxOcc = 2048;    // occluders per scene the cluster path accepts (shared-memory decision arrays)
@@ -1098,7 +1104,7 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
 }
 
 template <int C>
-__global__ void __launch_bounds__(kClusterGW * 32, 1) k_raster_views_cluster(const FrameParams p) {
+__global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const FrameParams p) {
   constexpr uint32_t GW = kClusterGW, NT = GW * 32, kWarps = C * GW;
   extern __shared__ __align__(16) uint32_t s_dyn[];
   uint2* s_lut = reinterpret_cast<uint2*>(s_dyn);
@@ -2059,9 +2065,6 @@ static int launch_cluster_t(orz_context* ctx, FrameParams p, uint32_t nViews, ui
     if (C > 8) ORZ_CUDA(cudaFuncSetAttribute(k_raster_views_cluster<C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     configured[ctx->device & 63] = smem;
   }
-  k_setup_views<<<dim3(p.nOcc, nViews), 256, 0, st>>>(p);
-  ctx->launches++;
-  ORZ_CUDA(cudaGetLastError());
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(nViews * (uint32_t)C);
@@ -2079,10 +2082,10 @@ static int launch_cluster_t(orz_context* ctx, FrameParams p, uint32_t nViews, ui
 }
 // one cluster per view.  Cluster size: as many CTAs as the view can use (one tile per warp) while all
 // views of the batch still fit the GPU in one wave; at least enough that a warp owns <= 32 tiles.
-static int launch_cluster(orz_context* ctx, const FrameParams& p, uint32_t nViews, cudaStream_t st) {
+static int launch_cluster(orz_context* ctx, const FrameParams& p, uint32_t nViews, uint32_t nBatch, cudaStream_t st) {
   const uint32_t nTiles = (((p.width >> 3) + kTileW - 1u) / kTileW) * (((p.height >> 3) + kTileH - 1u) / kTileH);
   uint32_t c = 2;
-  while (c < 16u && c * kClusterGW < nTiles && nViews * c * 2u <= (uint32_t)ctx->numSMs) c *= 2u;
+  while (c < 16u && c * kClusterGW < nTiles && nBatch * c * 2u <= (uint32_t)ctx->numSMs) c *= 2u;
   while (c < 16u && (nTiles + c * kClusterGW - 1u) / (c * kClusterGW) > 32u) c *= 2u;
   if (ctx->clusterSize) c = (uint32_t)ctx->clusterSize;
   if ((nTiles + c * kClusterGW - 1u) / (c * kClusterGW) > 32u) return fail(ORZ_ERR_ARG, "cluster path: target too large for this cluster size");
@@ -2230,12 +2233,31 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
       pc.recInfo = (uint4*)((uint8_t*)ctx->d_scratch[11] + ((hdrBytes + 15) & ~size_t(15)));
       pc.recBuf = (uint32_t*)((uint8_t*)pc.recInfo + (size_t)nv * nOcc * 32);
       pc.totalQuads = scene->totalQuads;
-      if ((e = launch_cluster(ctx, pc, nv, ctx->stream))) return e;
-      if (p.visBits || p.clipBits) {
-        pc.viewOrder = nullptr;
-        k_query_views<<<dim3((scene->nBoxes + 255) / 256, nv), 256, 0, ctx->stream>>>(pc);
-        ctx->launches++;
-        ORZ_CUDA(cudaGetLastError());
+      k_setup_views<<<dim3(pc.nOcc, nv), 256, 0, ctx->stream>>>(pc);
+      ctx->launches++;
+      ORZ_CUDA(cudaGetLastError());
+      // Large batches: sub-batches (by descending cost) on auxiliary streams, so that the occludee queries of a
+      // finished sub-batch share the SMs with the cluster kernel of the next one (it leaves room for one
+      // query CTA per SM and about half of its issue slots).
+      const bool wantQ = p.visBits || p.clipBits;
+      const int groupsC = (pc.viewOrder && wantQ && nv >= 256u) ? orz_context::kGroups : 1;
+      if (groupsC > 1) ORZ_CUDA(cudaEventRecord(ctx->evFork, ctx->stream));
+      for (int g = 0; g < groupsC; ++g) {
+        cudaStream_t st = groupsC > 1 ? ctx->aux[g] : ctx->stream;
+        if (groupsC > 1) ORZ_CUDA(cudaStreamWaitEvent(st, ctx->evFork, 0));
+        FrameParams pg = pc;
+        pg.viewBase = (uint32_t)((uint64_t)nv * g / groupsC);
+        pg.groupViews = (uint32_t)((uint64_t)nv * (g + 1) / groupsC) - pg.viewBase;
+        if ((e = launch_cluster(ctx, pg, pg.groupViews, nv, st))) return e;
+        if (wantQ) {
+          k_query_views<<<dim3((scene->nBoxes + 255) / 256, pg.groupViews), 256, 0, st>>>(pg);
+          ctx->launches++;
+          ORZ_CUDA(cudaGetLastError());
+        }
+        if (groupsC > 1) {
+          ORZ_CUDA(cudaEventRecord(ctx->evJoin[g], st));
+          ORZ_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evJoin[g], 0));
+        }
       }
       continue;
     }

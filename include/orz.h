@@ -94,6 +94,14 @@ int orz_rasterizer_debug_setup(orz_rasterizer* r, const orz_occluder* occ, int p
 int orz_scene_create(orz_context* ctx, const uint32_t* packets, const uint32_t* packetCounts, uint32_t nOccluders,
                      const float* refMin, const float* refMax, const float* boundsMin, const float* boundsMax,
                      const float* centers, orz_scene** out);
+/* Occluder::bake (Occluder.cpp:7-181) for every batch of a scene ON THE GPU, one CTA per batch, bit-exact with
+ * orz_bake; the scene is created directly in HBM.  vertices: all batches' float4 vertices concatenated (4 per
+ * quad), vertCounts[i] = vertices of batch i (multiple of 32); one refMin/refMax for all batches (Main.cpp:109-128).
+ * Optional host outputs (may be NULL): packetsOut = sum(vertCounts) words in the reference's packet layout,
+ * centersOut / boundsMinOut / boundsMaxOut = nOccluders x 4 floats (Occluder.h:13-15). */
+int orz_scene_bake(orz_context* ctx, const float* vertices, const uint32_t* vertCounts, uint32_t nOccluders,
+                   const float* refMin4, const float* refMax4, uint32_t* packetsOut, float* centersOut,
+                   float* boundsMinOut, float* boundsMaxOut, orz_scene** out);
 int orz_scene_set_occludees(orz_scene* scene, const float* boxes, uint32_t nBoxes); /* n x (min4, max4) */
 void orz_scene_destroy(orz_scene* scene);
 

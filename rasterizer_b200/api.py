@@ -77,6 +77,7 @@ EXPORTS = {
     "orz_rasterizer_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "orz_rasterizer_debug_setup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "orz_scene_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "orz_scene_bake": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "orz_scene_set_occludees": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "orz_scene_destroy": (None, [C.c_void_p]),
     "orz_render_views": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(ViewBatch)]),
@@ -323,6 +324,34 @@ class Scene:
         bx = prepared.quad_boxes() if isinstance(boxes, str) and boxes == "quads" else boxes
         return cls(ctx, [b[0] for b in baked], prepared.ref_min, prepared.ref_max, np.stack([b[2] for b in baked]),
                    np.stack([b[3] for b in baked]), np.stack([b[1] for b in baked]), bx)
+
+    @classmethod
+    def bake_on_device(cls, ctx: Context, batches, ref_min, ref_max, boxes=None) -> "Scene":
+        """Occluder::bake for every batch on the GPU (orz_scene_bake); the host copies of the baked data
+        (packets in the reference layout, bounds, centres) come back for the caller's own use."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        vs = [_f32(b).reshape(-1, 4) for b in batches]
+        n = len(vs)
+        counts = np.array([v.shape[0] for v in vs], np.uint32)
+        verts = np.ascontiguousarray(np.concatenate(vs))
+        rmn, rmx = _f32(ref_min).reshape(4), _f32(ref_max).reshape(4)
+        packets = np.zeros(int(counts.sum()), np.uint32)
+        cen, bmn, bmx = (np.zeros((n, 4), np.float32) for _ in range(3))
+        h = C.c_void_p()
+        _check(lib().orz_scene_bake(ctx.h, _p(verts), _p(counts), n, _p(rmn), _p(rmx), _p(packets), _p(cen), _p(bmn), _p(bmx), C.byref(h)))
+        self.h = h
+        self.n_occluders = n
+        ofs = np.concatenate([[0], np.cumsum(counts.astype(np.int64))]).astype(np.int64)
+        self.packed_list = [packets[int(ofs[i]):int(ofs[i + 1])] for i in range(n)]
+        self.quads_per_occluder = counts // 4
+        self.ref_min = np.ascontiguousarray(np.broadcast_to(rmn, (n, 4)))
+        self.ref_max = np.ascontiguousarray(np.broadcast_to(rmx, (n, 4)))
+        self.bounds_min, self.bounds_max, self.centers = bmn, bmx, cen
+        self.n_boxes = 0
+        if boxes is not None:
+            self.set_occludees(boxes)
+        return self
 
     def set_occludees(self, boxes):
         b = _f32(boxes).reshape(-1, 8)

@@ -164,3 +164,52 @@ def test_argument_errors(ctx, city):
     with pytest.raises(api.OrzError):
         r.query2D(0, 64, 0, 10, 5)                   # rectangle outside the buffer
     r.close(); sc.close()
+
+
+@pytest.mark.parametrize("name", ["city", "castle", "soup"])
+def test_device_bake_matches_host_bake(ctx, name):
+    """Occluder::bake on the GPU (orz_scene_bake, one CTA per batch) against the host bake: packets in the
+    reference layout, bounds and centres bit for bit; a scene baked on the device renders the same."""
+    if name == "soup":
+        ps = wl.synthetic_soup(4096, cube=60.0)
+    elif name == "city":
+        ps = wl.synthetic_city()
+    else:
+        if not wl.have_scene("castle"):
+            pytest.skip("castle scene data not shipped")
+        ps = wl.load_scene("castle")
+    host = [api.bake(b, ps.ref_min, ps.ref_max) for b in ps.batches]
+    boxes = ps.quad_boxes()[::11]
+    sd = api.Scene.bake_on_device(ctx, ps.batches, ps.ref_min, ps.ref_max, boxes)
+    for i, hb in enumerate(host):
+        assert np.array_equal(sd.packed_list[i], hb[0]), (name, i)
+        assert np.array_equal(sd.centers[i].view(np.uint32), hb[1].view(np.uint32)), (name, i)
+        assert np.array_equal(sd.bounds_min[i].view(np.uint32), hb[2].view(np.uint32)), (name, i)
+        assert np.array_equal(sd.bounds_max[i].view(np.uint32), hb[3].view(np.uint32)), (name, i)
+    sh = api.Scene(ctx, [b[0] for b in host], ps.ref_min, ps.ref_max, np.stack([b[2] for b in host]), np.stack([b[3] for b in host]),
+                   np.stack([b[1] for b in host]), boxes)
+    mvps, poss = wl.camera_path(ps, 3, 640, 360)
+    a = sd.render_views(640, 360, mvps, cam_pos=poss, want=("vis", "gate", "depth", "hiz"))
+    b = sh.render_views(640, 360, mvps, cam_pos=poss, want=("vis", "gate", "depth", "hiz"))
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    sd.close(); sh.close()
+
+
+def test_device_bake_signed_zero_bounds_and_errors(ctx):
+    """minps / maxps keep the earlier operand on ties: +0 / -0 in the bounds must follow the serial order."""
+    rng = np.random.default_rng(5)
+    v = rng.uniform(0.5, 4.0, (64, 4)).astype(np.float32)
+    v[:, 3] = 1.0
+    v[40, 0] = 0.0; v[41, 0] = -0.0; v[50, 1] = -0.0; v[60, 1] = 0.0     # the minima of x and y are zeros of both signs
+    v[:, 2] = -np.abs(v[:, 2]); v[7, 2] = -0.0; v[30, 2] = 0.0            # the maximum of z too
+    rmn, rmx = np.array([-1, -1, -5, 0], np.float32), np.array([5, 5, 1, 0], np.float32)
+    hb = api.bake(v, rmn, rmx)
+    sd = api.Scene.bake_on_device(ctx, [v], rmn, rmx)
+    assert np.array_equal(sd.packed_list[0], hb[0])
+    assert np.array_equal(sd.bounds_min[0].view(np.uint32), hb[2].view(np.uint32))
+    assert np.array_equal(sd.bounds_max[0].view(np.uint32), hb[3].view(np.uint32))
+    assert np.array_equal(sd.centers[0].view(np.uint32), hb[1].view(np.uint32))
+    sd.close()
+    with pytest.raises(api.OrzError, match="multiple of 8 quads"):
+        api.Scene.bake_on_device(ctx, [v[:36]], rmn, rmx)

@@ -544,16 +544,43 @@ __device__ __forceinline__ bool query2d_warp(const Target& T, const BoxFront& f,
     const uint32_t cols = (maxX >> 3) - bx0 + 1u, n = cols * ((maxY >> 3) - by0 + 1u);
     const uint32_t magic = (65536u + cols - 1u) / cols;  // i / cols ~ (i * magic) >> 16, at most one too large (i < 65536)
     bool found = false;
-    for (uint32_t base = 0; base < n; base += 32u) {
-      const uint32_t i = base + (uint32_t)lane;
-      bool hit = false;
-      if (i < n) {
-        uint32_t ry = n <= 65536u ? (i * magic) >> 16 : i / cols;
-        if (ry * cols > i) --ry;
-        const uint32_t rx = i - ry * cols;
-        hit = query_block(T, bx0 + rx, by0 + ry, minX, maxX, minY, maxY, maxZ);
+    // 128 blocks per step: the four HiZ reads of a lane are in flight together (a fully occluded
+    // large box is a chain of dependent L2 round trips otherwise); fine tests only where needed
+    for (uint32_t base = 0; base < n && !found; base += 128u) {
+      uint32_t h[4], bxs[4], bys[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = base + (uint32_t)u * 32u + (uint32_t)lane;
+        h[u] = 0xffffu;  // maxZ <= 0xffff: skipped
+        bxs[u] = bys[u] = 0u;
+        if (i < n) {
+          uint32_t ry = n <= 65536u ? (i * magic) >> 16 : i / cols;
+          if (ry * cols > i) --ry;
+          bxs[u] = bx0 + (i - ry * cols); bys[u] = by0 + ry;
+          h[u] = T.hiz[bys[u] * T.blocksX + bxs[u]];
+        }
       }
+      bool hit = false;
+      uint32_t fine = 0u;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (maxZ > h[u]) {  // Rasterizer.cpp:310
+          const int sX = max((int)minX - (int)(8u * bxs[u]), 0), eX = min((int)maxX - (int)(8u * bxs[u]), 7);
+          const int sY = max((int)minY - (int)(8u * bys[u]), 0), eY = min((int)maxY - (int)(8u * bys[u]), 7);
+          if (h[u] == 1u || (sX == 0 && eX == 7 && sY == 0 && eY == 7)) hit = true;  // cleared block / Rasterizer.cpp:319-325
+          else fine |= 1u << u;
+        }
       if (__any_sync(kFull, hit)) { found = true; break; }
+      if (__any_sync(kFull, fine != 0u)) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if ((fine >> u) & 1u) {
+            const int sX = max((int)minX - (int)(8u * bxs[u]), 0), eX = min((int)maxX - (int)(8u * bxs[u]), 7);
+            const int sY = max((int)minY - (int)(8u * bys[u]), 0), eY = min((int)maxY - (int)(8u * bys[u]), 7);
+            hit = hit || block_fine_test(T.depth, bys[u] * T.blocksX + bxs[u], maxZ, sX, eX, sY, eY);
+          }
+        if (__any_sync(kFull, hit)) { found = true; break; }
+      }
     }
     if (lane == src) vis = found;
   }

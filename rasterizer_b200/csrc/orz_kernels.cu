@@ -983,6 +983,22 @@ __global__ void __launch_bounds__(256) k_setup_views(const FrameParams p) {
   }
 }
 
+// Decision words of the cluster kernel are read and written concurrently by design (monotonic
+// flags / counters): strong relaxed accesses at cluster scope, which the PTX memory model allows
+// to race (no data is published through them, only the decision itself).  compute-sanitizer's
+// racecheck still lists exactly these two accesses (it only exempts atomics); polling with
+// atomics instead was tried and starves the remote updates it is waiting for -- the kernel hangs.
+__device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_flag_remote(uint32_t* localPtr, uint32_t ctaRank, uint32_t val) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(localPtr)), "r"(ctaRank));
+  asm volatile("st.relaxed.cluster.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(val) : "memory");
+}
+
 // one block of query2D (Rasterizer.cpp:305-343) with the block's HiZ already at hand
 __device__ __forceinline__ bool query_block_h(const Target& T, uint32_t bx, uint32_t by, uint32_t h, uint32_t minX, uint32_t maxX,
                                               uint32_t minY, uint32_t maxY, uint32_t maxZ) {
@@ -1072,7 +1088,8 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
     }
   }
   const uint32_t updMask = __ballot_sync(kFull, upd);
-  if (!updMask) return;  // every lane has consumed its edge slots: `upd` depends on them
+  __syncwarp();  // orders this primitive's reads of the edge slots before the next primitive's writes (free: the warp is converged)
+  if (!updMask) return;
   {  // the eight depth lanes (Rasterizer.cpp:1103-1112) at the covered blocks
     const uint32_t rLast = (31u - (uint32_t)__clz((int)updMask)) >> 3, rLo = ((uint32_t)__ffs((int)updMask) - 1u) >> 3;
     const uint32_t cols = (updMask | (updMask >> 8) | (updMask >> 16) | (updMask >> 24)) & 0xffu;
@@ -1226,26 +1243,26 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
       // ---- gate: query2D (Rasterizer.cpp:283-349) on the part of the rectangle that lies on my tiles
       const uint32_t minX = hd[1], maxX = hd[2], minY = hd[3], maxY = hd[4], maxZ = hd[5];
       const uint32_t bx0 = minX >> 3, bx1 = maxX >> 3, by0 = minY >> 3, by1 = maxY >> 3;
-      volatile uint32_t* vis = s_vis + s;
+      const uint32_t* vis = s_vis + s;
       uint32_t tm = tiles_meeting(bx0, bx1, by0, by1);
-      if (tm && !*vis) {
+      if (tm && !ld_flag(vis)) {
         bool found = false;
         for (; tm; tm &= tm - 1u) {
           const uint32_t k = (uint32_t)__ffs((int)tm) - 1u;
           const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
-          if (*vis) break;  // another warp already found a visible pixel
+          if (ld_flag(vis)) break;  // another warp already found a visible pixel
           const bool hit = bx >= bx0 && bx <= bx1 && by >= by0 && by <= by1 && bx < T.blocksX && by < T.blocksY &&
                            query_block_h(T, bx, by, (uint32_t)myHiz[32u * k], minX, maxX, minY, maxY, maxZ);
           if (__any_sync(kFull, hit)) { found = true; break; }
         }
-        if (found) { if (lane < C) *cluster.map_shared_rank(s_vis + s, (unsigned)lane) = 1u; }
-        else if (!*vis) answer_no(s);
+        if (found) { if (lane < C) st_flag_remote(s_vis + s, (uint32_t)lane, 1u); }
+        else if (!ld_flag(vis)) answer_no(s);
       }
       // visible as soon as ONE warp says so, invisible when all 16 C warps have said no
-      volatile uint32_t* done = s_doneCta + s;
+      const uint32_t* done = s_doneCta + s;
       for (;;) {
-        if (*vis) break;
-        if (*done >= (uint32_t)C) { visible = *vis != 0u; break; }
+        if (ld_flag(vis)) break;
+        if (ld_flag(done) >= (uint32_t)C) { visible = ld_flag(vis) != 0u; break; }
 #if ORZ_SPIN_NAP
         __nanosleep(ORZ_SPIN_NAP);  // (a longer or growing nap was measured slower: the wake-up delay sits on the dependency chain)
 #endif

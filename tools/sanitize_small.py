@@ -10,10 +10,19 @@ ctx = api.Context(0)
 sc = api.Scene.from_prepared(ctx, ps)
 w, h = 320, 184
 mvps, poss = wl.camera_path(ps, 6, w, h)
+ctx.set_cluster_views(0)      # the one-CTA-per-view batch kernel
 for gw in (1, 4, 8):
     ctx.set_group_warps(gw)
     out = sc.render_views(w, h, mvps, cam_pos=poss, want=("vis", "clip", "gate", "depth", "hiz", "quads"))
 ctx.set_group_warps(0)
+ctx.set_cluster_views(1024)   # the cluster path (speculative setup + dataflow cluster kernel), every cluster size
+for cs in (0, 2, 4, 8, 16):
+    ctx.set_cluster_size(cs)
+    out2 = sc.render_views(w, h, mvps, cam_pos=poss, want=("vis", "clip", "gate", "depth", "hiz", "quads"))
+    assert all(np.array_equal(out[k], out2[k]) for k in out), cs
+ctx.set_cluster_size(0)
+sd = api.Scene.bake_on_device(ctx, ps.batches, ps.ref_min, ps.ref_max)   # device bake
+sd.close()
 out = sc.render_views(w, h, mvps[:2], cam_pos=poss[:2], flags=api.BATCH_NO_GATE | api.BATCH_FORCE_CLIPPED | api.BATCH_WIDE, want=("vis", "depth", "hiz"))
 r = api.Rasterizer(ctx, w, h)
 occs = [api.Occluder(ctx, p, ps.ref_min, ps.ref_max) for p in sc.packed_list[:6]]

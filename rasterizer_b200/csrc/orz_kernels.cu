@@ -2357,7 +2357,11 @@ static int launch_cluster(orz_context* ctx, const FrameParams& p, uint32_t nView
   if (ctx->clusterSize) c = (uint32_t)ctx->clusterSize;
   if ((nTiles + c * kClusterGW - 1u) / (c * kClusterGW) > 32u) return fail(ORZ_ERR_ARG, "cluster path: target too large for this cluster size");
   switch (c) {
-    case 16: return launch_cluster_t<16>(ctx, p, nViews, nTiles, st);
+    case 16:  // non-portable cluster size: when the device (e.g. a partitioned one) cannot place it, use 8
+      if (launch_cluster_t<16>(ctx, p, nViews, nTiles, st) == ORZ_OK) return ORZ_OK;
+      (void)cudaGetLastError();
+      if ((nTiles + 8u * kClusterGW - 1u) / (8u * kClusterGW) > 32u) return fail(ORZ_ERR_CUDA, "cluster path: 16-CTA clusters are not available on this device");
+      return launch_cluster_t<8>(ctx, p, nViews, nTiles, st);
     case 8: return launch_cluster_t<8>(ctx, p, nViews, nTiles, st);
     case 4: return launch_cluster_t<4>(ctx, p, nViews, nTiles, st);
     default: return launch_cluster_t<2>(ctx, p, nViews, nTiles, st);

@@ -1,20 +1,78 @@
-import subprocess,sys,re,collections
-out=subprocess.run(['python','tools/ncu_lines.py',sys.argv[1],sys.argv[2],'400'],capture_output=True,text=True).stdout.splitlines()
-src=open('rasterizer_b200/csrc/orz_kernels.cu').read().splitlines()
-def find(pat,start=0):
-    for i,l in enumerate(src[start:],start):
-        if pat in l: return i+1
-    return None
-marks=[('raster_preamble',find('__device__ __forceinline__ void raster_prim')),('row_loop',find('for (uint32_t by = 0; by < rangeY')),('segment',find('for (uint32_t s0 = a; s0 < b')),('cand_loop',find('while (cand) {')),('chain_steps',find('for (uint32_t i = 0; i < steps')),('post_steps',find('owed = 0; pos = j;')),('convex_mask',find('if (convex) {  // Rasterizer')),('nonconvex_mask',find('} else {  // Rasterizer.cpp:1188')),('update',find('uint32_t* dptr = depthWords')),('hiz',find('uint32_t mn = min(val')),('row_end',find('owed += m - pos;')),('after_raster',find('// query2D, Rasterizer.cpp:283-349')),('query',find('block_fine_test')),('setup_chunk',find('void setup_chunk')),('frame',find('k_render_views(const FrameParams p)')),('end',find('k_query_views(const FrameParams'))]
-agg=collections.Counter(); smp=collections.Counter()
-for l in out[3:]:
-    m=re.match(r'(\S+):(\d+)\s+([\d.]+)\s+([\d.]+)',l)
-    if not m: continue
-    f,n,i,s=m.group(1),int(m.group(2)),float(m.group(3)),float(m.group(4))
-    if f!='orz_kernels.cu': reg='other:'+f
-    else:
-        reg='pre'
-        for name,ln in marks:
-            if ln and n>=ln: reg=name
-    agg[reg]+=i; smp[reg]+=s
-for k,v in sorted(agg.items(),key=lambda kv:-kv[1]): print(f'{k:40s} inst {v:6.2f}%  samples {smp[k]:6.2f}%')
+"""Instruction / stall-sample shares of the cluster kernel by code region (source line ranges of
+orz_kernels.cu found by their marker comments), from an ncu report with --import-source on.
+usage: python tools/ncu_regions.py <report.ncu-rep> <kernel-substring>"""
+import csv, os, re, subprocess, sys, tempfile, collections
+rep, kern = sys.argv[1], sys.argv[2]
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+src = open(os.path.join(root, "rasterizer_b200", "csrc", "orz_kernels.cu")).read().splitlines()
+def line_of(marker):
+    for i, l in enumerate(src):
+        if marker in l: return i + 1
+    raise SystemExit("marker not found: " + marker)
+marks = [
+    ("step_chain (iterated add chains)", "__device__ __forceinline__ void step_chain("),
+    ("tile_prim: HiZ test + chain set-up", "__device__ __forceinline__ void tile_prim("),
+    ("tile_prim: coverage (edge masks)", "// ---- coverage (Rasterizer.cpp:1155-1239)"),
+    ("tile_prim: depth chains set-up", "const uint32_t updMask = "),
+    ("tile_prim: depth rows + merge + HiZ", "// ---- depth rows, merge into the registers"),
+    ("kernel prologue (tables, clear)", "k_raster_views_cluster(const FrameParams p) {"),
+    ("pre-announce loop", "// ---- candidates whose rectangle does not touch my tiles"),
+    ("walk: slot bookkeeping", "  uint32_t quadsSubmitted = 0;"),
+    ("gate test on my tiles", "// ---- gate: query2D (Rasterizer.cpp:283-349) on the part"),
+    ("decision wait (spin)", "// visible as soon as ONE warp says so"),
+    ("occluder prologue (info, box)", "// ---- rasterize<clipped>(occluder): the records k_setup_views wrote"),
+    ("flush: gather + tile loop", "    auto flush = [&]() {"),
+    ("flush: tile open (load)", "// bring the tile into registers"),
+    ("flush: tile close (store)", "        if (dirty) {"),
+    ("header scan + staging", "    for (uint32_t r0 = 0; r0 < cnt; r0 += 32u) {"),
+    ("epilogue (zero fill, final barrier)", "  if (p.quadsSubmitted && reporter)"),
+    ("(after kernel)", "// queryVisibility for every (view, occludee box) on the finished buffers"),
+]
+bounds = sorted((line_of(m), name) for name, m in marks)
+def region(f, n):
+    if f != "orz_kernels.cu": return "inlined helpers (" + f + ")"
+    name = "(before)"
+    for ln, nm in bounds:
+        if n >= ln: name = nm
+    return name
+so = os.path.join(root, "rasterizer_b200", "librasterizer_b200.so")
+tmp = tempfile.mkdtemp()
+subprocess.check_call(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL)
+cubin = [f for f in os.listdir(tmp) if f.startswith("orz_kernels.sm")][0]
+dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+addr_line, cur, infn = {}, None, False
+for l in dis:
+    if l.startswith("//--------------------- .text."):
+        infn = kern in l; continue
+    if not infn: continue
+    m = re.match(r'\s*//## File "([^"]+)", line (\d+)(.*)', l)
+    if m:
+        # innermost frame of an inlined chain names the helper; keep the OUTERMOST orz_kernels.cu line for the region
+        f, n, rest = os.path.basename(m.group(1)), int(m.group(2)), m.group(3)
+        if "inlined at" in rest:
+            mm = re.findall(r'"([^"]+)", line (\d+)', rest)
+            outer = [(os.path.basename(a), int(b)) for a, b in mm if os.path.basename(a) == "orz_kernels.cu"]
+            cur = outer[0] if (f != "orz_kernels.cu" and outer) else (f, n)
+        else:
+            cur = (f, n)
+        continue
+    m = re.match(r'\s*/\*([0-9a-f]{4,})\*/\s+(.*);', l)
+    if m: addr_line[int(m.group(1), 16)] = cur
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}
+agg = collections.defaultdict(collections.Counter); base = None
+for r in rows[2:]:
+    if len(r) < len(hdr) or not r[0].startswith("0x"): continue
+    a = int(r[0], 16)
+    if base is None: base = a
+    k = addr_line.get(a - base) or ("?", 0)
+    g = agg[region(*k)]
+    g["inst"] += int(r[ix["Instructions Executed"]] or 0)
+    g["thr"] += int(r[ix["Predicated-On Thread Instructions Executed"]] or 0)
+    g["smp"] += int(r[ix["# Samples"]] or 0)
+ti = sum(g["inst"] for g in agg.values()); ts = sum(g["smp"] for g in agg.values())
+print(f"{'region':42s} {'inst%':>7s} {'lanes':>6s} {'samples%':>9s}")
+for name, g in sorted(agg.items(), key=lambda kv: -kv[1]["inst"]):
+    print(f"{name:42s} {100*g['inst']/ti:7.2f} {g['thr']/max(1,g['inst']):6.1f} {100*g['smp']/max(1,ts):9.2f}")
+print(f"total warp instructions {ti:,}, samples {ts:,}")

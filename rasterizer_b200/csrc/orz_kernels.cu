@@ -901,6 +901,7 @@ __global__ void __launch_bounds__(GW * 32, (kTrav == 2 ? ORZ_THREADS_PER_SM_V2 :
 #endif
 constexpr int kClusterGW = ORZ_CLUSTER_GW;  // warps per CTA of the cluster kernel; registers per thread capped so that they fit one SM
 constexpr uint32_t kTileW = 8, kTileH = 4;   // blocks per tile: lane = 8 * (row in tile) + column in tile
+constexpr uint32_t kChainStride = 33;        // words between two chains' slots: the publishing lanes (chain, tile row) hit 32 different banks
 constexpr uint32_t kStageCap = 32;           // records a warp stages at a time
 constexpr uint32_t kClusterMaxOcc = 2048;    // occluders per scene the cluster path accepts (shared-memory decision arrays)
 constexpr uint32_t kHeadWords = 6;           // status, minX, maxX, minY, maxY, maxZ of kFrontWords
@@ -909,7 +910,7 @@ struct ClusterSmem {
   static constexpr uint32_t kLutWords = 4096 * 2;
   static constexpr uint32_t kStageWords = kClusterGW * kStageCap * kRecStride;
   static constexpr uint32_t kIdxWords = kClusterGW * kStageCap;
-  static constexpr uint32_t kChainWords = kClusterGW * 12 * 32;
+  static constexpr uint32_t kChainWords = kClusterGW * 12 * kChainStride;
   static constexpr uint32_t kFixedWords = kLutWords + kStageWords + kIdxWords + kChainWords;
   // + [nOcc][6] gate heads, 3 x [nOcc] decision words, [GW][K][32] u16 HiZ mirror
   static size_t bytes(uint32_t tilesPerWarp, uint32_t nOcc) {
@@ -1055,7 +1056,7 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
     const bool active = lane < 16 && r >= rFirst && r <= rLast;
     float cur = 0.0f, incX = 0.0f, incY = 0.0f;
     if (active) { cur = u2f(rec[14 + e]); incX = u2f(rec[6 + e]); incY = u2f(rec[10 + e]); }
-    step_chain(cur, incX, incY, ya - minY, r - rFirst, x0 + cA - minX, cA, cB, active, sm + e * 32u + r * 8u);
+    step_chain(cur, incX, incY, ya - minY, r - rFirst, x0 + cA - minX, cA, cB, active, sm + e * kChainStride + r * 8u);
   }
   __syncwarp();
 
@@ -1063,7 +1064,7 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
   bool upd = false;
   uint2 mk = make_uint2(0u, 0u);
   if (pass) {
-    const float o0 = sm[0 * 32 + lane], o1 = sm[1 * 32 + lane], o2 = sm[2 * 32 + lane], o3 = sm[3 * 32 + lane];
+    const float o0 = sm[0 * kChainStride + lane], o1 = sm[1 * kChainStride + lane], o2 = sm[2 * kChainStride + lane], o3 = sm[3 * kChainStride + lane];
     const uint32_t slope01 = rec[18], slope23 = rec[19];
     const uint32_t s0 = slope01 & 0xffffu, s1 = slope01 >> 16, s2 = slope23 & 0xffffu, s3 = slope23 >> 16;
     if (mode == kConvex) {
@@ -1098,19 +1099,19 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
     const bool active = r >= rLo && r <= rLast;
     const float s = -0.5f + 1.0f / 16.0f;
     const float cur = ORZ_FMA(dzdx, s + 0.125f * (float)(l & 3u), ORZ_FMA(dzdy, (l >> 2) ? s + 0.125f : s, u2f(rec[5])));
-    step_chain(cur, dzdx, dzdy, y0 + rLo - minY, r - rLo, x0 + cA - minX, cA, cB, active, sm + (4u + l) * 32u + r * 8u);
+    step_chain(cur, dzdx, dzdy, y0 + rLo - minY, r - rLo, x0 + cA - minX, cA, cB, active, sm + (4u + l) * kChainStride + r * 8u);
   }
   __syncwarp();
   // ---- depth rows, merge into the registers, HiZ (Rasterizer.cpp:1241-1290)
   if (upd) {
-    const float* smd = sm + 4 * 32 + lane;
+    const float* smd = sm + 4 * kChainStride + lane;
     const uint32_t keep = h != 1u ? 0xffffffffu : 0u;  // a cleared block is overwritten (:1271-1278)
     uint32_t r0[2][4], r4[2][4], r8[2][4];
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
       float dv[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) dv[k] = smd[(4 * rr + k) * 32];
+      for (int k = 0; k < 4; ++k) dv[k] = smd[(4 * rr + k) * kChainStride];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float a = dv[(2 * i) & 3], b = dv[(2 * i + 1) & 3];
@@ -1185,7 +1186,7 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
   const bool forceClip = (p.flags & ORZ_BATCH_FORCE_CLIPPED) != 0u;
   const uint4* recInfo = p.recInfo + (size_t)view * nOcc * 2u;
   uint16_t* myHiz = s_hiz + (size_t)warp * K * 32u + lane;  // + 32 k
-  float* myChain = s_chain + warp * (12 * 32);
+  float* myChain = s_chain + warp * (12 * kChainStride);
   uint32_t* myStage = s_stageAll + (uint32_t)warp * kStageCap * kRecStride;
   uint32_t* myIdx = s_idxAll + (uint32_t)warp * kStageCap;
   const uint32_t lx = (uint32_t)lane & 7u, ly = (uint32_t)lane >> 3;

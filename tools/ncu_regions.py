@@ -31,7 +31,7 @@ marks = [
 bounds = sorted((line_of(m), name) for name, m in marks)
 def region(f, n):
     if f != "orz_kernels.cu": return "inlined helpers (" + f + ")"
-    name = "(before)"
+    name = "helpers above step_chain (avg_u16x2, pack16 callers, block_fine_test, store_record)"
     for ln, nm in bounds:
         if n >= ln: name = nm
     return name
@@ -72,7 +72,7 @@ for r in rows[2:]:
     g["thr"] += int(r[ix["Predicated-On Thread Instructions Executed"]] or 0)
     g["smp"] += int(r[ix["# Samples"]] or 0)
 ti = sum(g["inst"] for g in agg.values()); ts = sum(g["smp"] for g in agg.values())
-print(f"{'region':42s} {'inst%':>7s} {'lanes':>6s} {'samples%':>9s}")
+print(f"{'region':60s} {'inst%':>7s} {'lanes':>6s} {'samples%':>9s}")
 for name, g in sorted(agg.items(), key=lambda kv: -kv[1]["inst"]):
-    print(f"{name:42s} {100*g['inst']/ti:7.2f} {g['thr']/max(1,g['inst']):6.1f} {100*g['smp']/max(1,ts):9.2f}")
+    print(f"{name[:60]:60s} {100*g['inst']/ti:7.2f} {g['thr']/max(1,g['inst']):6.1f} {100*g['smp']/max(1,ts):9.2f}")
 print(f"total warp instructions {ti:,}, samples {ts:,}")

@@ -896,6 +896,12 @@ __global__ void __launch_bounds__(GW * 32, (kTrav == 2 ? ORZ_THREADS_PER_SM_V2 :
 #ifndef ORZ_CLUSTER_GW
 #define ORZ_CLUSTER_GW 16
 #endif
+#ifndef ORZ_CLUSTER_LUT_SMEM
+#define ORZ_CLUSTER_LUT_SMEM 1  // edge-mask table staged in shared memory (0: read through L1)
+#endif
+#ifndef ORZ_CLUSTER_CTAS_PER_SM
+#define ORZ_CLUSTER_CTAS_PER_SM 0  // > 0: compile with __launch_bounds__(threads, this) instead of the register cap
+#endif
 #ifndef ORZ_CLUSTER_REGS
 #define ORZ_CLUSTER_REGS 96  // 16 warps x 96 registers leave room for one CTA of the query kernel on the same SM
 #endif
@@ -907,7 +913,7 @@ constexpr uint32_t kClusterMaxOcc = 2048;    // occluders per scene the cluster 
 constexpr uint32_t kHeadWords = 6;           // status, minX, maxX, minY, maxY, maxZ of kFrontWords
 
 struct ClusterSmem {
-  static constexpr uint32_t kLutWords = 4096 * 2;
+  static constexpr uint32_t kLutWords = ORZ_CLUSTER_LUT_SMEM ? 4096 * 2 : 0;
   static constexpr uint32_t kStageWords = kClusterGW * kStageCap * kRecStride;
   static constexpr uint32_t kIdxWords = kClusterGW * kStageCap;
   static constexpr uint32_t kChainWords = kClusterGW * 12 * kChainStride;
@@ -1149,7 +1155,11 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
 }
 
 template <int C>
+#if ORZ_CLUSTER_CTAS_PER_SM
+__global__ void __launch_bounds__(kClusterGW * 32, ORZ_CLUSTER_CTAS_PER_SM) k_raster_views_cluster(const FrameParams p) {
+#else
 __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const FrameParams p) {
+#endif
   constexpr uint32_t GW = kClusterGW, NT = GW * 32, kWarps = C * GW;
   extern __shared__ __align__(16) uint32_t s_dyn[];
   uint2* s_lut = reinterpret_cast<uint2*>(s_dyn);
@@ -1173,7 +1183,7 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
   const uint32_t nOcc = p.nOcc;
 
   const uint32_t* front = p.frontBuf + (size_t)view * nOcc * kFrontWords;
-  for (uint32_t i = tid; i < 4096u; i += NT) s_lut[i] = p.lut[i];
+  if (ORZ_CLUSTER_LUT_SMEM) for (uint32_t i = tid; i < 4096u; i += NT) s_lut[i] = p.lut[i];
   for (uint32_t i = tid; i < nOcc * kHeadWords; i += NT) s_head[i] = front[(size_t)(i / kHeadWords) * kFrontWords + i % kHeadWords];
   for (uint32_t i = tid; i < nOcc * 3u; i += NT) s_vis[i] = 0u;
 
@@ -1316,7 +1326,7 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
         for (int y = 0; y < 8; ++y) d[y] = load ? dp[y] : make_uint4(0u, 0u, 0u, 0u);
         bool dirty = false;
         for (; hits; hits &= hits - 1u)
-          tile_prim(myStage + ((uint32_t)__ffs((int)hits) - 1u) * kRecStride, lane, x0, y0, x1, y1, s_lut, myChain, d, h, dirty);
+          tile_prim(myStage + ((uint32_t)__ffs((int)hits) - 1u) * kRecStride, lane, x0, y0, x1, y1, ORZ_CLUSTER_LUT_SMEM ? s_lut : p.lut, myChain, d, h, dirty);
         if (dirty) {
 #pragma unroll
           for (int y = 0; y < 8; ++y) dp[y] = d[y];

@@ -232,8 +232,10 @@ def run_ours(args):
     cluster_path = n_views <= cluster_limit and blocks <= 65536
     scene = api.Scene.from_prepared(ctx, ps)
     n_boxes, n_occ, words = scene.n_boxes, scene.n_occluders, (scene.n_boxes + 31) // 32
+    # views dealt round-robin (rank, rank + world, ...): camera paths are coherent, contiguous slices of the Castle
+    # orbit differ in work by up to 1.7x (tools/slice_balance.py), which would measure the heaviest arc, not scaling
     mvps_all, poss_all = make_views(ps, kind, n_views * world, w, h)
-    mvps, poss = mvps_all[rank * n_views:(rank + 1) * n_views], poss_all[rank * n_views:(rank + 1) * n_views]
+    mvps, poss = np.ascontiguousarray(mvps_all[rank::world]), np.ascontiguousarray(poss_all[rank::world])
     with_targets = args.workload != "castle_512x256_probes"  # probes: visibility bits only (depth stays scratch)
 
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
@@ -337,7 +339,7 @@ def run_ours(args):
                        "outputs": "depth+HiZ+visibility bits per view (HBM resident)" if with_targets else "visibility bits per view",
                        "l2": f"working set per step {n_views * (2 * w * h + 2 * blocks) / 1e6:.0f} MB of per-view depth+HiZ, larger than the 126 MB L2" if with_targets
                              else "L2 flushed by construction: every view clears and rewrites its scratch target",
-                       "group_warps": args.group_warps or "auto", "parallelism": f"views sharded over {world} GPU(s), NCCL all-gather of bitmasks"},
+                       "group_warps": args.group_warps or "auto", "parallelism": f"views dealt round-robin to {world} GPU(s), NCCL all-gather of bitmasks"},
             "mquads_per_sec": quads_submitted * world / (kern / 1e3) / 1e6,
             "queries_per_sec": n_boxes * total_views / (kern / 1e3),
             "kernel_ms_per_step": kern, "step_ms": step_ms,
@@ -384,6 +386,11 @@ def run_ours(args):
 
 
 if __name__ == "__main__":
+    # the contract is ONE JSON line on stdout: libraries (NCCL prints its version banner there when NCCL_DEBUG is
+    # set) write to fd 1 directly, so fd 1 is pointed at stderr and the line goes to the original stdout
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
     a = parse()
     if a.impl == "reference":
         run_reference(a)

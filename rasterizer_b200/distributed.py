@@ -31,9 +31,18 @@ def all_gather_bits(local_bits, n_views: int):
     return out.view(world * local_bits.shape[0], -1)[:n_views]
 
 
-def render_views_sharded(scene, width, height, mvps, cam_pos=None, orders=None, flags=0, device=None):
+def interleaved_rows(n_views: int, rank: int, world: int):
+    """Views rank, rank + world, ... -> (indices, per_rank).  Camera paths are coherent, so contiguous
+    slices differ in work by up to 1.7x (Castle orbit, tools/slice_balance.py); interleaving gives
+    every rank the same mix."""
+    per = (n_views + world - 1) // world
+    return np.arange(rank, n_views, world), per
+
+
+def render_views_sharded(scene, width, height, mvps, cam_pos=None, orders=None, flags=0, device=None, balance="contiguous"):
     """Render rank's slice of `mvps` through the C ABI and gather every view's visibility bitmask.
-    Returns a torch int32 tensor [n_views, words] identical on all ranks."""
+    Returns a torch int32 tensor [n_views, words] identical on all ranks.  balance="interleaved"
+    deals the views round-robin instead of in contiguous slices (same result, even work)."""
     import torch
     import torch.distributed as dist
 
@@ -41,6 +50,18 @@ def render_views_sharded(scene, width, height, mvps, cam_pos=None, orders=None, 
     world = dist.get_world_size() if dist.is_initialized() else 1
     mvps = np.ascontiguousarray(mvps, np.float32).reshape(-1, 16)
     n = mvps.shape[0]
+    if balance == "interleaved":
+        idx, per = interleaved_rows(n, rank, world)
+        words = (scene.n_boxes + 31) // 32
+        local = np.zeros((per, words), np.uint32)
+        if idx.size:
+            kw = dict(orders=np.asarray(orders)[idx]) if orders is not None else dict(cam_pos=np.asarray(cam_pos)[idx])
+            local[: idx.size] = scene.render_views(width, height, mvps[idx], flags=flags, want=("vis",), **kw)["vis"]
+        t = torch.from_numpy(local.view(np.int32))
+        if device is not None:
+            t = t.to(device)
+        g = all_gather_bits(t, per * world)  # row r * per + i holds view i * world + r
+        return g.view(world, per, -1).transpose(0, 1).reshape(per * world, -1)[:n].contiguous()
     start, stop, per = view_slice(n, rank, world)
     words = (scene.n_boxes + 31) // 32
     local = np.zeros((per, words), np.uint32)

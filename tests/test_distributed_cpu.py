@@ -34,6 +34,27 @@ def _worker(rank, world, port, n_views, words, q):
     dist.destroy_process_group()
 
 
+class _FakeScene:
+    """Stands in for api.Scene on CPU: `render_views` fabricates the bits of the views it is handed
+    (identified by the first matrix element), so the sharding + gather logic runs without a GPU."""
+
+    n_boxes = 5 * 32
+
+    def render_views(self, width, height, mvps, flags=0, want=("vis",), **kw):
+        return {"vis": _fake_bits(np.asarray(mvps)[:, 0].astype(np.uint32), 5)}
+
+
+def _worker_sharded(rank, world, port, n_views, balance, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mvps = np.zeros((n_views, 16), np.float32)
+    mvps[:, 0] = np.arange(n_views)
+    out = D.render_views_sharded(_FakeScene(), 64, 64, mvps, cam_pos=np.zeros((n_views, 3), np.float32), balance=balance)
+    q.put((rank, out.numpy().view(np.uint32).copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -69,3 +90,23 @@ def test_view_slices_partition():
                 assert 0 <= b - a <= per
                 seen += list(range(a, b))
             assert seen == list(range(n))
+
+
+@pytest.mark.parametrize("balance", ["contiguous", "interleaved"])
+@pytest.mark.parametrize("n_views", [9, 2, 1])
+def test_render_views_sharded_world2(n_views, balance):
+    """Both ways of dealing views to ranks return every view's bits in view order on every rank."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_sharded, args=(r, world, port, n_views, balance, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = _fake_bits(range(n_views), 5)
+    for r in range(world):
+        assert np.array_equal(got[r], want), (balance, r)

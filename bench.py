@@ -228,7 +228,7 @@ def run_ours(args):
         ctx.set_group_warps(args.group_warps)
     if args.cluster_views >= 0:
         ctx.set_cluster_views(args.cluster_views)
-    cluster_limit = (args.cluster_views if args.cluster_views >= 0 else 1024) * (4 if blocks >= 8192 else 3) // 4
+    cluster_limit = args.cluster_views if args.cluster_views >= 0 else 1024
     cluster_path = n_views <= cluster_limit and blocks <= 65536
     scene = api.Scene.from_prepared(ctx, ps)
     n_boxes, n_occ, words = scene.n_boxes, scene.n_occluders, (scene.n_boxes + 31) // 32

@@ -1959,7 +1959,7 @@ extern "C" int orz_context_set_cluster_views(orz_context* ctx, int maxViews) {
   return ORZ_OK;
 }
 extern "C" int orz_context_set_cluster_size(orz_context* ctx, int ctas) {
-  if (!ctx || (ctas != 0 && ctas != 2 && ctas != 4 && ctas != 8 && ctas != 16)) return fail(ORZ_ERR_ARG, "cluster size must be 0, 2, 4, 8 or 16");
+  if (!ctx || (ctas != 0 && ctas != 1 && ctas != 2 && ctas != 4 && ctas != 8 && ctas != 16)) return fail(ORZ_ERR_ARG, "cluster size must be 0, 1, 2, 4, 8 or 16");
   ctx->clusterSize = ctas;
   return ORZ_OK;
 }
@@ -2362,7 +2362,7 @@ static int launch_cluster_t(orz_context* ctx, FrameParams p, uint32_t nViews, ui
 // views of the batch still fit the GPU in one wave; at least enough that a warp owns <= 32 tiles.
 static int launch_cluster(orz_context* ctx, const FrameParams& p, uint32_t nViews, uint32_t nBatch, cudaStream_t st) {
   const uint32_t nTiles = (((p.width >> 3) + kTileW - 1u) / kTileW) * (((p.height >> 3) + kTileH - 1u) / kTileH);
-  uint32_t c = 2;
+  uint32_t c = 1;
   while (c < 16u && c * kClusterGW < nTiles && nBatch * c * 2u <= (uint32_t)ctx->numSMs) c *= 2u;
   while (c < 16u && (nTiles + c * kClusterGW - 1u) / (c * kClusterGW) > 32u) c *= 2u;
   if (ctx->clusterSize) c = (uint32_t)ctx->clusterSize;
@@ -2375,7 +2375,8 @@ static int launch_cluster(orz_context* ctx, const FrameParams& p, uint32_t nView
       return launch_cluster_t<8>(ctx, p, nViews, nTiles, st);
     case 8: return launch_cluster_t<8>(ctx, p, nViews, nTiles, st);
     case 4: return launch_cluster_t<4>(ctx, p, nViews, nTiles, st);
-    default: return launch_cluster_t<2>(ctx, p, nViews, nTiles, st);
+    case 2: return launch_cluster_t<2>(ctx, p, nViews, nTiles, st);
+    default: return launch_cluster_t<1>(ctx, p, nViews, nTiles, st);
   }
 }
 
@@ -2456,8 +2457,8 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
     p.viewCost = (uint32_t*)(prep + chunk * sizeof(ViewMatrices) + chunk * nOcc * 4 + chunk * nOcc * kFrontWords * 4);
     const bool wide = (b->flags & ORZ_BATCH_NO_GATE) && ((b->flags & ORZ_BATCH_WIDE) || (nv <= 8u && scene->totalQuads >= 65536u));
     // (above 65 536 blocks the reference's 16-bit index wrap needs the linear traversal of the batch kernel)
-    // measured crossover with the batch kernel: ~2000 views at 1920x1080, ~800 at 512x256 (profiles/r1_few_views_*)
-    const uint32_t clusterLimit = blocks >= 8192u ? (uint32_t)ctx->clusterViews : (uint32_t)ctx->clusterViews * 3u / 4u;
+    // measured crossover with the batch kernel: ~2000 views at 1920x1080, ~1500 at 512x256 (profiles/r1_few_views_*)
+    const uint32_t clusterLimit = (uint32_t)ctx->clusterViews;
     const bool clusterPath = !wide && ctx->clusterViews > 0 && nv <= clusterLimit && blocks <= 65536u && nOcc <= kClusterMaxOcc &&
                              (size_t)nv * scene->totalQuads * (kRecStride * 4 + 8) <= (size_t(8) << 30);
     p.viewOrder = (nv <= 16384u && !(clusterPath && nv * 2u <= (uint32_t)ctx->numSMs)) ? p.viewCost + chunk : nullptr;

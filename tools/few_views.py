@@ -18,7 +18,7 @@ def main():
     sweep = [int(x) for x in os.environ.get('FEW_VIEWS_NV', '1,2,4,8,16,18,32,36,64,128').split(',')]
     paths = [("cluster", 1 << 20), ("cta", 0)] if not os.environ.get('FEW_VIEWS_ONLY_CLUSTER') else [("cluster", 1 << 20)]
     if os.environ.get('FEW_VIEWS_CSWEEP'):
-        paths = [("cluster", 1 << 20)] + [(f"c{c}", -c) for c in (2, 4, 8, 16)]
+        paths = [("cluster", 1 << 20)] + [(f"c{c}", -c) for c in (1, 2, 4, 8, 16)]
     for nv in sweep:
         mvps, poss = wl.camera_path(ps, nv, w, h)
         d_mvp, d_pos = torch.from_numpy(mvps).to(dev), torch.from_numpy(poss).to(dev)

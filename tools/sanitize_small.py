@@ -16,7 +16,7 @@ for gw in (1, 4, 8):
     out = sc.render_views(w, h, mvps, cam_pos=poss, want=("vis", "clip", "gate", "depth", "hiz", "quads"))
 ctx.set_group_warps(0)
 ctx.set_cluster_views(1024)   # the cluster path (speculative setup + dataflow cluster kernel), every cluster size
-for cs in (0, 2, 4, 8, 16):
+for cs in (0, 1, 2, 4, 8, 16):
     ctx.set_cluster_size(cs)
     out2 = sc.render_views(w, h, mvps, cam_pos=poss, want=("vis", "clip", "gate", "depth", "hiz", "quads"))
     assert all(np.array_equal(out[k], out2[k]) for k in out), cs

@@ -918,9 +918,9 @@ struct ClusterSmem {
   static constexpr uint32_t kIdxWords = kClusterGW * kStageCap;
   static constexpr uint32_t kChainWords = kClusterGW * 12 * kChainStride;
   static constexpr uint32_t kFixedWords = kLutWords + kStageWords + kIdxWords + kChainWords;
-  // + [nOcc][6] gate heads, 3 x [nOcc] decision words, [GW][K][32] u16 HiZ mirror, [GW][K] tile origins
+  // + [nOcc][6] gate heads, 3 x [nOcc] decision words, [GW][K][32] u16 HiZ mirror
   static size_t bytes(uint32_t tilesPerWarp, uint32_t nOcc) {
-    return (size_t)(kFixedWords + nOcc * (kHeadWords + 3u)) * 4 + (size_t)kClusterGW * tilesPerWarp * (32 * 2 + 4);
+    return (size_t)(kFixedWords + nOcc * (kHeadWords + 3u)) * 4 + (size_t)kClusterGW * tilesPerWarp * 32 * 2;
   }
 };
 
@@ -1202,31 +1202,17 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
   const uint32_t lx = (uint32_t)lane & 7u, ly = (uint32_t)lane >> 3;
   const bool reporter = rank == 0u && warp == 0 && lane == 0;  // writes the per-slot outputs of the view
 
-  // origins (in blocks, x | y << 16) of my tiles k = 0 .. K-1 (K <= 64); 0xffffffff = none
-  uint32_t* myTiles = reinterpret_cast<uint32_t*>(s_hiz + (size_t)GW * K * 32u) + (uint32_t)warp * K;
-  for (uint32_t k = (uint32_t)lane; k < K; k += 32u) {
-    const uint32_t t = gw + k * kWarps;
-    uint32_t xy = 0xffffffffu;
-    if (t < nTiles) { const uint32_t ty = t / tilesX; xy = ((t - ty * tilesX) * kTileW) | ((ty * kTileH) << 16); }
-    myTiles[k] = xy;
+  // lane k keeps the origin (in blocks) of my k-th tile; 0xffff = none
+  uint32_t tileX0 = 0xffffu, tileY0 = 0xffffu;
+  if ((uint32_t)lane < K) {
+    const uint32_t t = gw + (uint32_t)lane * kWarps;
+    if (t < nTiles) { const uint32_t ty = t / tilesX; tileX0 = (t - ty * tilesX) * kTileW; tileY0 = ty * kTileH; }
   }
-  __syncwarp();
-  // my tiles that meet the block rectangle [bx0, bx1] x [by0, by1] (inclusive), as a mask over k
-  auto tiles_meeting = [&](uint32_t bx0, uint32_t bx1, uint32_t by0, uint32_t by1) -> unsigned long long {
-    unsigned long long m = 0ull;
-    for (uint32_t k0 = 0; k0 < K; k0 += 32u) {
-      const uint32_t k = k0 + (uint32_t)lane;
-      const uint32_t xy = k < K ? myTiles[k] : 0xffffffffu;
-      const uint32_t tx = xy & 0xffffu, ty = xy >> 16;
-      m |= (unsigned long long)__ballot_sync(kFull, xy != 0xffffffffu && tx <= bx1 && tx + kTileW > bx0 && ty <= by1 && ty + kTileH > by0) << k0;
-    }
-    return m;
-  };
-  const unsigned long long allTiles = tiles_meeting(0u, 0xffffu, 0u, 0xffffu);
+  const uint32_t allTiles = __ballot_sync(kFull, tileX0 != 0xffffu);
   // clear (Rasterizer.cpp:107-121): HiZ := 1 on my tiles; depth is overwritten by the first update
-  for (unsigned long long m = allTiles; m; m &= m - 1ull) {
-    const uint32_t k = (uint32_t)__ffsll((long long)m) - 1u;
-    const uint32_t bx = (myTiles[k] & 0xffffu) + lx, by = (myTiles[k] >> 16) + ly;
+  for (uint32_t m = allTiles; m; m &= m - 1u) {
+    const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+    const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
     myHiz[32u * k] = 1;
     if (bx < T.blocksX && by < T.blocksY) T.hiz[by * T.blocksX + bx] = 1;
   }
@@ -1240,6 +1226,11 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
     old = __shfl_sync(kFull, old, 0);
     if (old == GW - 1u && lane < C) atomicAdd(cluster.map_shared_rank(&s_doneCta[s], (unsigned)lane), 1u);
   };
+  // my tiles that meet the block rectangle [bx0, bx1] x [by0, by1] (inclusive), as a mask over k
+  auto tiles_meeting = [&](uint32_t bx0, uint32_t bx1, uint32_t by0, uint32_t by1) -> uint32_t {
+    return __ballot_sync(kFull, tileX0 != 0xffffu && tileX0 <= bx1 && tileX0 + kTileW > bx0 && tileY0 <= by1 && tileY0 + kTileH > by0);
+  };
+
   // ---- candidates whose rectangle does not touch my tiles: answered before the walk starts
   for (uint32_t s = 0; s < nOcc; ++s) {
     const uint32_t* hd = s_head + s * kHeadWords;
@@ -1264,12 +1255,12 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
       const uint32_t minX = hd[1], maxX = hd[2], minY = hd[3], maxY = hd[4], maxZ = hd[5];
       const uint32_t bx0 = minX >> 3, bx1 = maxX >> 3, by0 = minY >> 3, by1 = maxY >> 3;
       const uint32_t* vis = s_vis + s;
-      unsigned long long tm = tiles_meeting(bx0, bx1, by0, by1);
+      uint32_t tm = tiles_meeting(bx0, bx1, by0, by1);
       if (tm && !ld_flag(vis)) {
         bool found = false;
-        for (; tm; tm &= tm - 1ull) {
-          const uint32_t k = (uint32_t)__ffsll((long long)tm) - 1u;
-          const uint32_t bx = (myTiles[k] & 0xffffu) + lx, by = (myTiles[k] >> 16) + ly;
+        for (; tm; tm &= tm - 1u) {
+          const uint32_t k = (uint32_t)__ffs((int)tm) - 1u;
+          const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
           if (ld_flag(vis)) break;  // another warp already found a visible pixel
           const bool hit = bx >= bx0 && bx <= bx1 && by >= by0 && by <= by1 && bx < T.blocksX && by < T.blocksY &&
                            query_block_h(T, bx, by, (uint32_t)myHiz[32u * k], minX, maxX, minY, maxY, maxZ);
@@ -1295,7 +1286,7 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
     if (!visible || info.x == 0u) continue;
 
     // ---- rasterize<clipped>(occluder): the records k_setup_views wrote, on my tiles
-    unsigned long long tmOcc = 0ull;
+    uint32_t tmOcc = 0u;
     if (box.x < box.z) tmOcc = tiles_meeting(box.x, box.z - 1u, box.y, box.w - 1u);
     if (!tmOcc) continue;
     const uint32_t cnt = info.x;
@@ -1312,9 +1303,9 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
       for (uint32_t i = 0; i < nStaged; ++i)
         if (lane < kRecStride) myStage[i * kRecStride + lane] = recs[(size_t)myIdx[i] * kRecStride + lane];
       __syncwarp();
-      for (unsigned long long m = tmOcc; m; m &= m - 1ull) {
-        const uint32_t k = (uint32_t)__ffsll((long long)m) - 1u;
-        const uint32_t x0 = myTiles[k] & 0xffffu, y0 = myTiles[k] >> 16;
+      for (uint32_t m = tmOcc; m; m &= m - 1u) {
+        const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+        const uint32_t x0 = __shfl_sync(kFull, tileX0, (int)k), y0 = __shfl_sync(kFull, tileY0, (int)k);
         const uint32_t x1 = min(x0 + kTileW, T.blocksX), y1 = min(y0 + kTileH, T.blocksY);
         bool touches = false;
         if ((uint32_t)lane < nStaged) {
@@ -1353,9 +1344,9 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
         hx0 = hdr.x & 0xffffu; hy0 = hdr.x >> 16; hx1 = hx0 + (hdr.y & 0xffffu); hy1 = hy0 + (hdr.y >> 16);
       }
       bool touches = false;
-      for (unsigned long long m = tmOcc; m; m &= m - 1ull) {
-        const int k = __ffsll((long long)m) - 1;
-        const uint32_t x0 = myTiles[k] & 0xffffu, y0 = myTiles[k] >> 16;
+      for (uint32_t m = tmOcc; m; m &= m - 1u) {
+        const int k = __ffs((int)m) - 1;
+        const uint32_t x0 = __shfl_sync(kFull, tileX0, k), y0 = __shfl_sync(kFull, tileY0, k);
         touches = touches || (hx0 < x0 + kTileW && hx1 > x0 && hy0 < y0 + kTileH && hy1 > y0);
       }
       uint32_t hits = __ballot_sync(kFull, touches);
@@ -1373,9 +1364,9 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
   if (p.quadsSubmitted && reporter) p.quadsSubmitted[view] = quadsSubmitted;
   if (p.exportDepth) {  // canonical depth for the caller: blocks that stayed cleared read as zero
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    for (unsigned long long m = allTiles; m; m &= m - 1ull) {
-      const uint32_t k = (uint32_t)__ffsll((long long)m) - 1u;
-      const uint32_t bx = (myTiles[k] & 0xffffu) + lx, by = (myTiles[k] >> 16) + ly;
+    for (uint32_t m = allTiles; m; m &= m - 1u) {
+      const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+      const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
       if (bx < T.blocksX && by < T.blocksY && myHiz[32u * k] == 1) {
         uint4* d4 = reinterpret_cast<uint4*>(T.depth) + (size_t)(by * T.blocksX + bx) * 8u;
 #pragma unroll
@@ -2373,15 +2364,14 @@ static int launch_cluster(orz_context* ctx, const FrameParams& p, uint32_t nView
   const uint32_t nTiles = (((p.width >> 3) + kTileW - 1u) / kTileW) * (((p.height >> 3) + kTileH - 1u) / kTileH);
   uint32_t c = 1;
   while (c < 16u && c * kClusterGW < nTiles && nBatch * c * 2u <= (uint32_t)ctx->numSMs) c *= 2u;
-  // at most 32 tiles per warp (measured at 1080p: 64 tiles on one CTA is slower than 32 on two); the kernel itself takes 64
   while (c < 16u && (nTiles + c * kClusterGW - 1u) / (c * kClusterGW) > 32u) c *= 2u;
   if (ctx->clusterSize) c = (uint32_t)ctx->clusterSize;
-  if ((nTiles + c * kClusterGW - 1u) / (c * kClusterGW) > 64u) return fail(ORZ_ERR_ARG, "cluster path: target too large for this cluster size");
+  if ((nTiles + c * kClusterGW - 1u) / (c * kClusterGW) > 32u) return fail(ORZ_ERR_ARG, "cluster path: target too large for this cluster size");
   switch (c) {
     case 16:  // non-portable cluster size: when the device (e.g. a partitioned one) cannot place it, use 8
       if (launch_cluster_t<16>(ctx, p, nViews, nTiles, st) == ORZ_OK) return ORZ_OK;
       (void)cudaGetLastError();
-      if ((nTiles + 8u * kClusterGW - 1u) / (8u * kClusterGW) > 64u) return fail(ORZ_ERR_CUDA, "cluster path: 16-CTA clusters are not available on this device");
+      if ((nTiles + 8u * kClusterGW - 1u) / (8u * kClusterGW) > 32u) return fail(ORZ_ERR_CUDA, "cluster path: 16-CTA clusters are not available on this device");
       return launch_cluster_t<8>(ctx, p, nViews, nTiles, st);
     case 8: return launch_cluster_t<8>(ctx, p, nViews, nTiles, st);
     case 4: return launch_cluster_t<4>(ctx, p, nViews, nTiles, st);

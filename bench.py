@@ -78,6 +78,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
+        self.t0 = time.perf_counter()
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -314,6 +315,11 @@ def run_ours(args):
         gather()
     sync_all()
     e2e_s = time.perf_counter() - t0
+    # nvidia-smi samples every 100 ms and the timed regions are tens of ms long: keep the same load running (untimed)
+    # until the sampler has seen at least half a second of it
+    while time.perf_counter() - sampler.t0 < 0.6:
+        scene.render_views_raw(dbatch, device=True)
+        torch.cuda.synchronize()
     clocks = sampler.stop()
     t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:

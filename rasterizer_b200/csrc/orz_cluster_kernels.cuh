@@ -1,0 +1,520 @@
+// Cluster path: speculative setup (k_setup_views) + dataflow cluster rasteriser (k_raster_views_cluster).
+// Part of the single translation unit orz_kernels.cu (included inside namespace orz); see DESIGN.md section 4.
+#pragma once
+
+// ---------------------------------------------------------------------------------------------
+// Few views (BASELINE configs 1 and 2 are ONE view): the latency path.  A single view is a chain
+// of dependent gate -> setup -> traversal steps (Main.cpp:192-206) and, inside one occluder,
+// primitives stack on the same blocks (Castle, default camera: ~300 in-order updates of one
+// block per frame), so what counts is the length of the dependency chain, not throughput.
+//
+//   k_setup_views           everything that does not depend on the depth buffer, at full width:
+//                           one CTA per (occluder that survives the frustum, view) sets up its
+//                           quads (Rasterizer.cpp:657-1086) and writes the valid primitives in
+//                           order as records + 8-byte bounding-box headers (speculative: the
+//                           gate may still reject the occluder)
+//   k_raster_views_cluster  one thread-block CLUSTER of C CTAs x 16 warps per view, run as a
+//                           DATAFLOW machine with no barrier in its main loop:
+//     * the screen is cut into TILES of 8x4 blocks; tile t belongs to warp t mod (16 C) of the
+//       cluster for the whole view, lane <-> block.  A tile is only ever read or written by its
+//       owner (gate included): no cross-SM traffic on depth / HiZ, order preserved per block;
+//     * every warp walks the occluders front to back at ITS OWN pace.  For a rectangle candidate
+//       it tests the part of the rectangle that lies on its tiles (query2D, Rasterizer.cpp:283-349)
+//       -- at that point it has applied every earlier visible occluder to those tiles, which is
+//       all the test depends on -- and either raises the candidate's `visible` flag in the shared
+//       memory of every CTA (DSMEM stores) or adds itself to the candidate's `done` count
+//       (per-CTA count, forwarded to every CTA by the CTA's last warp).  Warps whose tiles do not
+//       meet the rectangle are counted before the walk starts.  A candidate is visible as soon as
+//       ONE warp says so, invisible when all have said no: fast warps run ahead and only the true
+//       dependencies remain (sum over occluders of the slowest warp -> slowest warp's own total:
+//       660 -> 176 primitive-tile steps on the Castle default view);
+//     * TILE-MAJOR traversal: for each of its tiles a warp walks the occluder's primitives in
+//       order with the tile's depth held in REGISTERS (one 8x8 block = 8 x uint4 per lane) and
+//       its HiZ in a register + shared-memory mirror: a stacked primitive costs shared-memory and
+//       ALU latency only; the L2 round trip (load at first touch, store at the end) is paid once
+//       per (occluder, tile) instead of once per (primitive, block);
+//     * the edge-mask table (32 KB) lives in shared memory; records are gathered from L2 into a
+//       per-warp staging area 32 at a time with all loads in flight together.
+#ifndef ORZ_CLUSTER_GW
+#define ORZ_CLUSTER_GW 16
+#endif
+#ifndef ORZ_CLUSTER_LUT_SMEM
+#define ORZ_CLUSTER_LUT_SMEM 1  // edge-mask table staged in shared memory (0: read through L1)
+#endif
+#ifndef ORZ_CLUSTER_CTAS_PER_SM
+#define ORZ_CLUSTER_CTAS_PER_SM 0  // > 0: compile with __launch_bounds__(threads, this) instead of the register cap
+#endif
+#ifndef ORZ_CLUSTER_REGS
+#define ORZ_CLUSTER_REGS 96  // 16 warps x 96 registers leave room for one CTA of the query kernel on the same SM
+#endif
+constexpr int kClusterGW = ORZ_CLUSTER_GW;  // warps per CTA of the cluster kernel; registers per thread capped so that they fit one SM
+constexpr uint32_t kTileW = 8, kTileH = 4;   // blocks per tile: lane = 8 * (row in tile) + column in tile
+constexpr uint32_t kChainStride = 33;        // words between two chains' slots: the publishing lanes (chain, tile row) hit 32 different banks
+constexpr uint32_t kStageCap = 32;           // records a warp stages at a time
+constexpr uint32_t kClusterMaxOcc = 2048;    // occluders per scene the cluster path accepts (shared-memory decision arrays)
+constexpr uint32_t kHeadWords = 6;           // status, minX, maxX, minY, maxY, maxZ of kFrontWords
+
+struct ClusterSmem {
+  static constexpr uint32_t kLutWords = ORZ_CLUSTER_LUT_SMEM ? 4096 * 2 : 0;
+  static constexpr uint32_t kStageWords = kClusterGW * kStageCap * kRecStride;
+  static constexpr uint32_t kIdxWords = kClusterGW * kStageCap;
+  static constexpr uint32_t kChainWords = kClusterGW * 12 * kChainStride;
+  static constexpr uint32_t kFixedWords = kLutWords + kStageWords + kIdxWords + kChainWords;
+  // + [nOcc][6] gate heads, 3 x [nOcc] decision words, [GW][K][32] u16 HiZ mirror
+  static size_t bytes(uint32_t tilesPerWarp, uint32_t nOcc) {
+    return (size_t)(kFixedWords + nOcc * (kHeadWords + 3u)) * 4 + (size_t)kClusterGW * tilesPerWarp * 32 * 2;
+  }
+};
+
+// ---- speculative setup of every occluder that survives the frustum, Rasterizer.cpp:657-1086
+__global__ void __launch_bounds__(256) k_setup_views(const FrameParams p) {
+  __shared__ uint32_t s_cnt[8];
+  __shared__ uint32_t s_box[4];
+  const uint32_t slot = blockIdx.x, view = blockIdx.y, tid = threadIdx.x;
+  const int warp = (int)(tid >> 5), lane = (int)(tid & 31u);
+  const uint32_t* fr = p.frontBuf + ((size_t)view * p.nOcc + slot) * kFrontWords;
+  const uint32_t status = fr[0];
+  if (status == kBoxCulled) {
+    if (tid == 0) p.recInfo[((size_t)view * p.nOcc + slot) * 2u] = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  const bool useGate = (p.flags & ORZ_BATCH_NO_GATE) == 0u;
+  const bool clipped = status == kBoxNearClip ? (useGate ? true : (p.flags & ORZ_BATCH_FORCE_CLIPPED) != 0u) : false;
+  const uint32_t* order = p.orders ? p.orders + (size_t)view * p.nOcc : p.orderBuf + (size_t)view * p.nOcc;
+  const OccMeta& om = p.occ[order[slot]];
+  const RcpTable rt{p.rcp, p.rcpShift};
+  CallMatrix cm;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { cm.rx[k] = u2f(fr[6 + k]); cm.ry[k] = u2f(fr[10 + k]); cm.rw[k] = u2f(fr[14 + k]); }
+  cm.c0 = u2f(fr[18]); cm.c1 = u2f(fr[19]);
+  const int32_t blocksX = (int32_t)(p.width >> 3), blocksY = (int32_t)(p.height >> 3);
+  const size_t recBase = (size_t)view * p.totalQuads + om.quadOffset;  // records of this (view, occluder) start here
+  uint32_t* recs = p.recBuf + recBase * kRecStride;
+  uint2* hdrs = p.hdrBuf + recBase;
+  if (tid < 4) s_box[tid] = tid < 2 ? 0xffffffffu : 0u;
+  uint32_t written = 0;
+  uint32_t bx0 = 0xffffffffu, by0 = 0xffffffffu, bx1 = 0u, by1 = 0u;
+  for (uint32_t q0 = 0; q0 < om.quadCount; q0 += 256u) {
+    const uint32_t qi = q0 + tid;
+    bool ok = false;
+    Prim P;
+    if (qi < om.quadCount) {
+      const uint4 v = p.quads[om.quadOffset + qi];  // 128-bit coalesced load: the four packed vertices of this lane's quad
+      const uint32_t word[4] = {v.x, v.y, v.z, v.w};
+      ok = clipped ? setup_quad<true>(word, cm, rt, c_modeNibbles, blocksX, blocksY, P)
+                   : setup_quad<false>(word, cm, rt, c_modeNibbles, blocksX, blocksY, P);
+    }
+    const uint32_t valid = __ballot_sync(kFull, ok);
+    __syncthreads();  // s_cnt of the previous chunk has been read
+    if (lane == 0) s_cnt[warp] = (uint32_t)__popc(valid);
+    __syncthreads();
+    uint32_t base = written, total = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < 8; ++w2) { const uint32_t c = s_cnt[w2]; base += w2 < warp ? c : 0u; total += c; }
+    if (ok) {  // in order: binning by prefix-sum compaction
+      const uint32_t at = base + (uint32_t)__popc(valid & ((1u << lane) - 1u));
+      store_record(recs + (size_t)at * kRecStride, P);
+      hdrs[at] = make_uint2((uint32_t)P.minX | ((uint32_t)P.minY << 16), (uint32_t)P.rangeX | ((uint32_t)P.rangeY << 16));
+      bx0 = min(bx0, (uint32_t)P.minX); by0 = min(by0, (uint32_t)P.minY);
+      bx1 = max(bx1, (uint32_t)(P.minX + P.rangeX)); by1 = max(by1, (uint32_t)(P.minY + P.rangeY));
+    }
+    written += total;
+  }
+  bx0 = __reduce_min_sync(kFull, bx0); by0 = __reduce_min_sync(kFull, by0);
+  bx1 = __reduce_max_sync(kFull, bx1); by1 = __reduce_max_sync(kFull, by1);
+  __syncthreads();
+  if (lane == 0) { atomicMin(&s_box[0], bx0); atomicMin(&s_box[1], by0); atomicMax(&s_box[2], bx1); atomicMax(&s_box[3], by1); }
+  __syncthreads();
+  if (tid == 0) {
+    p.recInfo[((size_t)view * p.nOcc + slot) * 2u] = make_uint4(written, om.quadOffset, om.quadCount, 0u);
+    // block rectangle that holds every primitive of the occluder, half open (lo > hi when there is none)
+    p.recInfo[((size_t)view * p.nOcc + slot) * 2u + 1u] = make_uint4(s_box[0], s_box[1], s_box[2], s_box[3]);
+  }
+}
+
+// Decision words of the cluster kernel are read and written concurrently by design (monotonic
+// flags / counters): strong relaxed accesses at cluster scope, which the PTX memory model allows
+// to race (no data is published through them, only the decision itself).  compute-sanitizer's
+// racecheck still lists exactly these two accesses (it only exempts atomics); polling with
+// atomics instead was tried and starves the remote updates it is waiting for -- the kernel hangs.
+__device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_flag_remote(uint32_t* localPtr, uint32_t ctaRank, uint32_t val) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(localPtr)), "r"(ctaRank));
+  asm volatile("st.relaxed.cluster.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(val) : "memory");
+}
+
+// one block of query2D (Rasterizer.cpp:305-343) with the block's HiZ already at hand
+__device__ __forceinline__ bool query_block_h(const Target& T, uint32_t bx, uint32_t by, uint32_t h, uint32_t minX, uint32_t maxX,
+                                              uint32_t minY, uint32_t maxY, uint32_t maxZ) {
+  if (maxZ <= h) return false;  // Rasterizer.cpp:310
+  if (h == 1u) return true;     // cleared block: depth reads as 0 < maxZ (fresh state)
+  const int sX = max((int)minX - (int)(8u * bx), 0), eX = min((int)maxX - (int)(8u * bx), 7);
+  const int sY = max((int)minY - (int)(8u * by), 0), eY = min((int)maxY - (int)(8u * by), 7);
+  if (sX == 0 && eX == 7 && sY == 0 && eY == 7) return true;  // Rasterizer.cpp:319-325
+  return block_fine_test(T.depth, by * T.blocksX + bx, maxZ, sX, eX, sY, eY);
+}
+
+// One iterated chain for one tile row: nyCommon + nyExtra y steps, nPre x steps up to tile column
+// cA, then the values at tile columns [cA, cB] go to out[c].  Trip counts are warp uniform except
+// nyExtra (0-3, the row inside the tile); every add is the reference's own (same operands, same
+// order), only lanes differ in what they own.
+__device__ __forceinline__ void step_chain(float cur, const float incX, const float incY, const uint32_t nyCommon, const uint32_t nyExtra,
+                                           const uint32_t nPre, const uint32_t cA, const uint32_t cB, const bool active, float* out) {
+#pragma unroll kChainUnroll
+  for (uint32_t i = 0; i < nyCommon; ++i) cur = cur + incY;  // Rasterizer.cpp:1130-1131
+#pragma unroll
+  for (uint32_t i = 0; i < kTileH - 1u; ++i) cur = i < nyExtra ? cur + incY : cur;
+#pragma unroll kChainUnroll
+  for (uint32_t i = 0; i < nPre; ++i) cur = incX + cur;      // Rasterizer.cpp:1145-1146
+  for (uint32_t c = cA; c <= cB; ++c) {
+    if (active) out[c] = cur;
+    cur = incX + cur;
+  }
+}
+
+// One primitive on the tile a warp has open (Rasterizer.cpp:1098-1292 restricted to the tile's
+// blocks).  d[8] / h are the lane's block and its HiZ, kept in registers between primitives.
+__device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, const int lane, const uint32_t x0, const uint32_t y0,
+                                          const uint32_t x1, const uint32_t y1, const uint2* __restrict__ lut, float* __restrict__ sm,
+                                          uint4 (&d)[8], uint32_t& h, bool& dirty) {
+  const uint32_t w0 = rec[0], w1 = rec[1], w2 = rec[2];
+  const uint32_t minX = w0 & 0xffffu, minY = w0 >> 16, maxZ = w2 & 0xffffu, mode = w2 >> 16;
+  const uint32_t xa = max(minX, x0), xb = min(minX + (w1 & 0xffffu), x1), ya = max(minY, y0), yb = min(minY + (w1 >> 16), y1);
+  const uint32_t bx = x0 + ((uint32_t)lane & 7u), by = y0 + ((uint32_t)lane >> 3);
+  const bool pass = bx >= xa && bx < xb && by >= ya && by < yb && h < maxZ;  // Rasterizer.cpp:1148-1152
+  const uint32_t passMask = __ballot_sync(kFull, pass);
+  if (!passMask) return;  // the whole tile is behind its HiZ: no chain has to be stepped at all
+
+  // ---- the iterated add chains, stepped exactly as the reference does: y chain from the
+  // primitive's first row (Rasterizer.cpp:1130), x chain restarted at every row start (:1136,
+  // :1145).  One lane per (chain, tile row): first the 4 edge offsets x 4 rows (16 lanes); the
+  // 8 depth chains x 4 rows (32 lanes) only when some block is really covered.
+  const float dzdx = u2f(rec[3]), dzdy = u2f(rec[4]);
+  const uint32_t rFirst = ya - y0;
+  {
+    const uint32_t rLast = (31u - (uint32_t)__clz((int)passMask)) >> 3;
+    const uint32_t cols = (passMask | (passMask >> 8) | (passMask >> 16) | (passMask >> 24)) & 0xffu;
+    const uint32_t cA = (uint32_t)__ffs((int)cols) - 1u, cB = 31u - (uint32_t)__clz((int)cols);
+    const uint32_t r = (uint32_t)lane >> 2, e = (uint32_t)lane & 3u;
+    const bool active = lane < 16 && r >= rFirst && r <= rLast;
+    float cur = 0.0f, incX = 0.0f, incY = 0.0f;
+    if (active) { cur = u2f(rec[14 + e]); incX = u2f(rec[6 + e]); incY = u2f(rec[10 + e]); }
+    step_chain(cur, incX, incY, ya - minY, r - rFirst, x0 + cA - minX, cA, cB, active, sm + e * kChainStride + r * 8u);
+  }
+  __syncwarp();
+
+  // ---- coverage (Rasterizer.cpp:1155-1239)
+  bool upd = false;
+  uint2 mk = make_uint2(0u, 0u);
+  if (pass) {
+    const float o0 = sm[0 * kChainStride + lane], o1 = sm[1 * kChainStride + lane], o2 = sm[2 * kChainStride + lane], o3 = sm[3 * kChainStride + lane];
+    const uint32_t slope01 = rec[18], slope23 = rec[19];
+    const uint32_t s0 = slope01 & 0xffffu, s1 = slope01 >> 16, s2 = slope23 & 0xffffu, s3 = slope23 >> 16;
+    if (mode == kConvex) {
+      if (!(o0 >= 63.0f || o1 >= 63.0f || o2 >= 63.0f || o3 >= 63.0f)) {
+        const uint2 A = lut[s0 | (uint32_t)__float2int_rz(fmaxf(o0, 0.0f))], B = lut[s1 | (uint32_t)__float2int_rz(fmaxf(o1, 0.0f))];
+        const uint2 C2 = lut[s2 | (uint32_t)__float2int_rz(fmaxf(o2, 0.0f))], D = lut[s3 | (uint32_t)__float2int_rz(fmaxf(o3, 0.0f))];
+        mk.x = (A.x & B.x) & (C2.x & D.x); mk.y = (A.y & B.y) & (C2.y & D.y);
+        upd = true;  // no empty-mask test on this path (Rasterizer.cpp:1186)
+      }
+    } else {
+      const uint32_t q0 = o0 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o0, 0.0f), 63.0f)) : 0u;
+      const uint32_t q1 = o1 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o1, 0.0f), 63.0f)) : 0u;
+      const uint32_t q2 = o2 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o2, 0.0f), 63.0f)) : 0u;
+      const uint32_t q3 = o3 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o3, 0.0f), 63.0f)) : 0u;
+      const uint2 A = lut[s0 | q0], B = lut[s1 | q1], C2 = lut[s2 | q2], D = lut[s3 | q3];
+      if (mode == kTriangle0) { mk.x = A.x & B.x & C2.x; mk.y = A.y & B.y & C2.y; }
+      else if (mode == kTriangle1) { mk.x = A.x & C2.x & D.x; mk.y = A.y & C2.y & D.y; }
+      else if (mode == kConcaveRight) { mk.x = (A.x | D.x) & (B.x & C2.x); mk.y = (A.y | D.y) & (B.y & C2.y); }
+      else if (mode == kConcaveCenter) { mk.x = (A.x & B.x) | (C2.x & D.x); mk.y = (A.y & B.y) | (C2.y & D.y); }
+      else { mk.x = (A.x & D.x) & (B.x | C2.x); mk.y = (A.y & D.y) & (B.y | C2.y); }
+      upd = (mk.x | mk.y) != 0u;
+    }
+  }
+  const uint32_t updMask = __ballot_sync(kFull, upd);
+  __syncwarp();  // orders this primitive's reads of the edge slots before the next primitive's writes (free: the warp is converged)
+  if (!updMask) return;
+  {  // the eight depth lanes (Rasterizer.cpp:1103-1112) at the covered blocks
+    const uint32_t rLast = (31u - (uint32_t)__clz((int)updMask)) >> 3, rLo = ((uint32_t)__ffs((int)updMask) - 1u) >> 3;
+    const uint32_t cols = (updMask | (updMask >> 8) | (updMask >> 16) | (updMask >> 24)) & 0xffu;
+    const uint32_t cA = (uint32_t)__ffs((int)cols) - 1u, cB = 31u - (uint32_t)__clz((int)cols);
+    const uint32_t r = (uint32_t)lane >> 3, l = (uint32_t)lane & 7u;
+    const bool active = r >= rLo && r <= rLast;
+    const float s = -0.5f + 1.0f / 16.0f;
+    const float cur = ORZ_FMA(dzdx, s + 0.125f * (float)(l & 3u), ORZ_FMA(dzdy, (l >> 2) ? s + 0.125f : s, u2f(rec[5])));
+    step_chain(cur, dzdx, dzdy, y0 + rLo - minY, r - rLo, x0 + cA - minX, cA, cB, active, sm + (4u + l) * kChainStride + r * 8u);
+  }
+  __syncwarp();
+  // ---- depth rows, merge into the registers, HiZ (Rasterizer.cpp:1241-1290)
+  if (upd) {
+    const float* smd = sm + 4 * kChainStride + lane;
+    const uint32_t keep = h != 1u ? 0xffffffffu : 0u;  // a cleared block is overwritten (:1271-1278)
+    uint32_t r0[2][4], r4[2][4], r8[2][4];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      float dv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dv[k] = smd[(4 * rr + k) * kChainStride];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a = dv[(2 * i) & 3], b = dv[(2 * i + 1) & 3];
+        if (i >= 2) { a = ORZ_FMA(dzdx, 0.5f, a); b = ORZ_FMA(dzdx, 0.5f, b); }  // depth1, :1243
+        const float a8 = dzdy + a, b8 = dzdy + b;                                // depth8/9, :1244-1245
+        r0[rr][i] = pack16(a) | (pack16(b) << 16);  // (a run-time "finite plane" shortcut for the NaN guard was measured slower)
+        r8[rr][i] = pack16(a8) | (pack16(b8) << 16);
+        r4[rr][i] = avg_u16x2(r0[rr][i], r8[rr][i]);                             // :1252
+      }
+    }
+    uint32_t mnAcc = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int y = 2 * k + rr;
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          w[i] = k == 0 ? r0[rr][i] : k == 2 ? r4[rr][i] : k == 1 ? avg_u16x2(r0[rr][i], r4[rr][i]) : avg_u16x2(r4[rr][i], r8[rr][i]);  // :1253-1254
+        const int ky = (rr ? 0 : 4) + k;  // pixel px of row y <-> bit 8 px + ky (:1257-1268)
+        const uint32_t lo = ((mk.x >> ky) & 0x01010101u) * 0xffu, hi = ((mk.y >> ky) & 0x01010101u) * 0xffu;
+        uint4 v;
+        v.x = __vmaxu2(w[0] & __byte_perm(lo, 0u, 0x1100), d[y].x & keep);
+        v.y = __vmaxu2(w[1] & __byte_perm(lo, 0u, 0x3322), d[y].y & keep);
+        v.z = __vmaxu2(w[2] & __byte_perm(hi, 0u, 0x1100), d[y].z & keep);
+        v.w = __vmaxu2(w[3] & __byte_perm(hi, 0u, 0x3322), d[y].w & keep);
+        d[y] = v;
+        mnAcc = __vminu2(mnAcc, __vminu2(__vminu2(v.x, v.y), __vminu2(v.z, v.w)));
+      }
+    h = min(mnAcc & 0xffffu, mnAcc >> 16);  // Rasterizer.cpp:1287-1290
+    dirty = true;
+  }
+  __syncwarp();  // chain slots are rewritten by the next primitive
+}
+
+template <int C>
+#if ORZ_CLUSTER_CTAS_PER_SM
+__global__ void __launch_bounds__(kClusterGW * 32, ORZ_CLUSTER_CTAS_PER_SM) k_raster_views_cluster(const FrameParams p) {
+#else
+__global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const FrameParams p) {
+#endif
+  constexpr uint32_t GW = kClusterGW, NT = GW * 32, kWarps = C * GW;
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  uint2* s_lut = reinterpret_cast<uint2*>(s_dyn);
+  uint32_t* s_stageAll = s_dyn + ClusterSmem::kLutWords;
+  uint32_t* s_idxAll = s_stageAll + ClusterSmem::kStageWords;
+  float* s_chain = reinterpret_cast<float*>(s_idxAll + ClusterSmem::kIdxWords);
+  uint32_t* s_head = s_dyn + ClusterSmem::kFixedWords;     // [nOcc][6]: status + gate rectangle of every order slot
+  uint32_t* s_vis = s_head + p.nOcc * kHeadWords;          // [nOcc]: some warp saw a visible pixel
+  uint32_t* s_doneLocal = s_vis + p.nOcc;                  // [nOcc]: warps of THIS CTA that answered "not on my tiles"
+  uint32_t* s_doneCta = s_doneLocal + p.nOcc;              // [nOcc]: CTAs of the cluster whose 16 warps all answered
+  uint16_t* s_hiz = reinterpret_cast<uint16_t*>(s_doneCta + p.nOcc);  // [GW][K][32]: HiZ of the tiles my warps own
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const uint32_t rank = cluster.block_rank();
+  const uint32_t vrank = p.viewBase + blockIdx.x / (uint32_t)C;
+  const uint32_t view = p.viewOrder ? p.viewOrder[vrank] : vrank;  // longest first: clusters are scheduled in grid order
+  const uint32_t tid = threadIdx.x;
+  const int warp = (int)(tid >> 5), lane = (int)(tid & 31u);
+  const uint32_t gw = (uint32_t)warp * (uint32_t)C + rank;  // my tiles: t % kWarps == gw
+  const uint32_t K = p.clusterK;
+  const uint32_t nOcc = p.nOcc;
+
+  const uint32_t* front = p.frontBuf + (size_t)view * nOcc * kFrontWords;
+  if (ORZ_CLUSTER_LUT_SMEM) for (uint32_t i = tid; i < 4096u; i += NT) s_lut[i] = p.lut[i];
+  for (uint32_t i = tid; i < nOcc * kHeadWords; i += NT) s_head[i] = front[(size_t)(i / kHeadWords) * kFrontWords + i % kHeadWords];
+  for (uint32_t i = tid; i < nOcc * 3u; i += NT) s_vis[i] = 0u;
+
+  Target T;
+  T.width = p.width; T.height = p.height; T.blocksX = p.width >> 3; T.blocksY = p.height >> 3;
+  T.depth = p.depth + (size_t)view * p.depthStride;
+  T.hiz = p.hiz + (size_t)view * p.hizStride;
+  const uint32_t tilesX = (T.blocksX + kTileW - 1u) / kTileW, tilesY = (T.blocksY + kTileH - 1u) / kTileH, nTiles = tilesX * tilesY;
+  const bool useGate = (p.flags & ORZ_BATCH_NO_GATE) == 0u;
+  const bool forceClip = (p.flags & ORZ_BATCH_FORCE_CLIPPED) != 0u;
+  const uint4* recInfo = p.recInfo + (size_t)view * nOcc * 2u;
+  uint16_t* myHiz = s_hiz + (size_t)warp * K * 32u + lane;  // + 32 k
+  float* myChain = s_chain + warp * (12 * kChainStride);
+  uint32_t* myStage = s_stageAll + (uint32_t)warp * kStageCap * kRecStride;
+  uint32_t* myIdx = s_idxAll + (uint32_t)warp * kStageCap;
+  const uint32_t lx = (uint32_t)lane & 7u, ly = (uint32_t)lane >> 3;
+  const bool reporter = rank == 0u && warp == 0 && lane == 0;  // writes the per-slot outputs of the view
+
+  // lane k keeps the origin (in blocks) of my k-th tile; 0xffff = none
+  uint32_t tileX0 = 0xffffu, tileY0 = 0xffffu;
+  if ((uint32_t)lane < K) {
+    const uint32_t t = gw + (uint32_t)lane * kWarps;
+    if (t < nTiles) { const uint32_t ty = t / tilesX; tileX0 = (t - ty * tilesX) * kTileW; tileY0 = ty * kTileH; }
+  }
+  const uint32_t allTiles = __ballot_sync(kFull, tileX0 != 0xffffu);
+  // clear (Rasterizer.cpp:107-121): HiZ := 1 on my tiles; depth is overwritten by the first update
+  for (uint32_t m = allTiles; m; m &= m - 1u) {
+    const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+    const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
+    myHiz[32u * k] = 1;
+    if (bx < T.blocksX && by < T.blocksY) T.hiz[by * T.blocksX + bx] = 1;
+  }
+  __syncwarp();
+  cluster.sync();  // tables staged, decision words zero in every CTA before the first remote access
+
+  // "no visible pixel on my tiles" for candidate s: per-CTA count, forwarded by the CTA's last warp
+  auto answer_no = [&](uint32_t s) {
+    uint32_t old = 0u;
+    if (lane == 0) old = atomicAdd(&s_doneLocal[s], 1u);
+    old = __shfl_sync(kFull, old, 0);
+    if (old == GW - 1u && lane < C) atomicAdd(cluster.map_shared_rank(&s_doneCta[s], (unsigned)lane), 1u);
+  };
+  // my tiles that meet the block rectangle [bx0, bx1] x [by0, by1] (inclusive), as a mask over k
+  auto tiles_meeting = [&](uint32_t bx0, uint32_t bx1, uint32_t by0, uint32_t by1) -> uint32_t {
+    return __ballot_sync(kFull, tileX0 != 0xffffu && tileX0 <= bx1 && tileX0 + kTileW > bx0 && tileY0 <= by1 && tileY0 + kTileH > by0);
+  };
+
+  // ---- candidates whose rectangle does not touch my tiles: answered before the walk starts
+  for (uint32_t s = 0; s < nOcc; ++s) {
+    const uint32_t* hd = s_head + s * kHeadWords;
+    if (hd[0] != kBoxRect) continue;
+    if (!tiles_meeting(hd[1] >> 3, hd[2] >> 3, hd[3] >> 3, hd[4] >> 3)) answer_no(s);
+  }
+
+  uint32_t quadsSubmitted = 0;
+  for (uint32_t s = 0; s < nOcc; ++s) {
+    const uint32_t* hd = s_head + s * kHeadWords;
+    const uint32_t status = hd[0];
+    if (status == kBoxCulled) {
+      if (p.gate && reporter) p.gate[(size_t)view * nOcc + s] = 0;
+      continue;
+    }
+    const uint4 info = recInfo[2u * s], box = recInfo[2u * s + 1u];  // requested now, needed after the gate
+    bool visible = true, clipped = false;
+    if (status == kBoxNearClip) {
+      clipped = useGate ? true : forceClip;
+    } else {
+      // ---- gate: query2D (Rasterizer.cpp:283-349) on the part of the rectangle that lies on my tiles
+      const uint32_t minX = hd[1], maxX = hd[2], minY = hd[3], maxY = hd[4], maxZ = hd[5];
+      const uint32_t bx0 = minX >> 3, bx1 = maxX >> 3, by0 = minY >> 3, by1 = maxY >> 3;
+      const uint32_t* vis = s_vis + s;
+      uint32_t tm = tiles_meeting(bx0, bx1, by0, by1);
+      if (tm && !ld_flag(vis)) {
+        bool found = false;
+        for (; tm; tm &= tm - 1u) {
+          const uint32_t k = (uint32_t)__ffs((int)tm) - 1u;
+          const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
+          if (ld_flag(vis)) break;  // another warp already found a visible pixel
+          const bool hit = bx >= bx0 && bx <= bx1 && by >= by0 && by <= by1 && bx < T.blocksX && by < T.blocksY &&
+                           query_block_h(T, bx, by, (uint32_t)myHiz[32u * k], minX, maxX, minY, maxY, maxZ);
+          if (__any_sync(kFull, hit)) { found = true; break; }
+        }
+        if (found) { if (lane < C) st_flag_remote(s_vis + s, (uint32_t)lane, 1u); }
+        else if (!ld_flag(vis)) answer_no(s);
+      }
+      // visible as soon as ONE warp says so, invisible when all 16 C warps have said no
+      const uint32_t* done = s_doneCta + s;
+      for (;;) {
+        if (ld_flag(vis)) break;
+        if (ld_flag(done) >= (uint32_t)C) { visible = ld_flag(vis) != 0u; break; }
+#if ORZ_SPIN_NAP
+        __nanosleep(ORZ_SPIN_NAP);  // (a longer or growing nap was measured slower: the wake-up delay sits on the dependency chain)
+#endif
+      }
+    }
+    if (reporter) {
+      if (p.gate) p.gate[(size_t)view * nOcc + s] = (uint8_t)((visible ? 1 : 0) | (clipped && useGate ? 2 : 0));
+      if (visible) quadsSubmitted += info.z;
+    }
+    if (!visible || info.x == 0u) continue;
+
+    // ---- rasterize<clipped>(occluder): the records k_setup_views wrote, on my tiles
+    uint32_t tmOcc = 0u;
+    if (box.x < box.z) tmOcc = tiles_meeting(box.x, box.z - 1u, box.y, box.w - 1u);
+    if (!tmOcc) continue;
+    const uint32_t cnt = info.x;
+    const size_t recBase = (size_t)view * p.totalQuads + info.y;
+    const uint32_t* recs = p.recBuf + recBase * kRecStride;
+    const uint2* hdrs = p.hdrBuf + recBase;
+    if ((uint32_t)lane * 16u < cnt) prefetch_l1(hdrs + (uint32_t)lane * 16u);  // <= 504 headers = 32 lines
+
+    uint32_t nStaged = 0;
+    // staged records -> my tiles, tile-major, each tile's primitives in order
+    auto flush = [&]() {
+      __syncwarp();
+#pragma unroll 8
+      for (uint32_t i = 0; i < nStaged; ++i)
+        if (lane < kRecStride) myStage[i * kRecStride + lane] = recs[(size_t)myIdx[i] * kRecStride + lane];
+      __syncwarp();
+      for (uint32_t m = tmOcc; m; m &= m - 1u) {
+        const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+        const uint32_t x0 = __shfl_sync(kFull, tileX0, (int)k), y0 = __shfl_sync(kFull, tileY0, (int)k);
+        const uint32_t x1 = min(x0 + kTileW, T.blocksX), y1 = min(y0 + kTileH, T.blocksY);
+        bool touches = false;
+        if ((uint32_t)lane < nStaged) {
+          const uint32_t a = myStage[lane * kRecStride], b = myStage[lane * kRecStride + 1];
+          const uint32_t minX = a & 0xffffu, minY = a >> 16;
+          touches = minX < x1 && minX + (b & 0xffffu) > x0 && minY < y1 && minY + (b >> 16) > y0;
+        }
+        uint32_t hits = __ballot_sync(kFull, touches);
+        if (!hits) continue;
+        // bring the tile into registers
+        const uint32_t bx = x0 + lx, by = y0 + ly;
+        const bool inScreen = bx < x1 && by < y1;
+        uint4* dp = reinterpret_cast<uint4*>(T.depth) + (size_t)(by * T.blocksX + bx) * 8u;
+        uint32_t h = inScreen ? (uint32_t)myHiz[32u * k] : 0xffffu;  // off-screen lanes never pass
+        const bool load = inScreen && h != 1u;
+        uint4 d[8];
+#pragma unroll
+        for (int y = 0; y < 8; ++y) d[y] = load ? dp[y] : make_uint4(0u, 0u, 0u, 0u);
+        bool dirty = false;
+        for (; hits; hits &= hits - 1u)
+          tile_prim(myStage + ((uint32_t)__ffs((int)hits) - 1u) * kRecStride, lane, x0, y0, x1, y1, ORZ_CLUSTER_LUT_SMEM ? s_lut : p.lut, myChain, d, h, dirty);
+        if (dirty) {
+#pragma unroll
+          for (int y = 0; y < 8; ++y) dp[y] = d[y];
+          myHiz[32u * k] = (uint16_t)h;
+          T.hiz[by * T.blocksX + bx] = (uint16_t)h;
+        }
+      }
+      __syncwarp();
+      nStaged = 0;
+    };
+    for (uint32_t r0 = 0; r0 < cnt; r0 += 32u) {
+      uint32_t hx0 = 0, hx1 = 0, hy0 = 0, hy1 = 0;  // empty
+      if (r0 + (uint32_t)lane < cnt) {
+        const uint2 hdr = hdrs[r0 + (uint32_t)lane];
+        hx0 = hdr.x & 0xffffu; hy0 = hdr.x >> 16; hx1 = hx0 + (hdr.y & 0xffffu); hy1 = hy0 + (hdr.y >> 16);
+      }
+      bool touches = false;
+      for (uint32_t m = tmOcc; m; m &= m - 1u) {
+        const int k = __ffs((int)m) - 1;
+        const uint32_t x0 = __shfl_sync(kFull, tileX0, k), y0 = __shfl_sync(kFull, tileY0, k);
+        touches = touches || (hx0 < x0 + kTileW && hx1 > x0 && hy0 < y0 + kTileH && hy1 > y0);
+      }
+      uint32_t hits = __ballot_sync(kFull, touches);
+      while (hits) {
+        const uint32_t take = min(kStageCap - nStaged, (uint32_t)__popc(hits));
+        const uint32_t myRank = (uint32_t)__popc(hits & ((1u << lane) - 1u));
+        if (((hits >> lane) & 1u) && myRank < take) myIdx[nStaged + myRank] = r0 + (uint32_t)lane;
+        for (uint32_t i = 0; i < take; ++i) hits &= hits - 1u;
+        nStaged += take;
+        if (nStaged == kStageCap) flush();
+      }
+    }
+    if (nStaged) flush();
+  }
+  if (p.quadsSubmitted && reporter) p.quadsSubmitted[view] = quadsSubmitted;
+  if (p.exportDepth) {  // canonical depth for the caller: blocks that stayed cleared read as zero
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t m = allTiles; m; m &= m - 1u) {
+      const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+      const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
+      if (bx < T.blocksX && by < T.blocksY && myHiz[32u * k] == 1) {
+        uint4* d4 = reinterpret_cast<uint4*>(T.depth) + (size_t)(by * T.blocksX + bx) * 8u;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) d4[y] = z;
+      }
+    }
+  }
+  cluster.sync();  // no CTA may leave while another one can still write its decision words
+}

@@ -1,10 +1,11 @@
 """Instruction / stall-sample shares of the cluster kernel by code region (source line ranges of
-orz_kernels.cu found by their marker comments), from an ncu report with --import-source on.
+orz_cluster_kernels.cuh found by their marker comments), from an ncu report with --import-source on.
 usage: python tools/ncu_regions.py <report.ncu-rep> <kernel-substring>"""
 import csv, os, re, subprocess, sys, tempfile, collections
 rep, kern = sys.argv[1], sys.argv[2]
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-src = open(os.path.join(root, "rasterizer_b200", "csrc", "orz_kernels.cu")).read().splitlines()
+SRC = "orz_cluster_kernels.cuh"
+src = open(os.path.join(root, "rasterizer_b200", "csrc", SRC)).read().splitlines()
 def line_of(marker):
     for i, l in enumerate(src):
         if marker in l: return i + 1
@@ -26,12 +27,11 @@ marks = [
     ("flush: tile close (store)", "        if (dirty) {"),
     ("header scan + staging", "    for (uint32_t r0 = 0; r0 < cnt; r0 += 32u) {"),
     ("epilogue (zero fill, final barrier)", "  if (p.quadsSubmitted && reporter)"),
-    ("(after kernel)", "// queryVisibility for every (view, occludee box) on the finished buffers"),
 ]
 bounds = sorted((line_of(m), name) for name, m in marks)
 def region(f, n):
-    if f != "orz_kernels.cu": return "inlined helpers (" + f + ")"
-    name = "helpers above step_chain (avg_u16x2, pack16 callers, block_fine_test, store_record)"
+    if f != SRC: return "inlined helpers (" + f + ")"
+    name = "setup kernel / helpers above step_chain (k_setup_views, query_block_h, decision words)"
     for ln, nm in bounds:
         if n >= ln: name = nm
     return name
@@ -47,12 +47,12 @@ for l in dis:
     if not infn: continue
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)(.*)', l)
     if m:
-        # innermost frame of an inlined chain names the helper; keep the OUTERMOST orz_kernels.cu line for the region
+        # innermost frame of an inlined chain names the helper; keep the OUTERMOST line of the cluster file for the region
         f, n, rest = os.path.basename(m.group(1)), int(m.group(2)), m.group(3)
         if "inlined at" in rest:
             mm = re.findall(r'"([^"]+)", line (\d+)', rest)
-            outer = [(os.path.basename(a), int(b)) for a, b in mm if os.path.basename(a) == "orz_kernels.cu"]
-            cur = outer[0] if (f != "orz_kernels.cu" and outer) else (f, n)
+            outer = [(os.path.basename(a), int(b)) for a, b in mm if os.path.basename(a) == SRC]
+            cur = outer[0] if (f != SRC and outer) else (f, n)
         else:
             cur = (f, n)
         continue

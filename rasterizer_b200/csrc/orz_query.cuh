@@ -62,24 +62,22 @@ __device__ __forceinline__ bool query2d_warp(const Target& T, const BoxFront& f,
     const uint32_t minY = __shfl_sync(kFull, f.minY, src), maxY = __shfl_sync(kFull, f.maxY, src);
     const uint32_t maxZ = __shfl_sync(kFull, f.maxZ, src);
     const uint32_t bx0 = minX >> 3, by0 = minY >> 3;
-    const uint32_t cols = (maxX >> 3) - bx0 + 1u, n = cols * ((maxY >> 3) - by0 + 1u);
-    const uint32_t magic = (65536u + cols - 1u) / cols;  // i / cols ~ (i * magic) >> 16, at most one too large (i < 65536)
+    const uint32_t cols = (maxX >> 3) - bx0 + 1u, rows = (maxY >> 3) - by0 + 1u;
+    // lane j starts at block j of the rectangle (row major) and advances 32 blocks at a time:
+    // (row, column) are stepped incrementally, two divisions per box instead of one per block
+    const uint32_t q32 = 32u / cols, r32 = 32u - q32 * cols;
+    uint32_t ry = (uint32_t)lane / cols, rx = (uint32_t)lane - ry * cols;
     bool found = false;
     // 128 blocks per step: the four HiZ reads of a lane are in flight together (a fully occluded
     // large box is a chain of dependent L2 round trips otherwise); fine tests only where needed
-    for (uint32_t base = 0; base < n && !found; base += 128u) {
+    while (__any_sync(kFull, ry < rows) && !found) {
       uint32_t h[4], bxs[4], bys[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const uint32_t i = base + (uint32_t)u * 32u + (uint32_t)lane;
-        h[u] = 0xffffu;  // maxZ <= 0xffff: skipped
-        bxs[u] = bys[u] = 0u;
-        if (i < n) {
-          uint32_t ry = n <= 65536u ? (i * magic) >> 16 : i / cols;
-          if (ry * cols > i) --ry;
-          bxs[u] = bx0 + (i - ry * cols); bys[u] = by0 + ry;
-          h[u] = T.hiz[bys[u] * T.blocksX + bxs[u]];
-        }
+        bxs[u] = bx0 + rx; bys[u] = by0 + ry;
+        h[u] = ry < rows ? (uint32_t)T.hiz[bys[u] * T.blocksX + bxs[u]] : 0xffffu;  // maxZ <= 0xffff: skipped
+        rx += r32; ry += q32;
+        if (rx >= cols) { rx -= cols; ++ry; }
       }
       bool hit = false;
       uint32_t fine = 0u;

@@ -88,7 +88,14 @@ __global__ void __launch_bounds__(256) k_setup_views(const FrameParams p) {
   for (int k = 0; k < 4; ++k) { cm.rx[k] = u2f(fr[6 + k]); cm.ry[k] = u2f(fr[10 + k]); cm.rw[k] = u2f(fr[14 + k]); }
   cm.c0 = u2f(fr[18]); cm.c1 = u2f(fr[19]);
   const int32_t blocksX = (int32_t)(p.width >> 3), blocksY = (int32_t)(p.height >> 3);
-  const size_t recBase = (size_t)view * p.totalQuads + om.quadOffset;  // records of this (view, occluder) start here
+  // Above 65 536 blocks the reference wraps the first-block index to 16 bits (Rasterizer.cpp:1054): a
+  // primitive row then starts at linear block fb + by * blocksX, which can straddle two screen rows.
+  // In screen space that is at most TWO rectangles sharing the primitive's chains: the second one
+  // starts `split` blocks into every chain row (record word 20 = x steps to skip).
+  const bool wrap = (uint32_t)blocksX * (uint32_t)blocksY > 65536u;
+  const uint32_t recSlots = wrap ? 2u : 1u;  // records a quad can produce
+  const uint32_t slotBase = om.quadOffset * recSlots;
+  const size_t recBase = (size_t)view * p.totalQuads + slotBase;  // records of this (view, occluder) start here
   uint32_t* recs = p.recBuf + recBase * kRecStride;
   uint2* hdrs = p.hdrBuf + recBase;
   if (tid < 4) s_box[tid] = tid < 2 ? 0xffffffffu : 0u;
@@ -104,19 +111,41 @@ __global__ void __launch_bounds__(256) k_setup_views(const FrameParams p) {
       ok = clipped ? setup_quad<true>(word, cm, rt, c_modeNibbles, blocksX, blocksY, P)
                    : setup_quad<false>(word, cm, rt, c_modeNibbles, blocksX, blocksY, P);
     }
-    const uint32_t valid = __ballot_sync(kFull, ok);
+    // screen rectangles of the primitive: {x, y, w, h, chain x offset}
+    uint32_t nPieces = ok ? 1u : 0u;
+    uint32_t px[2] = {0u, 0u}, py[2] = {0u, 0u}, pw[2] = {0u, 0u}, ph[2] = {0u, 0u}, pskip[2] = {0u, 0u};
+    if (ok) {
+      px[0] = (uint32_t)P.minX; py[0] = (uint32_t)P.minY; pw[0] = (uint32_t)P.rangeX; ph[0] = (uint32_t)P.rangeY;
+      if (wrap) {
+        const uint32_t fb = (((uint32_t)P.minY * (uint32_t)blocksX) & 0xffffu) + (uint32_t)P.minX;
+        const uint32_t r0 = fb / (uint32_t)blocksX, c0 = fb - r0 * (uint32_t)blocksX;
+        const uint32_t split = min((uint32_t)P.rangeX, (uint32_t)blocksX - c0);
+        px[0] = c0; py[0] = r0; pw[0] = split;
+        if (split < (uint32_t)P.rangeX) { nPieces = 2u; px[1] = 0u; py[1] = r0 + 1u; pw[1] = (uint32_t)P.rangeX - split; ph[1] = ph[0]; pskip[1] = split; }
+        // rows past the target would be out-of-bounds writes in the reference: never produced by its own scenes, dropped here
+        for (uint32_t k = 0; k < nPieces; ++k) ph[k] = py[k] < (uint32_t)blocksY ? min(ph[k], (uint32_t)blocksY - py[k]) : 0u;
+        if (nPieces == 2u && ph[1] == 0u) nPieces = 1u;
+        if (ph[0] == 0u) { nPieces = nPieces == 2u ? 1u : 0u; px[0] = px[1]; py[0] = py[1]; pw[0] = pw[1]; ph[0] = ph[1]; pskip[0] = pskip[1]; }
+      }
+    }
+    // in-order slots: inclusive warp scan of the piece counts, block prefix over the 8 warps
+    uint32_t incl = nPieces;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t t = __shfl_up_sync(kFull, incl, dd); if (lane >= dd) incl += t; }
     __syncthreads();  // s_cnt of the previous chunk has been read
-    if (lane == 0) s_cnt[warp] = (uint32_t)__popc(valid);
+    if (lane == 31) s_cnt[warp] = incl;
     __syncthreads();
     uint32_t base = written, total = 0;
 #pragma unroll
     for (int w2 = 0; w2 < 8; ++w2) { const uint32_t c = s_cnt[w2]; base += w2 < warp ? c : 0u; total += c; }
-    if (ok) {  // in order: binning by prefix-sum compaction
-      const uint32_t at = base + (uint32_t)__popc(valid & ((1u << lane) - 1u));
-      store_record(recs + (size_t)at * kRecStride, P);
-      hdrs[at] = make_uint2((uint32_t)P.minX | ((uint32_t)P.minY << 16), (uint32_t)P.rangeX | ((uint32_t)P.rangeY << 16));
-      bx0 = min(bx0, (uint32_t)P.minX); by0 = min(by0, (uint32_t)P.minY);
-      bx1 = max(bx1, (uint32_t)(P.minX + P.rangeX)); by1 = max(by1, (uint32_t)(P.minY + P.rangeY));
+    for (uint32_t k = 0; k < nPieces; ++k) {  // binning by prefix-sum compaction
+      const uint32_t at = base + incl - nPieces + k;
+      uint32_t* rec = recs + (size_t)at * kRecStride;
+      store_record(rec, P);
+      rec[0] = px[k] | (py[k] << 16); rec[1] = pw[k] | (ph[k] << 16); rec[20] = pskip[k];
+      hdrs[at] = make_uint2(rec[0], rec[1]);
+      bx0 = min(bx0, px[k]); by0 = min(by0, py[k]);
+      bx1 = max(bx1, px[k] + pw[k]); by1 = max(by1, py[k] + ph[k]);
     }
     written += total;
   }
@@ -126,7 +155,7 @@ __global__ void __launch_bounds__(256) k_setup_views(const FrameParams p) {
   if (lane == 0) { atomicMin(&s_box[0], bx0); atomicMin(&s_box[1], by0); atomicMax(&s_box[2], bx1); atomicMax(&s_box[3], by1); }
   __syncthreads();
   if (tid == 0) {
-    p.recInfo[((size_t)view * p.nOcc + slot) * 2u] = make_uint4(written, om.quadOffset, om.quadCount, 0u);
+    p.recInfo[((size_t)view * p.nOcc + slot) * 2u] = make_uint4(written, slotBase, om.quadCount, 0u);
     // block rectangle that holds every primitive of the occluder, half open (lo > hi when there is none)
     p.recInfo[((size_t)view * p.nOcc + slot) * 2u + 1u] = make_uint4(s_box[0], s_box[1], s_box[2], s_box[3]);
   }
@@ -204,7 +233,7 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
     const bool active = lane < 16 && r >= rFirst && r <= rLast;
     float cur = 0.0f, incX = 0.0f, incY = 0.0f;
     if (active) { cur = u2f(rec[14 + e]); incX = u2f(rec[6 + e]); incY = u2f(rec[10 + e]); }
-    step_chain(cur, incX, incY, ya - minY, r - rFirst, x0 + cA - minX, cA, cB, active, sm + e * kChainStride + r * 8u);
+    step_chain(cur, incX, incY, ya - minY, r - rFirst, x0 + cA - minX + rec[20], cA, cB, active, sm + e * kChainStride + r * 8u);
   }
   __syncwarp();
 
@@ -247,7 +276,7 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
     const bool active = r >= rLo && r <= rLast;
     const float s = -0.5f + 1.0f / 16.0f;
     const float cur = ORZ_FMA(dzdx, s + 0.125f * (float)(l & 3u), ORZ_FMA(dzdy, (l >> 2) ? s + 0.125f : s, u2f(rec[5])));
-    step_chain(cur, dzdx, dzdy, y0 + rLo - minY, r - rLo, x0 + cA - minX, cA, cB, active, sm + (4u + l) * kChainStride + r * 8u);
+    step_chain(cur, dzdx, dzdy, y0 + rLo - minY, r - rLo, x0 + cA - minX + rec[20], cA, cB, active, sm + (4u + l) * kChainStride + r * 8u);
   }
   __syncwarp();
   // ---- depth rows, merge into the registers, HiZ (Rasterizer.cpp:1241-1290)

@@ -84,6 +84,6 @@ struct FrameParams {
   // cluster path: speculative setup output per view (k_setup_views)
   uint32_t* recBuf;     // [nViews][totalQuads][kRecStride] records, each occluder's at its quadOffset
   uint2* hdrBuf;        // [nViews][totalQuads] bounding boxes of the records
-  uint4* recInfo;       // [nViews][nOcc][2]: {records, quadOffset, quadCount, -}, {block rectangle of all records, half open}
-  uint32_t totalQuads;
+  uint4* recInfo;       // [nViews][nOcc][2]: {records, first record slot, quadCount, -}, {block rectangle of all records, half open}
+  uint32_t totalQuads;  // record slots per view (2 per quad above 65 536 blocks: index wrap)
 };

@@ -687,11 +687,12 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
     p.viewCounter = ctx->d_counter;
     p.viewCost = (uint32_t*)(prep + chunk * sizeof(ViewMatrices) + chunk * nOcc * 4 + chunk * nOcc * kFrontWords * 4);
     const bool wide = (b->flags & ORZ_BATCH_NO_GATE) && ((b->flags & ORZ_BATCH_WIDE) || (nv <= 8u && scene->totalQuads >= 65536u));
-    // (above 65 536 blocks the reference's 16-bit index wrap needs the linear traversal of the batch kernel)
+    // (targets above 32 tiles per warp of a 16-CTA cluster -- beyond ~8K x 4K -- stay on the batch kernel)
     // measured crossover with the batch kernel: ~2000 views at 1920x1080, ~1500 at 512x256 (profiles/r1_few_views_*)
     const uint32_t clusterLimit = (uint32_t)ctx->clusterViews;
-    const bool clusterPath = !wide && ctx->clusterViews > 0 && nv <= clusterLimit && blocks <= 65536u && nOcc <= kClusterMaxOcc &&
-                             (size_t)nv * scene->totalQuads * (kRecStride * 4 + 8) <= (size_t(8) << 30);
+    const size_t nTilesC = (size_t)((b->width / 8 + kTileW - 1) / kTileW) * ((b->height / 8 + kTileH - 1) / kTileH);
+    const bool clusterPath = !wide && ctx->clusterViews > 0 && nv <= clusterLimit && nTilesC <= 32u * 16u * kClusterGW && nOcc <= kClusterMaxOcc &&
+                             (size_t)nv * scene->totalQuads * (blocks > 65536u ? 2 : 1) * (kRecStride * 4 + 8) <= (size_t(8) << 30);
     p.viewOrder = (nv <= 16384u && !(clusterPath && nv * 2u <= (uint32_t)ctx->numSMs)) ? p.viewCost + chunk : nullptr;
     k_prepare_views<<<nv, 128, 0, ctx->stream>>>(p);
     ctx->launches++;
@@ -741,12 +742,13 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
     if (clusterPath) {
       FrameParams pc = p;
       pc.viewBase = 0; pc.groupViews = nv;
-      const size_t recBytes = (size_t)nv * scene->totalQuads * kRecStride * 4, hdrBytes = (size_t)nv * scene->totalQuads * 8;
+      const size_t recSlots = (size_t)scene->totalQuads * (blocks > 65536u ? 2 : 1);  // a wrapped primitive is two records
+      const size_t recBytes = (size_t)nv * recSlots * kRecStride * 4, hdrBytes = (size_t)nv * recSlots * 8;
       if ((e = ensure_scratch(ctx, 11, recBytes + hdrBytes + (size_t)nv * nOcc * 32 + 64))) return e;
       pc.hdrBuf = (uint2*)ctx->d_scratch[11];
       pc.recInfo = (uint4*)((uint8_t*)ctx->d_scratch[11] + ((hdrBytes + 15) & ~size_t(15)));
       pc.recBuf = (uint32_t*)((uint8_t*)pc.recInfo + (size_t)nv * nOcc * 32);
-      pc.totalQuads = scene->totalQuads;
+      pc.totalQuads = (uint32_t)recSlots;
       k_setup_views<<<dim3(pc.nOcc, nv), 256, 0, ctx->stream>>>(pc);
       ctx->launches++;
       ORZ_CUDA(cudaGetLastError());

@@ -181,7 +181,8 @@ def test_view_batch(ctx, lut, name, size, nviews, gw, trav):
 
 
 @pytest.mark.parametrize("name,size,nviews", [("city", (640, 360), 6), ("castle", (1920, 1080), 5), ("castle", (512, 256), 12),
-                                              ("castle", (1280, 720), 3), ("castle", (2560, 1440), 2), ("sponza", (1920, 1080), 2)])
+                                              ("castle", (1280, 720), 3), ("castle", (2560, 1440), 2), ("sponza", (1920, 1080), 2),
+                                              ("castle", (3840, 2160), 2)])  # 3840x2160: 16-bit index wrap -> two records per wrapped primitive
 def test_view_cluster_path(ctx, lut, name, size, nviews):
     """Latency path for few views: speculative setup kernel + one thread-block cluster (2-16 CTAs) per
     view run as a dataflow machine (tile-local gates, DSMEM decision flags, k_raster_views_cluster)."""

@@ -56,6 +56,23 @@ uint32_t orz_bake(const float* vertices, uint32_t nVerts, const float* refMin4, 
                   uint32_t* packets, float* center4, float* boundsMin4, float* boundsMax4);
 int orz_set_rsqrt_table(const uint32_t* table, int bits); /* NULL: back to the host instruction */
 
+/* ---- scene preparation: the offline steps of Main.cpp:86-107, host side -------------------------
+ * orz_quad_decompose = QuadDecomposition::decompose (QuadDecomposition.h:10, QuadDecomposition.cpp:346-445):
+ * pairs the triangles of an indexed triangle list into quads by a maximum matching over the pairs whose
+ * two planes stay within 0.5 units of the shared quad.  indices: nIndices words (3 per triangle);
+ * vertices: nVertices float4.  quadIndices: room for 4 * (nIndices / 3) words; *nQuadIndices = words
+ * written, 4 per quad (a lone triangle i0 i1 i2 becomes i0 i2 i1 i0).  Same quads, same order as the
+ * reference.  Uses rsqrtps like Occluder::bake (orz_set_rsqrt_table applies). */
+int orz_quad_decompose(const uint32_t* indices, size_t nIndices, const float* vertices, size_t nVertices,
+                       uint32_t* quadIndices, size_t* nQuadIndices);
+/* orz_generate_batches = SurfaceAreaHeuristic::generateBatches (SurfaceAreaHeuristic.h:10,
+ * SurfaceAreaHeuristic.cpp:10-104): top-down SAH splits at multiples of splitGranularity until a side
+ * is smaller than targetSize.  aabbs: nAabbs x (min4, max4).  indicesOut: nAabbs words = the batches'
+ * members concatenated in the reference's batch order; batchSizes[b] = members of batch b (room for
+ * batchCapacity entries; nAabbs / splitGranularity always suffices); *nBatches = batches found. */
+int orz_generate_batches(const float* aabbs, uint32_t nAabbs, uint32_t targetSize, uint32_t splitGranularity,
+                         uint32_t* indicesOut, uint32_t* batchSizes, uint32_t batchCapacity, uint32_t* nBatches);
+
 /* ---- single-view path: the reference's per-call API ------------------------------------------- */
 /* upload one baked batch (re-laid out as one 16-byte record per quad for 128-bit coalesced loads) */
 int orz_occluder_create(orz_context* ctx, const uint32_t* packets, uint32_t packetCount, const float* refMin4,

@@ -123,6 +123,34 @@ void* ref_scene_load(const char* indexPath, const char* vertexPath) {
   return s.release();
 }
 
+// ---- the two preprocessing steps on their own (tests/test_scene_prep.py) -----------------------
+// QuadDecomposition::decompose (QuadDecomposition.cpp:346); out: room for 4 * (nIndices / 3) words
+size_t ref_quad_decompose(const uint32_t* indices, size_t nIndices, const float* verts, size_t nVerts, uint32_t* out) {
+  std::vector<uint32_t> idx(indices, indices + nIndices);
+  std::vector<__m128> v(nVerts);
+  for (size_t i = 0; i < nVerts; ++i) v[i] = _mm_loadu_ps(verts + 4 * i);
+  auto quads = QuadDecomposition::decompose(idx, v);
+  memcpy(out, quads.data(), quads.size() * 4);
+  return quads.size();
+}
+// SurfaceAreaHeuristic::generateBatches (SurfaceAreaHeuristic.cpp:96); aabbs: n x (min4, max4);
+// indicesOut: n words, batchSizes: room for n entries; returns the number of batches
+uint32_t ref_generate_batches(const float* aabbs, uint32_t n, uint32_t targetSize, uint32_t granularity,
+                              uint32_t* indicesOut, uint32_t* batchSizes) {
+  std::vector<Aabb> boxes(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    boxes[i].m_min = _mm_loadu_ps(aabbs + 8 * size_t(i));
+    boxes[i].m_max = _mm_loadu_ps(aabbs + 8 * size_t(i) + 4);
+  }
+  auto batches = SurfaceAreaHeuristic::generateBatches(boxes, targetSize, granularity);
+  uint32_t w = 0;
+  for (size_t b = 0; b < batches.size(); ++b) {
+    batchSizes[b] = uint32_t(batches[b].size());
+    for (auto q : batches[b]) indicesOut[w++] = q;
+  }
+  return uint32_t(batches.size());
+}
+
 // Scene from caller-made batches (synthetic scenes): bake every batch with the reference bake.
 void* ref_scene_from_batches(const float* verts, const uint32_t* batchQuads, uint32_t nBatches,
                              const float* refMin4, const float* refMax4) {

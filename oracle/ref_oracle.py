@@ -33,6 +33,8 @@ def lib():
             "ref_scene_load": (vp, [C.c_char_p, C.c_char_p]),
             "ref_scene_from_batches": (vp, [vp, vp, u32, vp, vp]),
             "ref_scene_free": (None, [vp]),
+            "ref_quad_decompose": (C.c_size_t, [vp, C.c_size_t, vp, C.c_size_t, vp]),
+            "ref_generate_batches": (u32, [vp, u32, u32, u32, vp, vp]),
             "ref_scene_num_occluders": (u32, [vp]),
             "ref_scene_num_boxes": (u32, [vp]),
             "ref_scene_boxes": (vp, [vp]),
@@ -83,6 +85,30 @@ def host_rsqrt(x: np.ndarray) -> np.ndarray:
     out = np.empty_like(x)
     lib().ref_rsqrt_ps(_p(x), _p(out), x.size)
     return out
+
+
+def quad_decompose(indices, vertices) -> np.ndarray:
+    """QuadDecomposition::decompose of the unmodified reference."""
+    idx = np.ascontiguousarray(indices, np.uint32).reshape(-1)
+    v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 4)
+    out = np.zeros(4 * (idx.size // 3), np.uint32)
+    n = lib().ref_quad_decompose(_p(idx), idx.size, _p(v), v.shape[0], _p(out))
+    return out[:n].copy()
+
+
+def generate_batches(aabbs, target_size=512, granularity=8):
+    """SurfaceAreaHeuristic::generateBatches of the unmodified reference -> list of index arrays."""
+    b = np.ascontiguousarray(aabbs, np.float32).reshape(-1, 8)
+    order = np.zeros(b.shape[0], np.uint32)
+    sizes = np.zeros(max(b.shape[0], 2), np.uint32)
+    n = lib().ref_generate_batches(_p(b), b.shape[0], target_size, granularity, _p(order), _p(sizes))
+    return np.split(order, np.cumsum(sizes[:n])[:-1])
+
+
+def load_mesh(name: str):
+    """Raw triangle list + float4 vertices of a reference scene (Main.cpp:56-84) from oracle/_ref/scenes."""
+    d = os.path.join(SCENE_DIR, name)
+    return np.fromfile(os.path.join(d, "IndexBuffer.bin"), np.uint32), np.fromfile(os.path.join(d, "VertexBuffer.bin"), np.float32).reshape(-1, 4)
 
 
 class RefScene:

@@ -44,6 +44,9 @@ class ViewBatch(C.Structure):
 
 
 EXPORTS = {
+    "orz_quad_decompose": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]),
+    "orz_generate_batches": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                       C.POINTER(C.c_uint32)]),
     "orz_last_error": (C.c_char_p, []),
     "orz_version": (C.c_int, []),
     "orz_context_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
@@ -127,6 +130,27 @@ def bake(vertices, ref_min, ref_max):
     if n * 8 != v.shape[0]:
         raise OrzError("orz_bake failed")
     return packets, c, bmin, bmax
+
+
+def quad_decompose(indices, vertices) -> np.ndarray:
+    """QuadDecomposition::decompose (QuadDecomposition.cpp:346-445): triangle list -> quad list (4 indices per quad)."""
+    idx = np.ascontiguousarray(indices, np.uint32).reshape(-1)
+    v = _f32(vertices).reshape(-1, 4)
+    out = np.zeros(4 * (idx.size // 3), np.uint32)
+    n = C.c_size_t()
+    _check(lib().orz_quad_decompose(_p(idx), idx.size, _p(v), v.shape[0], _p(out), C.byref(n)))
+    return out[: n.value].copy()
+
+
+def generate_batches(aabbs, target_size: int = 512, split_granularity: int = 8):
+    """SurfaceAreaHeuristic::generateBatches (SurfaceAreaHeuristic.cpp:96-104) -> list of index arrays."""
+    b = _f32(aabbs).reshape(-1, 8)
+    order = np.zeros(b.shape[0], np.uint32)
+    cap = b.shape[0] // max(split_granularity, 1) + 2
+    sizes = np.zeros(cap, np.uint32)
+    n = C.c_uint32()
+    _check(lib().orz_generate_batches(_p(b), b.shape[0], target_size, split_granularity, _p(order), _p(sizes), cap, C.byref(n)))
+    return np.split(order, np.cumsum(sizes[: n.value])[:-1])
 
 
 def edge_mask_table() -> np.ndarray:

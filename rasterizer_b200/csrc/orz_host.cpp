@@ -176,18 +176,7 @@ void current_rsqrt_table(std::vector<uint32_t>& table, int& bits) {
   table = host; bits = hostBits;
 }
 
-struct V3 { float x, y, z; };
-static inline V3 sub(const float* a, const float* b) { return {a[0] - b[0], a[1] - b[1], a[2] - b[2]}; }
-// normal() of VectorMath.h:6-18: cross(v1 - v0, v2 - v0), products rounded separately
-static inline V3 tri_normal(const float* v0, const float* v1, const float* v2) {
-  const V3 a = sub(v1, v0), b = sub(v2, v0);
-  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
-}
-static inline float dot3(const V3& a, const V3& b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }  // dpps 0x7F
-static inline V3 normalized(const V3& v) {  // VectorMath.h:20-23
-  const float s = rsqrt_x86(dot3(v, v));
-  return {v.x * s, v.y * s, v.z * s};
-}
+float rsqrt_current(float x) { return rsqrt_x86(x); }
 
 }  // namespace orz
 

@@ -64,6 +64,7 @@ using namespace orz;
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int orz::set_error(int code, const std::string& msg) { return fail(code, msg); }
 #define ORZ_CUDA(x)                                                                                   \
   do {                                                                                                \
     cudaError_t _e = (x);                                                                             \

@@ -1,11 +1,12 @@
 """Workload definitions for the BASELINE.json configs: prepared scenes, camera sets, occludee boxes.
 
 A *prepared scene* is what Main.cpp:56-113 produces before baking: batches of quads (4 float4
-vertices per quad, quad count a multiple of 8 per batch) plus one reference AABB.  Quad
-decomposition and SAH batching are offline preprocessing and out of scope (SURVEY section 2 rows
-9-10); for Castle/Sponza the prepared scene is produced once by tools/prepare_scenes.py and
-stored under scenes/_prepared/ (git-ignored: Castle is under the Intel Code Samples License).
-Synthetic scenes are generated here from a seed.
+vertices per quad, quad count a multiple of 8 per batch) plus one reference AABB.  `prepare_mesh`
+runs those steps through the product's own preparation (orz_quad_decompose, orz_generate_batches,
+bit-identical with the reference's QuadDecomposition / SurfaceAreaHeuristic); for Castle/Sponza the
+prepared scene is stored once under scenes/_prepared/ (git-ignored: Castle is under the Intel Code
+Samples License; the raw meshes only exist where /root/reference does).  Synthetic scenes are
+generated here from a seed.
 """
 from __future__ import annotations
 
@@ -94,6 +95,51 @@ def load_scene(name: str) -> PreparedScene:
         return synthetic_city()
     camera = {"castle": cam.CASTLE_CAMERA, "sponza": cam.SPONZA_CAMERA}[key]
     return PreparedScene.load(prepared_path(key), key, dict(camera))
+
+
+# ------------------------------------------------------------------------------------------------
+# Main.cpp:86-128 on a raw mesh
+def pad_quads(quad_indices: np.ndarray) -> np.ndarray:
+    """Main.cpp:91-94: repeat the first index until the quad count is a multiple of 8."""
+    q = np.ascontiguousarray(quad_indices, np.uint32).reshape(-1)
+    pad = (-q.size) % 32
+    return np.concatenate([q, np.full(pad, q[0], np.uint32)]) if pad else q
+
+
+def _fold_minmax(points: np.ndarray):
+    """Aabb::include (VectorMath.h:44-48) over axis 1: minps / maxps keep the NEW operand on ties,
+    which decides the sign of a zero bound."""
+    mn = np.full((points.shape[0], points.shape[2]), np.inf, f32)
+    mx = np.full_like(mn, -np.inf)
+    for k in range(points.shape[1]):
+        p = points[:, k]
+        mn = np.where(mn < p, mn, p)
+        mx = np.where(mx > p, mx, p)
+    return mn, mx
+
+
+def quad_aabbs(quad_indices: np.ndarray, vertices: np.ndarray) -> np.ndarray:
+    """Main.cpp:96-105: one Aabb per quad -> float32 [n, 8] (min4, max4)."""
+    v = np.ascontiguousarray(vertices, f32).reshape(-1, 4)
+    mn, mx = _fold_minmax(v[quad_indices.reshape(-1, 4)])
+    return np.ascontiguousarray(np.concatenate([mn, mx], axis=1))
+
+
+def prepare_mesh(name: str, indices: np.ndarray, vertices: np.ndarray, camera: dict | None = None, target_size: int = 512,
+                 split_granularity: int = 8, generate_batches=None) -> PreparedScene:
+    """Triangle list + float4 vertices -> prepared scene, the steps of Main.cpp:86-128 before bake:
+    quad decomposition, padding, per-quad AABBs, SAH batches, reference AABB over ALL vertices.
+    `generate_batches`: the batching entry to use (default: host; `Context.generate_batches` for the GPU)."""
+    from . import api
+
+    v = np.ascontiguousarray(vertices, f32).reshape(-1, 4)
+    quads = pad_quads(api.quad_decompose(indices, v))
+    batching = generate_batches or api.generate_batches
+    groups = batching(quad_aabbs(quads, v), target_size, split_granularity)
+    q4 = quads.reshape(-1, 4)
+    batches = [np.ascontiguousarray(v[q4[g].reshape(-1)]) for g in groups]
+    ref_min, ref_max = _fold_minmax(v[None])
+    return PreparedScene(name, batches, ref_min[0].copy(), ref_max[0].copy(), dict(camera or {}))
 
 
 # ------------------------------------------------------------------------------------------------

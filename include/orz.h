@@ -73,6 +73,12 @@ int orz_quad_decompose(const uint32_t* indices, size_t nIndices, const float* ve
 int orz_generate_batches(const float* aabbs, uint32_t nAabbs, uint32_t targetSize, uint32_t splitGranularity,
                          uint32_t* indicesOut, uint32_t* batchSizes, uint32_t batchCapacity, uint32_t* nBatches);
 
+/* The same batching on the GPU (level-synchronous: stable radix sorts by segment and centre, segmented
+ * box scans, atomicMin over (cost, axis, position)); same arguments and bit-identical results. */
+int orz_generate_batches_device(orz_context* ctx, const float* aabbs, uint32_t nAabbs, uint32_t targetSize,
+                                uint32_t splitGranularity, uint32_t* indicesOut, uint32_t* batchSizes,
+                                uint32_t batchCapacity, uint32_t* nBatches);
+
 /* ---- single-view path: the reference's per-call API ------------------------------------------- */
 /* upload one baked batch (re-laid out as one 16-byte record per quad for 128-bit coalesced loads) */
 int orz_occluder_create(orz_context* ctx, const uint32_t* packets, uint32_t packetCount, const float* refMin4,

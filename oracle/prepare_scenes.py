@@ -1,10 +1,8 @@
-"""BUILD-TIME DATA TOOL (test infrastructure side): run the reference's own offline preprocessing
-(QuadDecomposition.cpp + SurfaceAreaHeuristic.cpp + the padding / batching of Main.cpp:86-128,
-compiled unmodified into oracle/_ref/libref_oracle.so) over the reference's Castle / Sponza data
-and store the resulting quad batches as prepared scenes under scenes/_prepared/ (git-ignored).
-
-Quad decomposition and SAH batching are out of scope for the B200 path;
-the product only ever sees their output: batches of quads + one reference AABB.
+"""BUILD-TIME DATA TOOL: turn the reference's Castle / Sponza meshes (copied to oracle/_ref/scenes, git-ignored)
+into prepared scenes under scenes/_prepared/ (git-ignored) with the PRODUCT's own preparation
+(workloads.prepare_mesh: orz_quad_decompose + orz_generate_batches, Main.cpp:86-113), and check the result
+against what the reference's unmodified code (QuadDecomposition.cpp + SurfaceAreaHeuristic.cpp compiled into
+oracle/_ref/libref_oracle.so) makes of the same files: same batches, same vertices, same reference AABB.
 Usage: python -m oracle.prepare_scenes
 """
 from __future__ import annotations
@@ -30,8 +28,10 @@ def main() -> int:
             print(f"skip {name}: no scene data under oracle/_ref/scenes")
             continue
         s = ro.RefScene.load(name)
+        ps = wl.prepare_mesh(name.lower(), *ro.load_mesh(name), dict(camera))
         batches = [s.batch_vertices(i) for i in range(s.n_occluders)]
-        ps = wl.PreparedScene(name.lower(), batches, s.ref_min.copy(), s.ref_max.copy(), dict(camera))
+        assert len(batches) == len(ps.batches) and all(np.array_equal(a.view(np.uint32), b.view(np.uint32)) for a, b in zip(batches, ps.batches))
+        assert np.array_equal(ps.ref_min, s.ref_min) and np.array_equal(ps.ref_max, s.ref_max)
         ps.save(wl.prepared_path(name))
         back = wl.PreparedScene.load(wl.prepared_path(name))
         assert all(np.array_equal(a, b) for a, b in zip(batches, back.batches))

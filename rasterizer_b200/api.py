@@ -44,6 +44,8 @@ class ViewBatch(C.Structure):
 
 
 EXPORTS = {
+    "orz_generate_batches_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                              C.c_uint32, C.POINTER(C.c_uint32)]),
     "orz_quad_decompose": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]),
     "orz_generate_batches": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
                                        C.POINTER(C.c_uint32)]),
@@ -201,6 +203,17 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(lib().orz_context_launch_count(self.h))
+
+    def generate_batches(self, aabbs, target_size: int = 512, split_granularity: int = 8):
+        """SurfaceAreaHeuristic::generateBatches on the GPU -> list of index arrays (same as api.generate_batches)."""
+        b = _f32(aabbs).reshape(-1, 8)
+        order = np.zeros(b.shape[0], np.uint32)
+        cap = b.shape[0] // max(split_granularity, 1) + 2
+        sizes = np.zeros(cap, np.uint32)
+        n = C.c_uint32()
+        _check(lib().orz_generate_batches_device(self.h, _p(b), b.shape[0], target_size, split_granularity, _p(order), _p(sizes), cap,
+                                                 C.byref(n)))
+        return np.split(order, np.cumsum(sizes[: n.value])[:-1])
 
     def set_group_warps(self, warps: int):
         _check(lib().orz_context_set_group_warps(self.h, warps))

@@ -1,8 +1,12 @@
-// Thin C++ wrappers: reference signatures (Occluder.h:9, Rasterizer.h:13-26) over the C ABI.
+// Thin C++ wrappers: reference signatures (Occluder.h:9, Rasterizer.h:13-26, QuadDecomposition.h:10,
+// SurfaceAreaHeuristic.h:10) over the C ABI.
 // The reference has no error channel (asserts only, Rasterizer.cpp:68, Occluder.cpp:9); a failing
 // ABI call prints orz_last_error() and aborts, which keeps the void signatures.
 #include "Occluder.h"
+#include "QuadDecomposition.h"
 #include "Rasterizer.h"
+#include "SurfaceAreaHeuristic.h"
+#include "VectorMath.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -101,3 +105,34 @@ void Rasterizer::queryVisibilityBatch(const float* boxesMinMax, uint32_t count, 
   check(orz_rasterizer_query_boxes(m_impl, boxesMinMax, count, out), "orz_rasterizer_query_boxes");
 }
 void Rasterizer::download(uint16_t* depth, uint16_t* hiZ) const { check(orz_rasterizer_download(m_impl, depth, hiZ), "orz_rasterizer_download"); }
+
+// ---- scene preparation (Main.cpp:86-107) ----------------------------------------------------------
+std::vector<uint32_t> QuadDecomposition::decompose(const std::vector<uint32_t>& indices, const std::vector<__m128>& vertices) {
+  std::vector<uint32_t> quads(4 * (indices.size() / 3));
+  size_t words = 0;
+  check(orz_quad_decompose(indices.data(), indices.size(), reinterpret_cast<const float*>(vertices.data()), vertices.size(), quads.data(), &words),
+        "orz_quad_decompose");
+  quads.resize(words);
+  return quads;
+}
+
+std::vector<std::vector<uint32_t>> SurfaceAreaHeuristic::generateBatches(const std::vector<Aabb>& aabbs, uint32_t targetSize,
+                                                                         uint32_t splitGranularity) {
+  const uint32_t n = uint32_t(aabbs.size()), capacity = n / (splitGranularity ? splitGranularity : 1) + 2;
+  std::vector<uint32_t> order(n), sizes(capacity);
+  uint32_t nBatches = 0;
+  const float* boxes = reinterpret_cast<const float*>(aabbs.data());
+  const char* onHost = std::getenv("ORZ_PREP_ON_HOST");
+  if (onHost && onHost[0] == '1')
+    check(orz_generate_batches(boxes, n, targetSize, splitGranularity, order.data(), sizes.data(), capacity, &nBatches), "orz_generate_batches");
+  else
+    check(orz_generate_batches_device(Rasterizer::context(), boxes, n, targetSize, splitGranularity, order.data(), sizes.data(), capacity, &nBatches),
+          "orz_generate_batches_device");
+  std::vector<std::vector<uint32_t>> batches(nBatches);
+  size_t at = 0;
+  for (uint32_t b = 0; b < nBatches; ++b) {
+    batches[b].assign(order.begin() + at, order.begin() + at + sizes[b]);
+    at += sizes[b];
+  }
+  return batches;
+}

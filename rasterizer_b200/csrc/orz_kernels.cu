@@ -11,6 +11,7 @@
 //   orz_wide_kernels.cuh     config 4: one ungated view split over the whole GPU
 //   orz_percall_kernels.cuh  the reference's per-call API (Rasterizer.h:13-26)
 //   orz_bake_kernel.cuh      Occluder::bake (Occluder.cpp:7-181)
+//   orz_sah_kernels.cuh      SurfaceAreaHeuristic::generateBatches (SurfaceAreaHeuristic.cpp:10-104), level-synchronous
 //
 // Execution models, data layout and measurements: DESIGN.md sections 3 and 4.
 // No tensor cores: nothing here is a contraction.
@@ -55,6 +56,7 @@ namespace orz {
 #include "orz_wide_kernels.cuh"
 #include "orz_percall_kernels.cuh"
 #include "orz_bake_kernel.cuh"
+#include "orz_sah_kernels.cuh"
 
 }  // namespace orz
 
@@ -491,6 +493,10 @@ extern "C" int orz_scene_bake(orz_context* ctx, const float* vertices, const uin
   *out = s;
   return ORZ_OK;
 }
+// ---- SurfaceAreaHeuristic::generateBatches on the GPU: kernels in orz_sah_kernels.cuh, level loop here
+#define ORZ_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#include "orz_sah_driver.inl"
+
 extern "C" int orz_scene_set_occludees(orz_scene* s, const float* boxes, uint32_t n) {
   if (!s || (n && !boxes)) return fail(ORZ_ERR_ARG, "orz_scene_set_occludees: bad arguments");
   ORZ_CUDA(cudaSetDevice(s->ctx->device));

@@ -1,0 +1,81 @@
+"""Device batching (orz_generate_batches_device, orz_sah_kernels.cuh) against the host batching of the
+product and -- where oracle/_ref travelled -- the unmodified reference: same batches, same order."""
+import numpy as np
+import pytest
+
+from oracle import ref_oracle as ro
+from rasterizer_b200 import api
+from rasterizer_b200 import workloads as wl
+from prep_cases import boxes_case, same_batches, terrain
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("seed,n,target,gran,snap", [
+    (1, 24, 512, 8, None),          # one level, one tile
+    (3, 4000, 512, 8, None),
+    (4, 4000, 512, 8, 10.0),        # many equal centres: tie order of the stable sorts
+    (5, 20000, 512, 8, 5.0),
+    (6, 5000, 64, 16, 4.0),
+    (7, 3001, 100, 7, 2.0),
+    (8, 6000, 16, 1, 25.0),         # hundreds of segments per level: two segment digits in the sort
+    (9, 70000, 8, 2, 3.0),          # thousands of segments: three segment digits
+    (10, 300000, 512, 8, None),     # 147 sort tiles, 1 172 scan chunks in the root segment
+])
+def test_device_batches_equal_host(ctx, seed, n, target, gran, snap):
+    boxes = boxes_case(np.random.default_rng(seed), n, snap)
+    got = ctx.generate_batches(boxes, target, gran)
+    assert ctx.launch_count > 0
+    assert same_batches(got, api.generate_batches(boxes, target, gran))
+    if ro.available() and n <= 20000:
+        assert same_batches(got, ro.generate_batches(boxes, target, gran))
+
+
+@pytest.mark.parametrize("name", ["castle", "sponza"])
+def test_device_batches_of_the_reference_scenes(ctx, name):
+    if not wl.have_scene(name):
+        pytest.skip("prepared scene missing")
+    boxes = wl.load_scene(name).quadboxes_case()  # the quads' AABBs, in batch order instead of mesh order
+    got = ctx.generate_batches(boxes, 512, 8)
+    assert same_batches(got, api.generate_batches(boxes, 512, 8))
+    assert len(got) >= 70 and all(len(b) % 8 == 0 and len(b) < 512 for b in got)
+
+
+def test_device_batches_signed_zero_and_errors(ctx):
+    boxes = boxes_case(np.random.default_rng(21), 3000, 8.0)
+    boxes[::3, 1] = boxes[::3, 5] = 0.0
+    boxes[1::6, 1] = boxes[1::6, 5] = -0.0
+    boxes[::5, 0] = -boxes[::5, 4]
+    assert same_batches(ctx.generate_batches(boxes, 256, 8), api.generate_batches(boxes, 256, 8))
+    with pytest.raises(api.OrzError, match="no split position"):
+        ctx.generate_batches(boxes[:16], 512, 8)
+
+
+def test_prepare_mesh_on_device_feeds_the_renderer(ctx):
+    """Mesh in, visibility out, nothing from the reference in between: terrain -> quads -> device batches
+    -> device bake -> one view; equal to the same scene prepared on the host."""
+    from rasterizer_b200 import camera as cam
+
+    idx, verts = terrain(np.random.default_rng(5), 4000, 3.0)
+    api.set_rsqrt_table(None)
+    host = wl.prepare_mesh("terrain", idx, verts, {}, 128, 8)
+    dev = wl.prepare_mesh("terrain", idx, verts, {}, 128, 8, generate_batches=ctx.generate_batches)
+    assert len(host.batches) == len(dev.batches) > 8
+    assert all(np.array_equal(a.view(np.uint32), b.view(np.uint32)) for a, b in zip(host.batches, dev.batches))
+    scene = api.Scene.bake_on_device(ctx, dev.batches, dev.ref_min, dev.ref_max, dev.quadboxes_case())
+    scene_host = api.Scene.from_prepared(ctx, host)
+    w, h = 640, 360
+    pos = np.array([20.0, 15.0, -10.0], np.float32)
+    mvp = cam.view_projection(pos, np.array([0.0, -0.4, 0.9], np.float32), np.array([0.0, 1.0, 0.0], np.float32), 0.9, w, h)
+    out = scene.render_views(w, h, mvp[None], cam_pos=pos[None], want=("vis",))
+    vis = api.unpack_bits(out["vis"], dev.n_quads)[0]
+    assert 0 < vis.sum() < dev.n_quads
+    assert np.array_equal(out["vis"], scene_host.render_views(w, h, mvp[None], cam_pos=pos[None], want=("vis",))["vis"])
+    scene.close(); scene_host.close()

@@ -8,6 +8,7 @@ import pytest
 from oracle import ref_oracle as ro
 from rasterizer_b200 import api
 from rasterizer_b200 import workloads as wl
+from prep_cases import boxes_case, same_batches, terrain
 
 pytestmark = pytest.mark.skipif(not ro.available(), reason="oracle/_ref/libref_oracle.so not built (needs /root/reference)")
 
@@ -16,10 +17,6 @@ pytestmark = pytest.mark.skipif(not ro.available(), reason="oracle/_ref/libref_o
 def host_rsqrt():
     api.set_rsqrt_table(None)  # canMergeTrianglesToQuad normalises with this host's rsqrtps, as the reference build does
     yield
-
-
-def _same_batches(a, b):
-    return len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
 
 
 @pytest.mark.parametrize("name", ["Castle", "Sponza"])
@@ -31,29 +28,12 @@ def test_reference_scenes(name):
     quads = api.quad_decompose(idx, verts)
     assert np.array_equal(quads, ro.quad_decompose(idx, verts))
     boxes = wl.quad_aabbs(wl.pad_quads(quads), verts)
-    assert _same_batches(api.generate_batches(boxes, 512, 8), ro.generate_batches(boxes, 512, 8))
-
-
-def _terrain(rng, n, bump, shuffle=True):
-    """Consistently wound Delaunay triangulation of random points: the dual graph is full of odd
-    cycles (blossoms), `bump` makes part of the candidate pairs fail the planarity test."""
-    from scipy.spatial import Delaunay
-
-    pts = rng.uniform(0, 40, (n, 2)).astype(np.float32)
-    tri = Delaunay(pts.astype(np.float64)).simplices.astype(np.uint32)
-    a, b, c = pts[tri[:, 0]], pts[tri[:, 1]], pts[tri[:, 2]]
-    flip = ((b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (c[:, 0] - a[:, 0])) < 0
-    tri[flip] = tri[flip][:, [0, 2, 1]]
-    if shuffle:
-        tri = tri[rng.permutation(len(tri))]
-    z = (rng.uniform(0, 1, n) ** 4 * bump).astype(np.float32)
-    verts = np.stack([pts[:, 0], z, pts[:, 1], np.ones(n, np.float32)], axis=1).astype(np.float32)
-    return tri.reshape(-1), verts
+    assert same_batches(api.generate_batches(boxes, 512, 8), ro.generate_batches(boxes, 512, 8))
 
 
 @pytest.mark.parametrize("seed,n,bump", [(1, 60, 0.0), (2, 400, 0.0), (3, 400, 6.0), (4, 3000, 2.0), (5, 3000, 30.0), (6, 9000, 0.5)])
-def test_quad_decompose_terrain(seed, n, bump):
-    idx, verts = _terrain(np.random.default_rng(seed), n, bump)
+def test_quad_decomposeterrain(seed, n, bump):
+    idx, verts = terrain(np.random.default_rng(seed), n, bump)
     got, want = api.quad_decompose(idx, verts), ro.quad_decompose(idx, verts)
     assert np.array_equal(got, want)
     pairs = int(np.sum(got.reshape(-1, 4)[:, 0] != got.reshape(-1, 4)[:, 3]))
@@ -63,7 +43,7 @@ def test_quad_decompose_terrain(seed, n, bump):
 
 def test_quad_decompose_awkward_meshes():
     rng = np.random.default_rng(11)
-    idx, verts = _terrain(rng, 300, 1.0)
+    idx, verts = terrain(rng, 300, 1.0)
     tris = idx.reshape(-1, 3)
     cases = {
         "empty": np.zeros(0, np.uint32),
@@ -86,16 +66,6 @@ def test_quad_decompose_awkward_meshes():
         api.quad_decompose(np.array([0, 1, 5000], np.uint32), verts)
 
 
-def _boxes(rng, n, snap=None):
-    c = rng.uniform(-50, 50, (n, 3))
-    if snap:
-        c = np.round(c / snap) * snap  # many equal centres: the stable sorts' tie order becomes visible
-    e = rng.uniform(0.0, 3.0, (n, 3)) if not snap else np.round(rng.uniform(0.0, 3.0, (n, 3)))
-    mn, mx = (c - e).astype(np.float32), (c + e).astype(np.float32)
-    one = np.ones((n, 1), np.float32)
-    return np.concatenate([mn, one, mx, one], axis=1)
-
-
 @pytest.mark.parametrize("seed,n,target,gran,snap", [
     (1, 24, 512, 8, None),        # smaller than the target: the root is split anyway
     (2, 17, 16, 8, None),         # smallest size with a candidate position
@@ -107,23 +77,23 @@ def _boxes(rng, n, snap=None):
     (8, 6000, 256, 1, 25.0),
 ])
 def test_generate_batches(seed, n, target, gran, snap):
-    boxes = _boxes(np.random.default_rng(seed), n, snap)
+    boxes = boxes_case(np.random.default_rng(seed), n, snap)
     got, want = api.generate_batches(boxes, target, gran), ro.generate_batches(boxes, target, gran)
-    assert _same_batches(got, want)
+    assert same_batches(got, want)
     assert sorted(np.concatenate(got).tolist()) == list(range(n))
 
 
-def test_generate_batches_signed_zero_and_flat_boxes():
+def test_generate_batches_signed_zero_and_flatboxes_case():
     rng = np.random.default_rng(21)
-    boxes = _boxes(rng, 3000, 8.0)
+    boxes = boxes_case(rng, 3000, 8.0)
     boxes[::3, 1] = boxes[::3, 5] = 0.0          # flat in y at y = 0 ...
     boxes[1::6, 1] = boxes[1::6, 5] = -0.0       # ... some with negative zero
     boxes[::5, 0] = -boxes[::5, 4]               # centres x = +-0
-    assert _same_batches(api.generate_batches(boxes, 256, 8), ro.generate_batches(boxes, 256, 8))
+    assert same_batches(api.generate_batches(boxes, 256, 8), ro.generate_batches(boxes, 256, 8))
 
 
 def test_generate_batches_rejects_what_the_reference_cannot_split():
-    boxes = _boxes(np.random.default_rng(3), 16)
+    boxes = boxes_case(np.random.default_rng(3), 16)
     with pytest.raises(api.OrzError, match="no split position"):
         api.generate_batches(boxes, 512, 8)      # 16 <= 2 * 8: the reference reads areasFromLeft[-1]
     with pytest.raises(api.OrzError):
@@ -141,3 +111,65 @@ def test_prepare_mesh_matches_reference_scene():
     assert len(ps.batches) == len(ref.batches)
     assert all(np.array_equal(a.view(np.uint32), b.view(np.uint32)) for a, b in zip(ps.batches, ref.batches))
     assert np.array_equal(ps.ref_min, ref.ref_min) and np.array_equal(ps.ref_max, ref.ref_max)
+
+
+def test_cpp_dropin_preparation(tmp_path):
+    """tests/dropin_prepare.cpp -- Main.cpp:86-128 written against the reference's class names -- built on
+    the drop-in headers (host batching: ORZ_PREP_ON_HOST=1, no GPU here) gives the reference's baked scene."""
+    import os
+    import subprocess
+
+    if not ro.scene_available("Castle"):
+        pytest.skip("no Castle data under oracle/_ref/scenes")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "_build", "dropin_prepare")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-mavx2", "-msse4.1", "-Wno-ignored-attributes", "-I", os.path.join(root, "rasterizer_b200", "csrc", "dropin"),
+                           "-o", exe, os.path.join(root, "tests", "dropin_prepare.cpp"), "-L", os.path.join(root, "rasterizer_b200"),
+                           "-lrasterizer_b200", "-Wl,-rpath," + os.path.join(root, "rasterizer_b200")])
+    d = os.path.join(ro.SCENE_DIR, "Castle")
+    out = tmp_path / "castle_baked.bin"
+    subprocess.check_call([exe, os.path.join(d, "IndexBuffer.bin"), os.path.join(d, "VertexBuffer.bin"), str(out)], env=dict(os.environ, ORZ_PREP_ON_HOST="1"))
+    raw = np.fromfile(out, np.uint32)
+    s = ro.RefScene.load("Castle")
+    assert raw[0] == s.n_occluders
+    at = 1
+    for i in range(s.n_occluders):
+        nq = int(raw[at]); at += 1
+        meta = raw[at:at + 12].view(np.float32).reshape(3, 4); at += 12
+        packed = raw[at:at + 4 * nq]; at += 4 * nq
+        assert nq * 4 == int(s.packet_counts[i]) * 8
+        assert np.array_equal(meta.view(np.uint32), np.stack([s.centers[i], s.bounds_min[i], s.bounds_max[i]]).view(np.uint32))
+        assert np.array_equal(packed, s.packed(i))
+    s.close()
+
+
+@pytest.mark.parametrize("seed,n,target,gran,snap", [(1, 24, 512, 8, None), (4, 2600, 512, 8, 10.0), (8, 700, 16, 1, 25.0)])
+def test_device_batching_source_emulated_on_the_cpu(seed, n, target, gran, snap):
+    """tests/sah_emulation.cpp compiles the CUDA kernel source and the host level loop of the device
+    batching against a thread-per-lane emulation of launches, barriers, shuffles and atomics: their logic
+    is checked here, where no GPU exists (tests/test_gpu_scene_prep.py runs the real thing)."""
+    import ctypes as C
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(root, "tests", "_build", "libsah_emulation.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so,
+                           os.path.join(root, "tests", "sah_emulation.cpp"), "-lpthread"])
+    L = C.CDLL(so)
+    L.emu_last_error.restype = C.c_char_p
+    boxes = boxes_case(np.random.default_rng(seed), n, snap)
+    order, sizes, count = np.zeros(n, np.uint32), np.zeros(n // gran + 2, np.uint32), C.c_uint32()
+    rc = L.emu_generate_batches(boxes.ctypes.data_as(C.c_void_p), n, target, gran, order.ctypes.data_as(C.c_void_p),
+                                sizes.ctypes.data_as(C.c_void_p), sizes.size, C.byref(count), None)
+    assert rc == 0, L.emu_last_error().decode()
+    got = np.split(order, np.cumsum(sizes[: count.value])[:-1])
+    assert same_batches(got, api.generate_batches(boxes, target, gran))
+    if seed == 1:  # the radix histogram scan on its own, with carries across its 1 024-word rounds
+        for words in (1, 1025, 5000):
+            d = np.random.default_rng(words).integers(0, 3000, words).astype(np.uint32)
+            want = np.concatenate([[0], np.cumsum(d)[:-1]]).astype(np.uint32)
+            L.emu_scan(d.ctypes.data_as(C.c_void_p), words)
+            assert np.array_equal(d, want)

@@ -126,6 +126,21 @@ int orz_scene_bake(orz_context* ctx, const float* vertices, const uint32_t* vert
                    const float* refMin4, const float* refMax4, uint32_t* packetsOut, float* centersOut,
                    float* boundsMinOut, float* boundsMaxOut, orz_scene** out);
 int orz_scene_set_occludees(orz_scene* scene, const float* boxes, uint32_t nBoxes); /* n x (min4, max4) */
+/* Main.cpp:86-128 in one call: indexed triangle mesh -> quads (orz_quad_decompose) -> padding to 8 quads -> per-quad
+ * boxes -> SAH batches on the GPU (orz_generate_batches_device) -> reference box over all vertices -> Occluder::bake
+ * of every batch on the GPU (orz_scene_bake).  occludeesFromQuads != 0 installs the per-quad boxes (w := 1, batch
+ * order) as the occludee set (BASELINE configs 1-3).  splitGranularity: a multiple of 8. */
+typedef struct {
+  uint32_t nOccluders, nQuads; /* batches; quads after padding */
+  float refMin[4], refMax[4];  /* Main.cpp:109-113 */
+} orz_mesh_scene_info;
+int orz_scene_from_mesh(orz_context* ctx, const uint32_t* indices, size_t nIndices, const float* vertices, size_t nVertices,
+                        uint32_t targetSize, uint32_t splitGranularity, int occludeesFromQuads, orz_scene** out,
+                        orz_mesh_scene_info* info /* may be NULL */);
+/* What the application reads from its occluders (Occluder.h:11-20; Main.cpp:186-195 sorts by m_center and gates with
+ * the bounds): nOccluders x 4 floats each, quadCounts: nOccluders words.  Any output may be NULL. */
+int orz_scene_get_occluders(orz_scene* scene, uint32_t* nOccluders, float* centers, float* boundsMin, float* boundsMax,
+                            uint32_t* quadCounts);
 void orz_scene_destroy(orz_scene* scene);
 
 enum {

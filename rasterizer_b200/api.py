@@ -36,6 +36,10 @@ class PrimRecord(C.Structure):
                 ("nx", C.c_float * 4), ("ny", C.c_float * 4), ("off", C.c_float * 4), ("slope", C.c_uint32 * 4)]
 
 
+class MeshSceneInfo(C.Structure):
+    _fields_ = [("nOccluders", C.c_uint32), ("nQuads", C.c_uint32), ("refMin", C.c_float * 4), ("refMax", C.c_float * 4)]
+
+
 class ViewBatch(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("nViews", C.c_uint32), ("flags", C.c_uint32),
                 ("mvps", C.c_void_p), ("orders", C.c_void_p), ("camPos", C.c_void_p),
@@ -44,6 +48,9 @@ class ViewBatch(C.Structure):
 
 
 EXPORTS = {
+    "orz_scene_from_mesh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int,
+                                      C.POINTER(C.c_void_p), C.c_void_p]),
+    "orz_scene_get_occluders": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "orz_generate_batches_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                               C.c_uint32, C.POINTER(C.c_uint32)]),
     "orz_quad_decompose": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]),
@@ -388,6 +395,29 @@ class Scene:
         self.n_boxes = 0
         if boxes is not None:
             self.set_occludees(boxes)
+        return self
+
+    @classmethod
+    def from_mesh(cls, ctx: Context, indices, vertices, target_size: int = 512, split_granularity: int = 8, occludees_from_quads: bool = True) -> "Scene":
+        """Main.cpp:86-128 in one call (orz_scene_from_mesh): triangle mesh in, baked scene resident in HBM out."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        idx = np.ascontiguousarray(indices, np.uint32).reshape(-1)
+        v = _f32(vertices).reshape(-1, 4)
+        h, info = C.c_void_p(), MeshSceneInfo()
+        _check(lib().orz_scene_from_mesh(ctx.h, _p(idx), idx.size, _p(v), v.shape[0], target_size, split_granularity, int(occludees_from_quads),
+                                         C.byref(h), C.byref(info)))
+        self.h = h
+        n = self.n_occluders = int(info.nOccluders)
+        self.n_quads = int(info.nQuads)
+        self.centers, self.bounds_min, self.bounds_max = (np.zeros((n, 4), np.float32) for _ in range(3))
+        counts = np.zeros(n, np.uint32)
+        _check(lib().orz_scene_get_occluders(h, None, _p(self.centers), _p(self.bounds_min), _p(self.bounds_max), _p(counts)))
+        self.quads_per_occluder = counts
+        self.ref_min = np.ascontiguousarray(np.broadcast_to(np.array(info.refMin, np.float32), (n, 4)))
+        self.ref_max = np.ascontiguousarray(np.broadcast_to(np.array(info.refMax, np.float32), (n, 4)))
+        self.packed_list = None  # the baked words exist in HBM only
+        self.n_boxes = self.n_quads if occludees_from_quads else 0
         return self
 
     def set_occludees(self, boxes):

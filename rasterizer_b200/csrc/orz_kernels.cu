@@ -510,6 +510,23 @@ extern "C" int orz_scene_set_occludees(orz_scene* s, const float* boxes, uint32_
   }
   return ORZ_OK;
 }
+extern "C" int orz_scene_get_occluders(orz_scene* s, uint32_t* nOccluders, float* centers, float* boundsMin, float* boundsMax,
+                                       uint32_t* quadCounts) {
+  if (!s) return fail(ORZ_ERR_ARG, "orz_scene_get_occluders: scene is NULL");
+  if (nOccluders) *nOccluders = s->nOcc;
+  if (!centers && !boundsMin && !boundsMax && !quadCounts) return ORZ_OK;
+  ORZ_CUDA(cudaSetDevice(s->ctx->device));
+  std::vector<OccMeta> meta(s->nOcc);
+  ORZ_CUDA(cudaMemcpyAsync(meta.data(), s->d_occ, s->nOcc * sizeof(OccMeta), cudaMemcpyDeviceToHost, s->ctx->stream));
+  ORZ_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  for (uint32_t i = 0; i < s->nOcc; ++i) {
+    if (centers) memcpy(centers + 4 * i, meta[i].center, 16);
+    if (boundsMin) memcpy(boundsMin + 4 * i, meta[i].boundsMin, 16);
+    if (boundsMax) memcpy(boundsMax + 4 * i, meta[i].boundsMax, 16);
+    if (quadCounts) quadCounts[i] = meta[i].quadCount;
+  }
+  return ORZ_OK;
+}
 extern "C" void orz_scene_destroy(orz_scene* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);

@@ -528,3 +528,73 @@ extern "C" int orz_generate_batches(const float* aabbs, uint32_t nAabbs, uint32_
   for (size_t b = 0; b < st.leaves.size(); ++b) batchSizes[b] = st.leaves[b].second;
   return ORZ_OK;
 }
+
+// Main.cpp:86-128 in one call: mesh -> quads (host) -> pad -> per-quad boxes -> SAH batches (GPU) -> reference box
+// -> Occluder::bake of every batch (GPU).  The scene never exists on the host in baked form.
+extern "C" int orz_scene_from_mesh(orz_context* ctx, const uint32_t* indices, size_t nIndices, const float* vertices, size_t nVertices,
+                                   uint32_t targetSize, uint32_t splitGranularity, int occludeesFromQuads, orz_scene** out,
+                                   orz_mesh_scene_info* info) {
+  if (!ctx || !out || !vertices || nVertices == 0 || nIndices < 3) return set_error(ORZ_ERR_ARG, "orz_scene_from_mesh: bad arguments");
+  if (splitGranularity == 0 || splitGranularity % 8 != 0 || targetSize > 10240)
+    return set_error(ORZ_ERR_ARG, "orz_scene_from_mesh: splitGranularity must be a multiple of 8 (Occluder::bake packs 8 quads, Occluder.cpp:108) "
+                                  "and targetSize at most 10 240 (device bake)");
+  std::vector<uint32_t> quads(4 * (nIndices / 3));
+  size_t words = 0;
+  int rc = orz_quad_decompose(indices, nIndices, vertices, nVertices, quads.data(), &words);
+  if (rc != ORZ_OK) return rc;
+  quads.resize(words);
+  while (quads.size() % 32 != 0) quads.push_back(quads[0]);  // Main.cpp:91-94
+  const uint32_t nQuads = uint32_t(quads.size() / 4);
+  // Main.cpp:96-105: Aabb::include over the four corners, all four lanes
+  std::vector<float> boxes(size_t(nQuads) * 8);
+  parallel_ranges(nQuads, 1 << 14, [&](size_t, size_t q0, size_t q1) {
+    for (size_t q = q0; q < q1; ++q) {
+      float* b = boxes.data() + 8 * q;
+      for (int k = 0; k < 4; ++k) { b[k] = INFINITY; b[4 + k] = -INFINITY; }
+      for (int c = 0; c < 4; ++c) {
+        const float* v = vertices + 4 * size_t(quads[4 * q + c]);
+        for (int k = 0; k < 4; ++k) { b[k] = min_x86(b[k], v[k]); b[4 + k] = max_x86(b[4 + k], v[k]); }
+      }
+    }
+  });
+  std::vector<uint32_t> order(nQuads), sizes(nQuads / splitGranularity + 2);
+  uint32_t nBatches = 0;
+  rc = orz_generate_batches_device(ctx, boxes.data(), nQuads, targetSize, splitGranularity, order.data(), sizes.data(), uint32_t(sizes.size()), &nBatches);
+  if (rc != ORZ_OK) return rc;
+  float refMin[4], refMax[4];  // Main.cpp:109-113: over ALL vertices, referenced or not
+  for (int k = 0; k < 4; ++k) { refMin[k] = INFINITY; refMax[k] = -INFINITY; }
+  for (size_t v = 0; v < nVertices; ++v)
+    for (int k = 0; k < 4; ++k) { refMin[k] = min_x86(refMin[k], vertices[4 * v + k]); refMax[k] = max_x86(refMax[k], vertices[4 * v + k]); }
+  // Main.cpp:116-128: the batches' corner positions, then bake
+  std::vector<float> batchVerts(size_t(nQuads) * 16), occludees(occludeesFromQuads ? size_t(nQuads) * 8 : 0);
+  std::vector<uint32_t> vertCounts(nBatches);
+  for (uint32_t b = 0; b < nBatches; ++b) vertCounts[b] = sizes[b] * 4;
+  parallel_ranges(nQuads, 1 << 14, [&](size_t, size_t q0, size_t q1) {
+    for (size_t q = q0; q < q1; ++q) {
+      const uint32_t src = order[q];
+      for (int c = 0; c < 4; ++c) memcpy(batchVerts.data() + 16 * q + 4 * c, vertices + 4 * size_t(quads[4 * size_t(src) + c]), 16);
+      if (occludeesFromQuads) {
+        memcpy(occludees.data() + 8 * q, boxes.data() + 8 * size_t(src), 32);
+        occludees[8 * q + 3] = occludees[8 * q + 7] = 1.0f;  // w := 1 as Occluder.cpp:172-173 does for its bounds
+      }
+    }
+  });
+  orz_scene* scene = nullptr;
+  rc = orz_scene_bake(ctx, batchVerts.data(), vertCounts.data(), nBatches, refMin, refMax, nullptr, nullptr, nullptr, nullptr, &scene);
+  if (rc != ORZ_OK) return rc;
+  if (occludeesFromQuads) {
+    rc = orz_scene_set_occludees(scene, occludees.data(), nQuads);
+    if (rc != ORZ_OK) {
+      orz_scene_destroy(scene);
+      return rc;
+    }
+  }
+  if (info) {
+    info->nOccluders = nBatches;
+    info->nQuads = nQuads;
+    memcpy(info->refMin, refMin, 16);
+    memcpy(info->refMax, refMax, 16);
+  }
+  *out = scene;
+  return ORZ_OK;
+}

@@ -49,3 +49,23 @@ def test_cpp_frame_loop(tmp_path, name, size):
     assert np.array_equal(depth, port.depth())
     assert np.array_equal(image, port.readback())
     port.close()
+
+
+def test_cpp_preparation_on_the_gpu(tmp_path):
+    """tests/dropin_prepare.cpp (Main.cpp:86-128 against the reference's class names): with the drop-in
+    SurfaceAreaHeuristic batching on the GPU the baked scene equals the one batched on the host."""
+    from oracle import ref_oracle as ro
+
+    if not ro.scene_available("Castle"):
+        pytest.skip("no Castle data under oracle/_ref/scenes")
+    exe = os.path.join(ROOT, "tests", "_build", "dropin_prepare")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-mavx2", "-msse4.1", "-Wno-ignored-attributes", "-I", os.path.join(ROOT, "rasterizer_b200", "csrc", "dropin"),
+                           "-o", exe, os.path.join(ROOT, "tests", "dropin_prepare.cpp"), "-L", os.path.join(ROOT, "rasterizer_b200"),
+                           "-lrasterizer_b200", "-Wl,-rpath," + os.path.join(ROOT, "rasterizer_b200")])
+    d = os.path.join(ro.SCENE_DIR, "Castle")
+    files = [os.path.join(d, "IndexBuffer.bin"), os.path.join(d, "VertexBuffer.bin")]
+    subprocess.check_call([exe, *files, str(tmp_path / "host.bin")], env=dict(os.environ, ORZ_PREP_ON_HOST="1"))
+    subprocess.check_call([exe, *files, str(tmp_path / "gpu.bin")], env={k: v for k, v in os.environ.items() if k != "ORZ_PREP_ON_HOST"})
+    host, gpu = np.fromfile(tmp_path / "host.bin", np.uint32), np.fromfile(tmp_path / "gpu.bin", np.uint32)
+    assert host[0] == 76 and np.array_equal(host, gpu)

@@ -42,7 +42,7 @@ def test_device_batches_equal_host(ctx, seed, n, target, gran, snap):
 def test_device_batches_of_the_reference_scenes(ctx, name):
     if not wl.have_scene(name):
         pytest.skip("prepared scene missing")
-    boxes = wl.load_scene(name).quadboxes_case()  # the quads' AABBs, in batch order instead of mesh order
+    boxes = wl.load_scene(name).quad_boxes()  # the quads' AABBs, in batch order instead of mesh order
     got = ctx.generate_batches(boxes, 512, 8)
     assert same_batches(got, api.generate_batches(boxes, 512, 8))
     assert len(got) >= 70 and all(len(b) % 8 == 0 and len(b) < 512 for b in got)
@@ -69,7 +69,7 @@ def test_prepare_mesh_on_device_feeds_the_renderer(ctx):
     dev = wl.prepare_mesh("terrain", idx, verts, {}, 128, 8, generate_batches=ctx.generate_batches)
     assert len(host.batches) == len(dev.batches) > 8
     assert all(np.array_equal(a.view(np.uint32), b.view(np.uint32)) for a, b in zip(host.batches, dev.batches))
-    scene = api.Scene.bake_on_device(ctx, dev.batches, dev.ref_min, dev.ref_max, dev.quadboxes_case())
+    scene = api.Scene.bake_on_device(ctx, dev.batches, dev.ref_min, dev.ref_max, dev.quad_boxes())
     scene_host = api.Scene.from_prepared(ctx, host)
     w, h = 640, 360
     pos = np.array([20.0, 15.0, -10.0], np.float32)
@@ -79,3 +79,31 @@ def test_prepare_mesh_on_device_feeds_the_renderer(ctx):
     assert 0 < vis.sum() < dev.n_quads
     assert np.array_equal(out["vis"], scene_host.render_views(w, h, mvp[None], cam_pos=pos[None], want=("vis",))["vis"])
     scene.close(); scene_host.close()
+
+
+def test_scene_from_mesh_in_one_call(ctx):
+    """orz_scene_from_mesh (decompose on the host, batches + bake on the GPU) against the step-by-step host
+    preparation: same occluders, and the same frame."""
+    from rasterizer_b200 import camera as cam
+
+    api.set_rsqrt_table(None)
+    cases = [("terrain", *terrain(np.random.default_rng(9), 6000, 2.0), dict(pos=(20.0, 15.0, -10.0), dir=(0.0, -0.4, 0.9), up=(0.0, 1.0, 0.0), fov=0.9), (640, 360))]
+    if ro.available() and ro.scene_available("Castle"):
+        cases.append(("castle", *ro.load_mesh("Castle"), cam.CASTLE_CAMERA, (1920, 1080)))
+    for name, idx, verts, c, (w, h) in cases:
+        host = wl.prepare_mesh(name, idx, verts, {})
+        want = api.Scene.from_prepared(ctx, host)
+        got = api.Scene.from_mesh(ctx, idx, verts)
+        assert got.n_occluders == want.n_occluders and got.n_boxes == want.n_boxes == host.n_quads
+        for a, b in ((got.centers, want.centers), (got.bounds_min, want.bounds_min), (got.bounds_max, want.bounds_max)):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        assert np.array_equal(got.quads_per_occluder, [b.shape[0] // 4 for b in host.batches])
+        pos = np.asarray(c["pos"], np.float32)
+        mvp = cam.view_projection(pos, np.asarray(c["dir"], np.float32), np.asarray(c["up"], np.float32), c["fov"], w, h)
+        outs = [s.render_views(w, h, mvp[None], cam_pos=pos[None], want=("vis", "gate", "hiz", "quads")) for s in (got, want)]
+        for key in ("vis", "gate", "hiz", "depth", "quads"):
+            assert np.array_equal(outs[0][key], outs[1][key]), (name, key)
+        assert outs[0]["quads"][0] > 0
+        got.close(); want.close()
+    with pytest.raises(api.OrzError, match="multiple of 8"):
+        api.Scene.from_mesh(ctx, cases[0][1], cases[0][2], 512, 4)

@@ -95,56 +95,63 @@ __global__ void __launch_bounds__(kSahThreads) k_sah_hist(const uint32_t* __rest
   if (threadIdx.x < 16) hist[threadIdx.x * numTiles + blockIdx.x] = h[threadIdx.x];
 }
 
-// in-place exclusive scan of `count` words by ONE CTA of 1 024 threads (count = 16 * tiles: small)
+// in-place exclusive scan of `count` words by ONE CTA of 1 024 threads (count = 16 * tiles: small).  Every thread
+// owns ceil(count / 1024) CONSECUTIVE words: one pass to sum them, one block scan of the 1 024 sums, one pass to
+// write the prefixes -- a single round of barriers whatever the size.
 __global__ void __launch_bounds__(1024) k_sah_scan(uint32_t* __restrict__ data, uint32_t count) {
   __shared__ uint32_t warpSum[32];
-  __shared__ uint32_t carry;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  if (tid == 0) carry = 0;
+  const uint32_t per = (count + 1023u) / 1024u;
+  const uint32_t first = min(tid * per, count), last = min(first + per, count);
+  uint32_t sum = 0;
+  for (uint32_t i = first; i < last; ++i) sum += data[i];
+  uint32_t x = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(kFull, x, d);
+    if (lane >= (uint32_t)d) x += y;
+  }
+  if (lane == 31) warpSum[warp] = x;
   __syncthreads();
-  for (uint32_t base = 0; base < count; base += 1024) {
-    const uint32_t i = base + tid;
-    const uint32_t v = i < count ? data[i] : 0u;
-    uint32_t x = v;
+  if (warp == 0) {
+    uint32_t w = warpSum[lane];
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t y = __shfl_up_sync(kFull, x, d);
-      if (lane >= (uint32_t)d) x += y;
+      const uint32_t y = __shfl_up_sync(kFull, w, d);
+      if (lane >= (uint32_t)d) w += y;
     }
-    if (lane == 31) warpSum[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t w = warpSum[lane];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(kFull, w, d);
-        if (lane >= (uint32_t)d) w += y;
-      }
-      warpSum[lane] = w;
-    }
-    __syncthreads();
-    const uint32_t prefix = carry + (warp ? warpSum[warp - 1] : 0u) + x - v;
-    if (i < count) data[i] = prefix;
-    __syncthreads();
-    if (tid == 1023) carry = prefix + v;
-    __syncthreads();
+    warpSum[lane] = w;
+  }
+  __syncthreads();
+  uint32_t run = (warp ? warpSum[warp - 1] : 0u) + x - sum;
+  for (uint32_t i = first; i < last; ++i) {
+    const uint32_t v = data[i];
+    data[i] = run;
+    run += v;
   }
 }
 
 // Every thread owns kSahItems CONSECUTIVE elements and counts its digits in its own column of
 // cnt[digit][thread]; the block scan of cnt in (digit, thread) order then gives every element its
-// place in the tile's stable order without any cross-thread ranking.
+// place in the tile's stable order without any cross-thread ranking.  The tile is put into that order
+// in shared memory first, so that the global stores of a warp go to consecutive addresses (one run per
+// digit) instead of 32 different lines.  Counters are padded by one word per 16 (ORZ_SAH_CNT): both the
+// per-thread column accesses and the 16-consecutive-word accesses of the scan are then conflict-free.
+#define ORZ_SAH_CNT(L) cnt[(L) + ((L) >> 4)]
 __global__ void __launch_bounds__(kSahThreads) k_sah_scatter(const uint32_t* __restrict__ keyIn, const uint32_t* __restrict__ idxIn,
                                                              const uint32_t* __restrict__ segIn, uint32_t* __restrict__ keyOut,
                                                              uint32_t* __restrict__ idxOut, uint32_t* __restrict__ segOut, uint32_t M,
                                                              int shift, int bySegment, uint32_t numTiles,
                                                              const uint32_t* __restrict__ histScanned) {
-  __shared__ uint32_t cnt[16 * kSahThreads];
+  __shared__ uint32_t cnt[16 * kSahThreads + kSahThreads];
   __shared__ uint32_t warpTot[kSahThreads / 32];
+  __shared__ uint32_t sKey[kSahTile], sIdx[kSahTile], sSeg[kSahTile];
+  __shared__ uint32_t digitStart[16], globalStart[16];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 #pragma unroll
-  for (int d = 0; d < 16; ++d) cnt[d * kSahThreads + tid] = 0;
-  const uint32_t base = blockIdx.x * kSahTile + tid * kSahItems;
+  for (int d = 0; d < 16; ++d) ORZ_SAH_CNT(d * kSahThreads + tid) = 0;
+  const uint32_t tileStart = blockIdx.x * kSahTile, base = tileStart + tid * kSahItems;
+  const uint32_t tileCount = min((uint32_t)kSahTile, M - tileStart);
   uint32_t k[kSahItems], ix[kSahItems], sg[kSahItems], dg[kSahItems], rk[kSahItems];
 #pragma unroll
   for (int e = 0; e < kSahItems; ++e) {
@@ -154,7 +161,7 @@ __global__ void __launch_bounds__(kSahThreads) k_sah_scatter(const uint32_t* __r
       ix[e] = idxIn[base + e];
       sg[e] = segIn[base + e];
       dg[e] = ((bySegment ? sg[e] : k[e]) >> shift) & 15u;
-      rk[e] = cnt[dg[e] * kSahThreads + tid]++;
+      rk[e] = ORZ_SAH_CNT(dg[e] * kSahThreads + tid)++;
     }
   }
   __syncthreads();
@@ -162,7 +169,7 @@ __global__ void __launch_bounds__(kSahThreads) k_sah_scatter(const uint32_t* __r
   uint32_t vals[16], sum = 0;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    vals[i] = cnt[tid * 16 + i];
+    vals[i] = ORZ_SAH_CNT(tid * 16 + i);
     sum += vals[i];
   }
   uint32_t x = sum;
@@ -177,20 +184,33 @@ __global__ void __launch_bounds__(kSahThreads) k_sah_scatter(const uint32_t* __r
   for (uint32_t w = 0; w < warp; ++w) run += warpTot[w];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    cnt[tid * 16 + i] = run;
+    ORZ_SAH_CNT(tid * 16 + i) = run;
     run += vals[i];
   }
   __syncthreads();
+  if (tid < 16) {
+    digitStart[tid] = ORZ_SAH_CNT(tid * kSahThreads);
+    globalStart[tid] = histScanned[tid * numTiles + blockIdx.x];
+  }
 #pragma unroll
   for (int e = 0; e < kSahItems; ++e)
     if (dg[e] < 16u) {
-      const uint32_t d = dg[e];
-      const uint32_t dest = histScanned[d * numTiles + blockIdx.x] + (cnt[d * kSahThreads + tid] - cnt[d * kSahThreads]) + rk[e];
-      keyOut[dest] = k[e];
-      idxOut[dest] = ix[e];
-      segOut[dest] = sg[e];
+      const uint32_t place = ORZ_SAH_CNT(dg[e] * kSahThreads + tid) + rk[e];  // position in the tile's stable order
+      sKey[place] = k[e];
+      sIdx[place] = ix[e];
+      sSeg[place] = sg[e];
     }
+  __syncthreads();
+  for (uint32_t j = tid; j < tileCount; j += kSahThreads) {
+    const uint32_t key = sKey[j], seg = sSeg[j];
+    const uint32_t d = ((bySegment ? seg : key) >> shift) & 15u;
+    const uint32_t dest = globalStart[d] + (j - digitStart[d]);
+    keyOut[dest] = key;
+    idxOut[dest] = sIdx[j];
+    segOut[dest] = seg;
+  }
 }
+#undef ORZ_SAH_CNT
 
 // ---- prefix / suffix boxes and their areas --------------------------------------------------------
 __device__ __forceinline__ SahBox sah_empty() {
@@ -323,20 +343,32 @@ __global__ void __launch_bounds__(kSahChunk) k_sah_areas(const float4* __restric
 }
 
 // cost of splitting before position j (SurfaceAreaHeuristic.cpp:46-66); best[segment] = min over
-// (cost, axis, position): equal costs keep the earlier axis / position like the serial loop
+// (cost, axis, position): equal costs keep the earlier axis / position like the serial loop.  A block that
+// lies inside one segment (nearly all of them on the upper levels) reduces in shared memory first, so the
+// root's quarter of a million candidates do not queue up on one address.
 __global__ void __launch_bounds__(256) k_sah_costs(const float* __restrict__ areaLeft, const float* __restrict__ areaRight,
                                                    const uint32_t* __restrict__ segStatic, const SahSeg* __restrict__ segs, uint32_t M,
                                                    uint32_t granularity, uint32_t axis, unsigned long long* __restrict__ best) {
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= M) return;
-  const uint32_t sIdx = segStatic[j];
-  const SahSeg s = segs[sIdx];
-  const uint32_t pos = j - s.wstart;
-  if (pos < granularity || pos >= s.n - granularity || pos % granularity != 0) return;
-  const float scaledLeft = areaLeft[j - 1] * (float)(int)pos;
-  const float scaledRight = areaRight[j] * (float)(int)(s.n - pos);
-  const float cost = scaledLeft + scaledRight;
-  if (!(cost < u2f(0x7f800000u))) return;  // comilt against the initial +inf: never for inf / NaN
-  const unsigned long long packed = ((unsigned long long)sah_key(cost) << 32) | ((unsigned long long)axis << 30) | pos;
-  atomicMin(best + sIdx, packed);
+  __shared__ unsigned long long blockBest;
+  const uint32_t blockFirst = blockIdx.x * blockDim.x, blockLast = min(blockFirst + blockDim.x, M) - 1u;
+  const bool oneSegment = segStatic[blockFirst] == segStatic[blockLast];  // segments are contiguous
+  if (threadIdx.x == 0) blockBest = ~0ull;
+  __syncthreads();
+  const uint32_t j = blockFirst + threadIdx.x;
+  if (j < M) {
+    const uint32_t sIdx = segStatic[j];
+    const SahSeg s = segs[sIdx];
+    const uint32_t pos = j - s.wstart;
+    if (pos >= granularity && pos < s.n - granularity && pos % granularity == 0) {
+      const float scaledLeft = areaLeft[j - 1] * (float)(int)pos;
+      const float scaledRight = areaRight[j] * (float)(int)(s.n - pos);
+      const float cost = scaledLeft + scaledRight;
+      if (cost < u2f(0x7f800000u)) {  // comilt against the initial +inf: never for inf / NaN
+        const unsigned long long packed = ((unsigned long long)sah_key(cost) << 32) | ((unsigned long long)axis << 30) | pos;
+        atomicMin(oneSegment ? &blockBest : best + sIdx, packed);
+      }
+    }
+  }
+  __syncthreads();
+  if (oneSegment && threadIdx.x == 0 && blockBest != ~0ull) atomicMin(best + segStatic[blockFirst], blockBest);
 }

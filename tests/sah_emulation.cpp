@@ -54,6 +54,7 @@ static inline T __shfl_down_sync(unsigned, T v, int d) {
 }
 template <typename T>
 static inline T __shfl_sync(unsigned, T v, int src) { return emu_exchange(v, unsigned(src) & 31u); }
+static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) {
   unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);

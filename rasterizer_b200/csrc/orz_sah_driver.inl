@@ -6,7 +6,7 @@ namespace {
 struct SahBuffers {
   float4* boxes = nullptr;
   uint32_t *order = nullptr, *key[2] = {nullptr, nullptr}, *idx[2] = {nullptr, nullptr}, *seg[2] = {nullptr, nullptr};
-  uint32_t *segStatic = nullptr, *hist = nullptr, *segChunk0 = nullptr;
+  uint32_t *segStatic = nullptr, *hist = nullptr, *digitTotals = nullptr, *segChunk0 = nullptr;
   float *areaLeft = nullptr, *areaRight = nullptr;
   SahSeg* segs = nullptr;
   SahChunk* chunks = nullptr;
@@ -14,7 +14,7 @@ struct SahBuffers {
   unsigned long long* best = nullptr;
   int cur = 0;  // which half of key / idx / seg holds the current order
   ~SahBuffers() {
-    void* all[] = {boxes, order, key[0], key[1], idx[0], idx[1], seg[0], seg[1], segStatic, hist, segChunk0, areaLeft, areaRight,
+    void* all[] = {boxes, order, key[0], key[1], idx[0], idx[1], seg[0], seg[1], segStatic, hist, digitTotals, segChunk0, areaLeft, areaRight,
                    segs, chunks, chunkBox, before, after, best};
     for (void* p : all) cudaFree(p);
   }
@@ -27,9 +27,9 @@ void sah_sort(orz_context* ctx, SahBuffers& B, uint32_t M, uint32_t nSegs) {
   for (int pass = 0; pass < 8 + (segBits + 3) / 4; ++pass) {
     const int bySegment = pass >= 8, shift = 4 * (bySegment ? pass - 8 : pass), c = B.cur;
     ORZ_LAUNCH(k_sah_hist, tiles, kSahThreads, ctx->stream, bySegment ? B.seg[c] : B.key[c], M, shift, tiles, B.hist);
-    ORZ_LAUNCH(k_sah_scan, 1, 1024, ctx->stream, B.hist, 16 * tiles);
+    ORZ_LAUNCH(k_sah_scan, 16, 256, ctx->stream, B.hist, tiles, B.digitTotals);
     ORZ_LAUNCH(k_sah_scatter, tiles, kSahThreads, ctx->stream, B.key[c], B.idx[c], B.seg[c], B.key[c ^ 1], B.idx[c ^ 1], B.seg[c ^ 1], M, shift,
-                                                          bySegment, tiles, B.hist);
+                                                          bySegment, tiles, B.hist, B.digitTotals);
     ctx->launches += 3;
     B.cur ^= 1;
   }
@@ -58,6 +58,7 @@ extern "C" int orz_generate_batches_device(orz_context* ctx, const float* aabbs,
   ORZ_CUDA(cudaMalloc(&B.areaLeft, std::max<size_t>(n, 1) * 4));
   ORZ_CUDA(cudaMalloc(&B.areaRight, std::max<size_t>(n, 1) * 4));
   ORZ_CUDA(cudaMalloc(&B.hist, (size_t)16 * maxTiles * 4));
+  ORZ_CUDA(cudaMalloc(&B.digitTotals, 16 * 4));
   ORZ_CUDA(cudaMalloc(&B.segs, (size_t)maxSegs * sizeof(SahSeg)));
   ORZ_CUDA(cudaMalloc(&B.segChunk0, ((size_t)maxSegs + 1) * 4));
   ORZ_CUDA(cudaMalloc(&B.best, (size_t)maxSegs * 8));
@@ -104,7 +105,7 @@ extern "C" int orz_generate_batches_device(orz_context* ctx, const float* aabbs,
       ORZ_LAUNCH(k_sah_keys, grid, 256, ctx->stream, B.boxes, B.idx[B.cur], B.segStatic, B.segs, axis, M, B.key[B.cur]);
       sah_sort(ctx, B, M, nSegs);
       ORZ_LAUNCH(k_sah_chunk_boxes, nChunks, kSahChunk, ctx->stream, B.boxes, B.idx[B.cur], B.chunks, B.chunkBox);
-      ORZ_LAUNCH(k_sah_chunk_scan, nSegs, 32, ctx->stream, B.chunkBox, B.segChunk0, B.before, B.after);
+      ORZ_LAUNCH(k_sah_chunk_scan, nSegs, 64, ctx->stream, B.chunkBox, B.segChunk0, B.before, B.after);
       ORZ_LAUNCH(k_sah_areas, nChunks, kSahChunk, ctx->stream, B.boxes, B.idx[B.cur], B.chunks, B.before, B.after, B.areaLeft, B.areaRight);
       ORZ_LAUNCH(k_sah_costs, grid, 256, ctx->stream, B.areaLeft, B.areaRight, B.segStatic, B.segs, M, granularity, (uint32_t)axis, B.best);
       ctx->launches += 5;

@@ -95,40 +95,43 @@ __global__ void __launch_bounds__(kSahThreads) k_sah_hist(const uint32_t* __rest
   if (threadIdx.x < 16) hist[threadIdx.x * numTiles + blockIdx.x] = h[threadIdx.x];
 }
 
-// in-place exclusive scan of `count` words by ONE CTA of 1 024 threads (count = 16 * tiles: small).  Every thread
-// owns ceil(count / 1024) CONSECUTIVE words: one pass to sum them, one block scan of the 1 024 sums, one pass to
-// write the prefixes -- a single round of barriers whatever the size.
-__global__ void __launch_bounds__(1024) k_sah_scan(uint32_t* __restrict__ data, uint32_t count) {
-  __shared__ uint32_t warpSum[32];
+// One CTA per digit: in-place exclusive scan of the digit's row hist[digit * numTiles ..] (1 024 tiles per round,
+// 4 consecutive ones per thread) and the digit's total; k_sah_scatter adds the totals of the smaller digits itself.
+__global__ void __launch_bounds__(256) k_sah_scan(uint32_t* __restrict__ hist, uint32_t numTiles, uint32_t* __restrict__ totals) {
+  __shared__ uint32_t warpSum[8];
+  __shared__ uint32_t carry;
+  uint32_t* row = hist + blockIdx.x * numTiles;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const uint32_t per = (count + 1023u) / 1024u;
-  const uint32_t first = min(tid * per, count), last = min(first + per, count);
-  uint32_t sum = 0;
-  for (uint32_t i = first; i < last; ++i) sum += data[i];
-  uint32_t x = sum;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t y = __shfl_up_sync(kFull, x, d);
-    if (lane >= (uint32_t)d) x += y;
-  }
-  if (lane == 31) warpSum[warp] = x;
+  if (tid == 0) carry = 0;
   __syncthreads();
-  if (warp == 0) {
-    uint32_t w = warpSum[lane];
+  for (uint32_t base = 0; base < numTiles; base += 1024) {
+    const uint32_t i = base + 4 * tid;
+    uint32_t v[4], sum = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[e] = i + e < numTiles ? row[i + e] : 0u;
+      sum += v[e];
+    }
+    uint32_t x = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t y = __shfl_up_sync(kFull, w, d);
-      if (lane >= (uint32_t)d) w += y;
+      const uint32_t y = __shfl_up_sync(kFull, x, d);
+      if (lane >= (uint32_t)d) x += y;
     }
-    warpSum[lane] = w;
+    if (lane == 31) warpSum[warp] = x;
+    __syncthreads();
+    uint32_t run = carry + x - sum;
+    for (uint32_t w = 0; w < warp; ++w) run += warpSum[w];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (i + e < numTiles) row[i + e] = run;
+      run += v[e];
+    }
+    __syncthreads();
+    if (tid == 255) carry = run;
+    __syncthreads();
   }
-  __syncthreads();
-  uint32_t run = (warp ? warpSum[warp - 1] : 0u) + x - sum;
-  for (uint32_t i = first; i < last; ++i) {
-    const uint32_t v = data[i];
-    data[i] = run;
-    run += v;
-  }
+  if (tid == 0) totals[blockIdx.x] = carry;
 }
 
 // Every thread owns kSahItems CONSECUTIVE elements and counts its digits in its own column of
@@ -142,7 +145,8 @@ __global__ void __launch_bounds__(kSahThreads) k_sah_scatter(const uint32_t* __r
                                                              const uint32_t* __restrict__ segIn, uint32_t* __restrict__ keyOut,
                                                              uint32_t* __restrict__ idxOut, uint32_t* __restrict__ segOut, uint32_t M,
                                                              int shift, int bySegment, uint32_t numTiles,
-                                                             const uint32_t* __restrict__ histScanned) {
+                                                             const uint32_t* __restrict__ histScanned,
+                                                             const uint32_t* __restrict__ digitTotals) {
   __shared__ uint32_t cnt[16 * kSahThreads + kSahThreads];
   __shared__ uint32_t warpTot[kSahThreads / 32];
   __shared__ uint32_t sKey[kSahTile], sIdx[kSahTile], sSeg[kSahTile];
@@ -190,7 +194,9 @@ __global__ void __launch_bounds__(kSahThreads) k_sah_scatter(const uint32_t* __r
   __syncthreads();
   if (tid < 16) {
     digitStart[tid] = ORZ_SAH_CNT(tid * kSahThreads);
-    globalStart[tid] = histScanned[tid * numTiles + blockIdx.x];
+    uint32_t start = histScanned[tid * numTiles + blockIdx.x];  // elements of this digit in earlier tiles ...
+    for (uint32_t d = 0; d < tid; ++d) start += digitTotals[d];  // ... after all elements of smaller digits
+    globalStart[tid] = start;
   }
 #pragma unroll
   for (int e = 0; e < kSahItems; ++e)
@@ -291,28 +297,21 @@ __global__ void __launch_bounds__(kSahChunk) k_sah_chunk_boxes(const float4* __r
   }
 }
 
-// per segment (one warp): box of all chunks before / after each chunk
-__global__ void __launch_bounds__(32) k_sah_chunk_scan(const SahBox* __restrict__ chunkBox, const uint32_t* __restrict__ segChunk0,
+// per segment: box of all chunks before (warp 0) / after (warp 1) each chunk
+__global__ void __launch_bounds__(64) k_sah_chunk_scan(const SahBox* __restrict__ chunkBox, const uint32_t* __restrict__ segChunk0,
                                                        SahBox* __restrict__ before, SahBox* __restrict__ after) {
-  const uint32_t c0 = segChunk0[blockIdx.x], c1 = segChunk0[blockIdx.x + 1], lane = threadIdx.x;
+  const uint32_t c0 = segChunk0[blockIdx.x], c1 = segChunk0[blockIdx.x + 1], lane = threadIdx.x & 31u;
+  const bool fromRight = threadIdx.x >= 32;
+  SahBox* __restrict__ out = fromRight ? after : before;
   SahBox carry = sah_empty();
-  for (uint32_t base = c0; base < c1; base += 32) {
-    const uint32_t c = base + lane;
-    const SahBox incl = sah_warp_scan_up(c < c1 ? chunkBox[c] : sah_empty(), lane);
-    SahBox excl = sah_shfl_up(incl, 1);
-    if (lane == 0) excl = sah_empty();
-    if (c < c1) before[c] = sah_merge(carry, excl);
-    carry = sah_merge(carry, sah_shfl(incl, 31));
-  }
-  carry = sah_empty();
   for (uint32_t done = 0; c0 + done < c1; done += 32) {
-    const uint32_t back = done + lane;  // distance from the segment's last chunk
-    const bool valid = c0 + back < c1;
-    const uint32_t c = valid ? c1 - 1 - back : c0;
+    const uint32_t step = done + lane;  // distance from the segment's first (last) chunk
+    const bool valid = c0 + step < c1;
+    const uint32_t c = !valid ? c0 : (fromRight ? c1 - 1 - step : c0 + step);
     const SahBox incl = sah_warp_scan_up(valid ? chunkBox[c] : sah_empty(), lane);
     SahBox excl = sah_shfl_up(incl, 1);
     if (lane == 0) excl = sah_empty();
-    if (valid) after[c] = sah_merge(carry, excl);
+    if (valid) out[c] = sah_merge(carry, excl);
     carry = sah_merge(carry, sah_shfl(incl, 31));
   }
 }

@@ -125,5 +125,5 @@ extern "C" int emu_generate_batches(const float* aabbs, uint32_t n, uint32_t tar
   return rc;
 }
 extern "C" const char* emu_last_error() { return g_err.c_str(); }
-// k_sah_scan on its own: the in-place exclusive scan of the radix histograms (carry across 1 024-word rounds)
-extern "C" void emu_scan(uint32_t* data, uint32_t count) { ORZ_LAUNCH(k_sah_scan, 1, 1024, nullptr, data, count); }
+// k_sah_scan on its own: 16 digit rows of numTiles words, scanned in place (carry across 1 024-word rounds) + row totals
+extern "C" void emu_scan(uint32_t* hist, uint32_t numTiles, uint32_t* totals) { ORZ_LAUNCH(k_sah_scan, 16, 256, nullptr, hist, numTiles, totals); }

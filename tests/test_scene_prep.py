@@ -144,7 +144,7 @@ def test_cpp_dropin_preparation(tmp_path):
     s.close()
 
 
-@pytest.mark.parametrize("seed,n,target,gran,snap", [(1, 24, 512, 8, None), (4, 2600, 512, 8, 10.0), (8, 700, 16, 1, 25.0)])
+@pytest.mark.parametrize("seed,n,target,gran,snap", [(1, 24, 512, 8, None), (4, 2300, 1024, 8, 10.0), (8, 260, 16, 1, 25.0)])
 def test_device_batching_source_emulated_on_the_cpu(seed, n, target, gran, snap):
     """tests/sah_emulation.cpp compiles the CUDA kernel source and the host level loop of the device
     batching against a thread-per-lane emulation of launches, barriers, shuffles and atomics: their logic
@@ -168,8 +168,9 @@ def test_device_batching_source_emulated_on_the_cpu(seed, n, target, gran, snap)
     got = np.split(order, np.cumsum(sizes[: count.value])[:-1])
     assert same_batches(got, api.generate_batches(boxes, target, gran))
     if seed == 1:  # the radix histogram scan on its own, with carries across its 1 024-word rounds
-        for words in (1, 1025, 5000):
-            d = np.random.default_rng(words).integers(0, 3000, words).astype(np.uint32)
-            want = np.concatenate([[0], np.cumsum(d)[:-1]]).astype(np.uint32)
-            L.emu_scan(d.ctypes.data_as(C.c_void_p), words)
-            assert np.array_equal(d, want)
+        for tiles in (1, 1025, 2500):
+            d = np.random.default_rng(tiles).integers(0, 3000, (16, tiles)).astype(np.uint32)
+            want = np.concatenate([np.zeros((16, 1), np.uint32), np.cumsum(d, axis=1, dtype=np.uint32)[:, :-1]], axis=1)
+            totals, sums = np.zeros(16, np.uint32), d.sum(axis=1, dtype=np.uint32)
+            L.emu_scan(d.ctypes.data_as(C.c_void_p), tiles, totals.ctypes.data_as(C.c_void_p))
+            assert np.array_equal(d, want) and np.array_equal(totals, sums)

@@ -13,11 +13,8 @@ struct SahBuffers {
   SahBox *chunkBox = nullptr, *before = nullptr, *after = nullptr;
   unsigned long long* best = nullptr;
   int cur = 0;  // which half of key / idx / seg holds the current order
-  ~SahBuffers() {
-    void* all[] = {boxes, order, key[0], key[1], idx[0], idx[1], seg[0], seg[1], segStatic, hist, digitTotals, segChunk0, areaLeft, areaRight,
-                   segs, chunks, chunkBox, before, after, best};
-    for (void* p : all) cudaFree(p);
-  }
+  char* arena = nullptr;  // everything above lives in this one allocation
+  ~SahBuffers() { cudaFree(arena); }
 };
 // stable sort of the working array by (segment, key): 8 key digits, then as many segment digits as the level needs
 void sah_sort(orz_context* ctx, SahBuffers& B, uint32_t M, uint32_t nSegs) {
@@ -47,25 +44,32 @@ extern "C" int orz_generate_batches_device(orz_context* ctx, const float* aabbs,
   const uint32_t maxSegs = n / std::max(1u, std::min(granularity, targetSize)) + 2;  // every node holds >= granularity elements
   const uint32_t maxChunks = n / kSahChunk + maxSegs + 1, maxTiles = n / kSahTile + 1;
   SahBuffers B;
-  ORZ_CUDA(cudaMalloc(&B.boxes, std::max<size_t>(n, 1) * 32));
-  ORZ_CUDA(cudaMalloc(&B.order, std::max<size_t>(n, 1) * 4));
-  for (int h = 0; h < 2; ++h) {
-    ORZ_CUDA(cudaMalloc(&B.key[h], std::max<size_t>(n, 1) * 4));
-    ORZ_CUDA(cudaMalloc(&B.idx[h], std::max<size_t>(n, 1) * 4));
-    ORZ_CUDA(cudaMalloc(&B.seg[h], std::max<size_t>(n, 1) * 4));
+  {  // one device allocation for everything (cudaMalloc / cudaFree cost more than the kernels of a small scene)
+    const size_t elems = std::max<size_t>(n, 1);
+    size_t total = 0;
+    auto reserve = [&](size_t bytes) { const size_t at = total; total += (bytes + 255) & ~size_t(255); return at; };
+    const size_t oBoxes = reserve(elems * 32), oOrder = reserve(elems * 4), oKey0 = reserve(elems * 4), oKey1 = reserve(elems * 4),
+                 oIdx0 = reserve(elems * 4), oIdx1 = reserve(elems * 4), oSeg0 = reserve(elems * 4), oSeg1 = reserve(elems * 4),
+                 oSegStatic = reserve(elems * 4), oAreaLeft = reserve(elems * 4), oAreaRight = reserve(elems * 4),
+                 oHist = reserve((size_t)16 * maxTiles * 4), oTotals = reserve(16 * 4), oSegs = reserve((size_t)maxSegs * sizeof(SahSeg)),
+                 oSegChunk0 = reserve(((size_t)maxSegs + 1) * 4), oBest = reserve((size_t)maxSegs * 8),
+                 oChunks = reserve((size_t)maxChunks * sizeof(SahChunk)), oChunkBox = reserve((size_t)maxChunks * sizeof(SahBox)),
+                 oBefore = reserve((size_t)maxChunks * sizeof(SahBox)), oAfter = reserve((size_t)maxChunks * sizeof(SahBox));
+    ORZ_CUDA(cudaMalloc(&B.arena, total));
+    char* base = B.arena;
+    B.boxes = reinterpret_cast<float4*>(base + oBoxes);
+    B.order = reinterpret_cast<uint32_t*>(base + oOrder);
+    B.key[0] = reinterpret_cast<uint32_t*>(base + oKey0); B.key[1] = reinterpret_cast<uint32_t*>(base + oKey1);
+    B.idx[0] = reinterpret_cast<uint32_t*>(base + oIdx0); B.idx[1] = reinterpret_cast<uint32_t*>(base + oIdx1);
+    B.seg[0] = reinterpret_cast<uint32_t*>(base + oSeg0); B.seg[1] = reinterpret_cast<uint32_t*>(base + oSeg1);
+    B.segStatic = reinterpret_cast<uint32_t*>(base + oSegStatic);
+    B.areaLeft = reinterpret_cast<float*>(base + oAreaLeft); B.areaRight = reinterpret_cast<float*>(base + oAreaRight);
+    B.hist = reinterpret_cast<uint32_t*>(base + oHist); B.digitTotals = reinterpret_cast<uint32_t*>(base + oTotals);
+    B.segs = reinterpret_cast<SahSeg*>(base + oSegs); B.segChunk0 = reinterpret_cast<uint32_t*>(base + oSegChunk0);
+    B.best = reinterpret_cast<unsigned long long*>(base + oBest);
+    B.chunks = reinterpret_cast<SahChunk*>(base + oChunks); B.chunkBox = reinterpret_cast<SahBox*>(base + oChunkBox);
+    B.before = reinterpret_cast<SahBox*>(base + oBefore); B.after = reinterpret_cast<SahBox*>(base + oAfter);
   }
-  ORZ_CUDA(cudaMalloc(&B.segStatic, std::max<size_t>(n, 1) * 4));
-  ORZ_CUDA(cudaMalloc(&B.areaLeft, std::max<size_t>(n, 1) * 4));
-  ORZ_CUDA(cudaMalloc(&B.areaRight, std::max<size_t>(n, 1) * 4));
-  ORZ_CUDA(cudaMalloc(&B.hist, (size_t)16 * maxTiles * 4));
-  ORZ_CUDA(cudaMalloc(&B.digitTotals, 16 * 4));
-  ORZ_CUDA(cudaMalloc(&B.segs, (size_t)maxSegs * sizeof(SahSeg)));
-  ORZ_CUDA(cudaMalloc(&B.segChunk0, ((size_t)maxSegs + 1) * 4));
-  ORZ_CUDA(cudaMalloc(&B.best, (size_t)maxSegs * 8));
-  ORZ_CUDA(cudaMalloc(&B.chunks, (size_t)maxChunks * sizeof(SahChunk)));
-  ORZ_CUDA(cudaMalloc(&B.chunkBox, (size_t)maxChunks * sizeof(SahBox)));
-  ORZ_CUDA(cudaMalloc(&B.before, (size_t)maxChunks * sizeof(SahBox)));
-  ORZ_CUDA(cudaMalloc(&B.after, (size_t)maxChunks * sizeof(SahBox)));
   ORZ_CUDA(cudaMemcpyAsync(B.boxes, aabbs, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream));
   {
     std::vector<uint32_t> iota(n);

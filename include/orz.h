@@ -137,6 +137,14 @@ typedef struct {
 int orz_scene_from_mesh(orz_context* ctx, const uint32_t* indices, size_t nIndices, const float* vertices, size_t nVertices,
                         uint32_t targetSize, uint32_t splitGranularity, int occludeesFromQuads, orz_scene** out,
                         orz_mesh_scene_info* info /* may be NULL */);
+uint32_t orz_scene_occludee_count(orz_scene* scene); /* boxes installed by orz_scene_set_occludees / from_mesh / load */
+/* The same from the reference's raw scene files (Main.cpp:56-84: uint32 triangle indices, float4 vertices). */
+int orz_scene_from_mesh_files(orz_context* ctx, const char* indexPath, const char* vertexPath, uint32_t targetSize,
+                              uint32_t splitGranularity, int occludeesFromQuads, orz_scene** out, orz_mesh_scene_info* info);
+/* Cached baked scene: the scene's HBM layout -- occluder meta, one 16-byte record per quad,
+ * occludee boxes -- written to / read from one file; loading is three copies, no preparation and no bake. */
+int orz_scene_save(orz_scene* scene, const char* path);
+int orz_scene_load(orz_context* ctx, const char* path, orz_scene** out);
 /* What the application reads from its occluders (Occluder.h:11-20; Main.cpp:186-195 sorts by m_center and gates with
  * the bounds): nOccluders x 4 floats each, quadCounts: nOccluders words.  Any output may be NULL. */
 int orz_scene_get_occluders(orz_scene* scene, uint32_t* nOccluders, float* centers, float* boundsMin, float* boundsMax,

@@ -48,6 +48,10 @@ class ViewBatch(C.Structure):
 
 
 EXPORTS = {
+    "orz_scene_occludee_count": (C.c_uint32, [C.c_void_p]),
+    "orz_scene_from_mesh_files": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]),
+    "orz_scene_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "orz_scene_load": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
     "orz_scene_from_mesh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int,
                                       C.POINTER(C.c_void_p), C.c_void_p]),
     "orz_scene_get_occluders": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -419,6 +423,41 @@ class Scene:
         self.packed_list = None  # the baked words exist in HBM only
         self.n_boxes = self.n_quads if occludees_from_quads else 0
         return self
+
+    def _adopt(self, ctx, h):
+        """Fill the host-side fields of a scene that was created inside the library."""
+        self.ctx, self.h = ctx, h
+        n = C.c_uint32()
+        _check(lib().orz_scene_get_occluders(h, C.byref(n), None, None, None, None))
+        n = self.n_occluders = int(n.value)
+        self.centers, self.bounds_min, self.bounds_max = (np.zeros((n, 4), np.float32) for _ in range(3))
+        counts = np.zeros(n, np.uint32)
+        _check(lib().orz_scene_get_occluders(h, None, _p(self.centers), _p(self.bounds_min), _p(self.bounds_max), _p(counts)))
+        self.quads_per_occluder = counts
+        self.n_quads = int(counts.sum())
+        self.packed_list = None  # the baked words exist in HBM only
+        self.n_boxes = int(lib().orz_scene_occludee_count(h))
+        return self
+
+    @classmethod
+    def from_mesh_files(cls, ctx: Context, index_path: str, vertex_path: str, target_size: int = 512, split_granularity: int = 8,
+                        occludees_from_quads: bool = True) -> "Scene":
+        """The reference's raw scene files (Main.cpp:56-84) -> baked scene in HBM (orz_scene_from_mesh_files)."""
+        h = C.c_void_p()
+        _check(lib().orz_scene_from_mesh_files(ctx.h, index_path.encode(), vertex_path.encode(), target_size, split_granularity,
+                                               int(occludees_from_quads), C.byref(h), None))
+        return cls.__new__(cls)._adopt(ctx, h)
+
+    def save(self, path: str):
+        """Cached baked scene file (orz_scene_save)."""
+        _check(lib().orz_scene_save(self.h, path.encode()))
+
+    @classmethod
+    def load(cls, ctx: Context, path: str) -> "Scene":
+        """orz_scene_load: a file written by `save`, straight to HBM."""
+        h = C.c_void_p()
+        _check(lib().orz_scene_load(ctx.h, path.encode(), C.byref(h)))
+        return cls.__new__(cls)._adopt(ctx, h)
 
     def set_occludees(self, boxes):
         b = _f32(boxes).reshape(-1, 8)

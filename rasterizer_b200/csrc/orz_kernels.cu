@@ -527,6 +527,96 @@ extern "C" int orz_scene_get_occluders(orz_scene* s, uint32_t* nOccluders, float
   }
   return ORZ_OK;
 }
+extern "C" uint32_t orz_scene_occludee_count(orz_scene* s) { return s ? s->nBoxes : 0; }
+// ---- cached baked scene: the HBM layout written to / read from a file -----------
+namespace {
+struct SceneFileHeader {
+  char magic[8];  // "ORZBAKE1"
+  uint32_t nOcc, totalQuads, nBoxes, metaBytes;
+};
+}  // namespace
+extern "C" int orz_scene_save(orz_scene* s, const char* path) {
+  if (!s || !path) return fail(ORZ_ERR_ARG, "orz_scene_save: bad arguments");
+  ORZ_CUDA(cudaSetDevice(s->ctx->device));
+  std::vector<OccMeta> meta(s->nOcc);
+  std::vector<uint4> quads(s->totalQuads);
+  std::vector<float4> boxes((size_t)s->nBoxes * 2);
+  ORZ_CUDA(cudaMemcpyAsync(meta.data(), s->d_occ, meta.size() * sizeof(OccMeta), cudaMemcpyDeviceToHost, s->ctx->stream));
+  if (!quads.empty()) ORZ_CUDA(cudaMemcpyAsync(quads.data(), s->d_quads, quads.size() * sizeof(uint4), cudaMemcpyDeviceToHost, s->ctx->stream));
+  if (!boxes.empty()) ORZ_CUDA(cudaMemcpyAsync(boxes.data(), s->d_boxes, boxes.size() * sizeof(float4), cudaMemcpyDeviceToHost, s->ctx->stream));
+  ORZ_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(ORZ_ERR_ARG, std::string("orz_scene_save: cannot open ") + path);
+  SceneFileHeader h{{'O', 'R', 'Z', 'B', 'A', 'K', 'E', '1'}, s->nOcc, s->totalQuads, s->nBoxes, (uint32_t)sizeof(OccMeta)};
+  bool ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(meta.data(), sizeof(OccMeta), meta.size(), f) == meta.size() &&
+            fwrite(quads.data(), sizeof(uint4), quads.size(), f) == quads.size() &&
+            fwrite(boxes.data(), sizeof(float4), boxes.size(), f) == boxes.size();
+  ok = (fclose(f) == 0) && ok;
+  return ok ? ORZ_OK : fail(ORZ_ERR_ARG, std::string("orz_scene_save: short write to ") + path);
+}
+extern "C" int orz_scene_load(orz_context* ctx, const char* path, orz_scene** out) {
+  if (!ctx || !path || !out) return fail(ORZ_ERR_ARG, "orz_scene_load: bad arguments");
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(ORZ_ERR_ARG, std::string("orz_scene_load: cannot open ") + path);
+  SceneFileHeader h;
+  std::vector<OccMeta> meta;
+  std::vector<uint4> quads;
+  std::vector<float4> boxes;
+  bool ok = fread(&h, sizeof h, 1, f) == 1 && memcmp(h.magic, "ORZBAKE1", 8) == 0 && h.metaBytes == sizeof(OccMeta) && h.nOcc > 0;
+  if (ok) {
+    fseek(f, 0, SEEK_END);
+    const long size = ftell(f);
+    const uint64_t want = sizeof h + (uint64_t)h.nOcc * sizeof(OccMeta) + (uint64_t)h.totalQuads * sizeof(uint4) + (uint64_t)h.nBoxes * 2 * sizeof(float4);
+    ok = size >= 0 && (uint64_t)size == want;  // sizes in the header must describe exactly this file
+    fseek(f, sizeof h, SEEK_SET);
+  }
+  if (ok) {
+    meta.resize(h.nOcc); quads.resize(h.totalQuads); boxes.resize((size_t)h.nBoxes * 2);
+    ok = fread(meta.data(), sizeof(OccMeta), meta.size(), f) == meta.size() && fread(quads.data(), sizeof(uint4), quads.size(), f) == quads.size() &&
+         fread(boxes.data(), sizeof(float4), boxes.size(), f) == boxes.size();
+  }
+  fclose(f);
+  for (size_t i = 0; ok && i < meta.size(); ++i)  // every batch must lie inside the quad array
+    ok = (uint64_t)meta[i].quadOffset + meta[i].quadCount <= h.totalQuads;
+  if (!ok) return fail(ORZ_ERR_ARG, std::string("orz_scene_load: not a baked scene file (or truncated): ") + path);
+  ORZ_CUDA(cudaSetDevice(ctx->device));
+  orz_scene* s = new orz_scene();
+  s->ctx = ctx; s->nOcc = h.nOcc; s->totalQuads = h.totalQuads; s->nBoxes = h.nBoxes;
+  cudaError_t e = cudaMalloc(&s->d_quads, std::max<size_t>(quads.size(), 1) * sizeof(uint4));
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_occ, meta.size() * sizeof(OccMeta));
+  if (e == cudaSuccess && h.nBoxes) e = cudaMalloc(&s->d_boxes, boxes.size() * sizeof(float4));
+  if (e == cudaSuccess && !quads.empty()) e = cudaMemcpy(s->d_quads, quads.data(), quads.size() * sizeof(uint4), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(s->d_occ, meta.data(), meta.size() * sizeof(OccMeta), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && h.nBoxes) e = cudaMemcpy(s->d_boxes, boxes.data(), boxes.size() * sizeof(float4), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(s->d_quads); cudaFree(s->d_occ); cudaFree(s->d_boxes);
+    delete s;
+    return fail(ORZ_ERR_CUDA, std::string("orz_scene_load: ") + cudaGetErrorString(e));
+  }
+  *out = s;
+  return ORZ_OK;
+}
+// Main.cpp:56-84 + 86-128: the reference's raw scene files (uint32 triangle indices, float4 vertices) -> baked scene in HBM
+extern "C" int orz_scene_from_mesh_files(orz_context* ctx, const char* indexPath, const char* vertexPath, uint32_t targetSize,
+                                         uint32_t splitGranularity, int occludeesFromQuads, orz_scene** out, orz_mesh_scene_info* info) {
+  if (!ctx || !indexPath || !vertexPath || !out) return fail(ORZ_ERR_ARG, "orz_scene_from_mesh_files: bad arguments");
+  auto slurp = [](const char* path, std::vector<char>& data) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    const long size = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    data.resize(size > 0 ? (size_t)size : 0);
+    const bool ok = fread(data.data(), 1, data.size(), f) == data.size();
+    fclose(f);
+    return ok;
+  };
+  std::vector<char> idx, vtx;
+  if (!slurp(indexPath, idx)) return fail(ORZ_ERR_ARG, std::string("orz_scene_from_mesh_files: cannot read ") + indexPath);
+  if (!slurp(vertexPath, vtx)) return fail(ORZ_ERR_ARG, std::string("orz_scene_from_mesh_files: cannot read ") + vertexPath);
+  return orz_scene_from_mesh(ctx, reinterpret_cast<const uint32_t*>(idx.data()), idx.size() / 4, reinterpret_cast<const float*>(vtx.data()),
+                             vtx.size() / 16, targetSize, splitGranularity, occludeesFromQuads, out, info);
+}
 extern "C" void orz_scene_destroy(orz_scene* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);

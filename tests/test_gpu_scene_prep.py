@@ -107,3 +107,36 @@ def test_scene_from_mesh_in_one_call(ctx):
         got.close(); want.close()
     with pytest.raises(api.OrzError, match="multiple of 8"):
         api.Scene.from_mesh(ctx, cases[0][1], cases[0][2], 512, 4)
+
+
+def test_baked_scene_file_and_mesh_files(ctx, tmp_path):
+    """orz_scene_save / orz_scene_load (the HBM layout as a file) and orz_scene_from_mesh_files (the reference's raw
+    index / vertex files, Main.cpp:56-84): every way into HBM renders the same frame."""
+    from rasterizer_b200 import camera as cam
+
+    api.set_rsqrt_table(None)
+    idx, verts = terrain(np.random.default_rng(3), 5000, 2.5)
+    idx.astype(np.uint32).tofile(tmp_path / "IndexBuffer.bin")
+    verts.astype(np.float32).tofile(tmp_path / "VertexBuffer.bin")
+    first = api.Scene.from_mesh(ctx, idx, verts, 256, 8)
+    first.save(str(tmp_path / "terrain.orzbake"))
+    scenes = [first, api.Scene.load(ctx, str(tmp_path / "terrain.orzbake")),
+              api.Scene.from_mesh_files(ctx, str(tmp_path / "IndexBuffer.bin"), str(tmp_path / "VertexBuffer.bin"), 256, 8)]
+    w, h = 512, 256
+    pos = np.array([18.0, 12.0, -8.0], np.float32)
+    mvp = cam.view_projection(pos, np.array([0.1, -0.35, 0.9], np.float32), np.array([0.0, 1.0, 0.0], np.float32), 0.9, w, h)
+    outs = [s.render_views(w, h, mvp[None], cam_pos=pos[None], want=("vis", "gate", "hiz", "quads")) for s in scenes]
+    for s, o in zip(scenes[1:], outs[1:]):
+        assert s.n_occluders == first.n_occluders and s.n_boxes == first.n_boxes == first.n_quads
+        assert np.array_equal(s.centers.view(np.uint32), first.centers.view(np.uint32))
+        for key in ("vis", "gate", "hiz", "depth", "quads"):
+            assert np.array_equal(o[key], outs[0][key]), key
+    assert outs[0]["quads"][0] > 0
+    bad = tmp_path / "bad.orzbake"
+    bad.write_bytes((tmp_path / "terrain.orzbake").read_bytes()[:-16])
+    with pytest.raises(api.OrzError, match="truncated"):
+        api.Scene.load(ctx, str(bad))
+    with pytest.raises(api.OrzError, match="cannot read"):
+        api.Scene.from_mesh_files(ctx, str(tmp_path / "nope.bin"), str(tmp_path / "VertexBuffer.bin"))
+    for s in scenes:
+        s.close()

@@ -284,9 +284,15 @@ class Matcher {
 // SAH batching
 
 struct KeyIdx {
-  float key;
+  uint32_t key;  // the centre as an order-preserving integer, -0 == +0 (the same key the device batching sorts by)
   uint32_t idx;
 };
+inline uint32_t order_key(float c) {
+  uint32_t u;
+  memcpy(&u, &c, 4);
+  if ((u & 0x7fffffffu) == 0) u = 0;
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 
 struct SahInput {
   const float* boxes;  // n x (min4, max4)
@@ -313,12 +319,31 @@ struct Box3 {
   }
 };
 
+// Stable sort of a node's range by the centre on one axis: least-significant-digit radix sort over 11 + 11 + 10
+// bits (a pass whose digit is the same for every element is skipped); ties keep the order the previous sort left,
+// exactly what std::stable_sort with a `<` comparator does in the reference (SurfaceAreaHeuristic.cpp:22-24).
 void sort_by_axis(const SahInput& in, int axis, uint32_t* first, uint32_t n, std::vector<KeyIdx>& tmp) {
-  tmp.resize(n);
+  tmp.resize(2 * size_t(n));
+  KeyIdx *src = tmp.data(), *dst = tmp.data() + n;
   const float* c = in.center[axis].data();
-  for (uint32_t i = 0; i < n; ++i) tmp[i] = {c[first[i]], first[i]};
-  std::stable_sort(tmp.begin(), tmp.end(), [](const KeyIdx& a, const KeyIdx& b) { return a.key < b.key; });
-  for (uint32_t i = 0; i < n; ++i) first[i] = tmp[i].idx;
+  for (uint32_t i = 0; i < n; ++i) src[i] = {order_key(c[first[i]]), first[i]};
+  static const int kShift[3] = {0, 11, 22}, kBits[3] = {11, 11, 10};
+  uint32_t count[2048];
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t mask = (1u << kBits[pass]) - 1u, shift = uint32_t(kShift[pass]);
+    memset(count, 0, sizeof(uint32_t) << kBits[pass]);
+    for (uint32_t i = 0; i < n; ++i) ++count[(src[i].key >> shift) & mask];
+    if (count[(src[0].key >> shift) & mask] == n) continue;
+    uint32_t run = 0;
+    for (uint32_t d = 0; d <= mask; ++d) {
+      const uint32_t here = count[d];
+      count[d] = run;
+      run += here;
+    }
+    for (uint32_t i = 0; i < n; ++i) dst[count[(src[i].key >> shift) & mask]++] = src[i];
+    std::swap(src, dst);
+  }
+  for (uint32_t i = 0; i < n; ++i) first[i] = src[i].idx;
 }
 
 // sahSplit, SurfaceAreaHeuristic.cpp:10-75.  Returns the split position, 0 when no candidate has a

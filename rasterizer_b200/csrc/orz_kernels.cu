@@ -73,6 +73,16 @@ int orz::set_error(int code, const std::string& msg) { return fail(code, msg); }
     if (_e != cudaSuccess) return fail(ORZ_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e)); \
   } while (0)
 
+// same, for code that owns a half-built object: run `cleanup` before returning the error
+#define ORZ_CUDA_OR(cleanup, x)                                                \
+  do {                                                                         \
+    cudaError_t _e = (x);                                                      \
+    if (_e != cudaSuccess) {                                                   \
+      cleanup;                                                                 \
+      return fail(ORZ_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e)); \
+    }                                                                          \
+  } while (0)
+
 struct orz_context {
   int device = 0;
   int numSMs = 0;
@@ -140,35 +150,38 @@ extern "C" int orz_context_create(int device, orz_context** out) {
   orz_context* ctx = new orz_context();
   ctx->device = device;
   cudaDeviceProp prop;
-  ORZ_CUDA(cudaGetDeviceProperties(&prop, device));
+  ORZ_CUDA_OR(orz_context_destroy(ctx), cudaGetDeviceProperties(&prop, device));
   ctx->numSMs = prop.multiProcessorCount;
   ctx->arenaBudget = std::min<size_t>(size_t(24) << 30, prop.totalGlobalMem / 6);
-  ORZ_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  ORZ_CUDA(cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
+  ORZ_CUDA_OR(orz_context_destroy(ctx), cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ORZ_CUDA_OR(orz_context_destroy(ctx), cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
   for (int g = 0; g < orz_context::kGroups; ++g) {
-    ORZ_CUDA(cudaStreamCreateWithFlags(&ctx->aux[g], cudaStreamNonBlocking));
-    ORZ_CUDA(cudaEventCreateWithFlags(&ctx->evJoin[g], cudaEventDisableTiming));
+    ORZ_CUDA_OR(orz_context_destroy(ctx), cudaStreamCreateWithFlags(&ctx->aux[g], cudaStreamNonBlocking));
+    ORZ_CUDA_OR(orz_context_destroy(ctx), cudaEventCreateWithFlags(&ctx->evJoin[g], cudaEventDisableTiming));
   }
-  ORZ_CUDA(cudaMalloc(&ctx->d_lut, 4096 * sizeof(uint2)));
-  ORZ_CUDA(cudaMemcpy(ctx->d_lut, edge_mask_table(), 4096 * sizeof(uint2), cudaMemcpyHostToDevice));
+  ORZ_CUDA_OR(orz_context_destroy(ctx), cudaMalloc(&ctx->d_lut, 4096 * sizeof(uint2)));
+  ORZ_CUDA_OR(orz_context_destroy(ctx), cudaMemcpy(ctx->d_lut, edge_mask_table(), 4096 * sizeof(uint2), cudaMemcpyHostToDevice));
   probe_host_rcp(ctx->h_rcp, ctx->rcpBits, ctx->rcpExact);
-  ORZ_CUDA(cudaMalloc(&ctx->d_rcp, ctx->h_rcp.size() * 4));
-  ORZ_CUDA(cudaMemcpy(ctx->d_rcp, ctx->h_rcp.data(), ctx->h_rcp.size() * 4, cudaMemcpyHostToDevice));
-  ORZ_CUDA(cudaMalloc(&ctx->d_counter, 64));
-  ORZ_CUDA(cudaHostAlloc(&ctx->h_pinned, 64, cudaHostAllocDefault));
+  ORZ_CUDA_OR(orz_context_destroy(ctx), cudaMalloc(&ctx->d_rcp, ctx->h_rcp.size() * 4));
+  ORZ_CUDA_OR(orz_context_destroy(ctx), cudaMemcpy(ctx->d_rcp, ctx->h_rcp.data(), ctx->h_rcp.size() * 4, cudaMemcpyHostToDevice));
+  ORZ_CUDA_OR(orz_context_destroy(ctx), cudaMalloc(&ctx->d_counter, 64));
+  ORZ_CUDA_OR(orz_context_destroy(ctx), cudaHostAlloc(&ctx->h_pinned, 64, cudaHostAllocDefault));
   *out = ctx;
   return ORZ_OK;
 }
 extern "C" void orz_context_destroy(orz_context* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto& p : ctx->d_scratch) if (p) cudaFree(p);
   cudaFree(ctx->d_lut); cudaFree(ctx->d_rcp); cudaFree(ctx->d_counter);
-  cudaFreeHost(ctx->h_pinned);
-  for (int g = 0; g < orz_context::kGroups; ++g) { cudaStreamSynchronize(ctx->aux[g]); cudaStreamDestroy(ctx->aux[g]); cudaEventDestroy(ctx->evJoin[g]); }
-  cudaEventDestroy(ctx->evFork);
-  cudaStreamDestroy(ctx->stream);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  for (int g = 0; g < orz_context::kGroups; ++g) {  // a context that failed half-way through creation has null handles
+    if (ctx->aux[g]) { cudaStreamSynchronize(ctx->aux[g]); cudaStreamDestroy(ctx->aux[g]); }
+    if (ctx->evJoin[g]) cudaEventDestroy(ctx->evJoin[g]);
+  }
+  if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 extern "C" int orz_context_synchronize(orz_context* ctx) {
@@ -248,8 +261,8 @@ extern "C" int orz_occluder_create(orz_context* ctx, const uint32_t* packets, ui
   relayout_packets(packets, packetCount, tmp.data());
   o->d_quads = nullptr;
   if (o->nQuads) {
-    ORZ_CUDA(cudaMalloc(&o->d_quads, tmp.size() * sizeof(uint4)));
-    ORZ_CUDA(cudaMemcpy(o->d_quads, tmp.data(), tmp.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    ORZ_CUDA_OR(orz_occluder_destroy(o), cudaMalloc(&o->d_quads, tmp.size() * sizeof(uint4)));
+    ORZ_CUDA_OR(orz_occluder_destroy(o), cudaMemcpy(o->d_quads, tmp.data(), tmp.size() * sizeof(uint4), cudaMemcpyHostToDevice));
   }
   *out = o;
   return ORZ_OK;
@@ -270,10 +283,11 @@ extern "C" int orz_rasterizer_create(orz_context* ctx, uint32_t width, uint32_t 
   r->ctx = ctx;
   r->T.width = width; r->T.height = height; r->T.blocksX = width / 8; r->T.blocksY = height / 8;
   const size_t blocks = (size_t)r->T.blocksX * r->T.blocksY;
-  ORZ_CUDA(cudaMalloc(&r->T.depth, blocks * 128));
-  ORZ_CUDA(cudaMalloc(&r->T.hiz, (blocks + 8) * 2));
-  ORZ_CUDA(cudaMemsetAsync(r->T.depth, 0, blocks * 128, ctx->stream));
-  ORZ_CUDA(cudaMemsetAsync(r->T.hiz, 0, (blocks + 8) * 2, ctx->stream));  // Rasterizer.cpp:71: HiZ starts at 0 until clear()
+  r->T.depth = nullptr; r->T.hiz = nullptr;
+  ORZ_CUDA_OR(orz_rasterizer_destroy(r), cudaMalloc(&r->T.depth, blocks * 128));
+  ORZ_CUDA_OR(orz_rasterizer_destroy(r), cudaMalloc(&r->T.hiz, (blocks + 8) * 2));
+  ORZ_CUDA_OR(orz_rasterizer_destroy(r), cudaMemsetAsync(r->T.depth, 0, blocks * 128, ctx->stream));
+  ORZ_CUDA_OR(orz_rasterizer_destroy(r), cudaMemsetAsync(r->T.hiz, 0, (blocks + 8) * 2, ctx->stream));  // Rasterizer.cpp:71: HiZ starts at 0 until clear()
   memset(&r->vm, 0, sizeof r->vm);
   *out = r;
   return ORZ_OK;
@@ -427,10 +441,10 @@ extern "C" int orz_scene_create(orz_context* ctx, const uint32_t* packets, const
     relayout_packets(packets + pofs * 8, packetCounts[i], quads.data() + meta[i].quadOffset);
     pofs += packetCounts[i];
   }
-  ORZ_CUDA(cudaMalloc(&s->d_quads, std::max<size_t>(quads.size(), 1) * sizeof(uint4)));
-  ORZ_CUDA(cudaMemcpy(s->d_quads, quads.data(), quads.size() * sizeof(uint4), cudaMemcpyHostToDevice));
-  ORZ_CUDA(cudaMalloc(&s->d_occ, meta.size() * sizeof(OccMeta)));
-  ORZ_CUDA(cudaMemcpy(s->d_occ, meta.data(), meta.size() * sizeof(OccMeta), cudaMemcpyHostToDevice));
+  ORZ_CUDA_OR(orz_scene_destroy(s), cudaMalloc(&s->d_quads, std::max<size_t>(quads.size(), 1) * sizeof(uint4)));
+  ORZ_CUDA_OR(orz_scene_destroy(s), cudaMemcpy(s->d_quads, quads.data(), quads.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+  ORZ_CUDA_OR(orz_scene_destroy(s), cudaMalloc(&s->d_occ, meta.size() * sizeof(OccMeta)));
+  ORZ_CUDA_OR(orz_scene_destroy(s), cudaMemcpy(s->d_occ, meta.data(), meta.size() * sizeof(OccMeta), cudaMemcpyHostToDevice));
   *out = s;
   return ORZ_OK;
 }

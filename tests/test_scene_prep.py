@@ -174,3 +174,37 @@ def test_device_batching_source_emulated_on_the_cpu(seed, n, target, gran, snap)
             totals, sums = np.zeros(16, np.uint32), d.sum(axis=1, dtype=np.uint32)
             L.emu_scan(d.ctypes.data_as(C.c_void_p), tiles, totals.ctypes.data_as(C.c_void_p))
             assert np.array_equal(d, want) and np.array_equal(totals, sums)
+
+
+def test_quad_decompose_random_non_manifold_soups():
+    """Hundreds of small random triangle soups over a handful of vertices: every directed edge has many owners,
+    the candidate graph is dense and non-planar, augmenting paths run through nested blossoms.  Faces are
+    non-degenerate (a triangle that is its own neighbour makes the reference loop forever)."""
+    rng = np.random.default_rng(1234)
+    worst = 0
+    for case in range(400):
+        nv = int(rng.integers(4, 14))
+        nt = int(rng.integers(1, 40))
+        verts = np.zeros((nv, 4), np.float32)
+        verts[:, :2] = rng.integers(0, 6, (nv, 2))
+        verts[:, 2] = rng.choice([0.0, 0.0, 0.0, 0.3, 2.0], nv)      # mostly coplanar: most pairs may merge
+        verts[:, 3] = 1.0
+        tris = np.stack([rng.permutation(nv)[:3] for _ in range(nt)]).astype(np.uint32)
+        got, want = api.quad_decompose(tris.reshape(-1), verts), ro.quad_decompose(tris.reshape(-1), verts)
+        assert np.array_equal(got, want), (case, tris.tolist())
+        q = got.reshape(-1, 4)
+        worst = max(worst, int(np.sum(q[:, 0] != q[:, 3])))
+    assert worst >= 10  # the soups do produce many pairs
+
+
+def test_generate_batches_random_small_cases():
+    """Random sizes / targets / granularities over coarse grids of centres (ties everywhere); only shapes the
+    reference itself can split (every node it recurses into has more than two granules)."""
+    rng = np.random.default_rng(4321)
+    for case in range(150):
+        gran = int(rng.choice([1, 2, 3, 8, 16]))
+        target = int(rng.integers(2 * gran + 1, 2 * gran + 200))
+        n = int(rng.integers(2 * gran + 1, 1500))
+        boxes = boxes_case(rng, n, float(rng.choice([1.0, 4.0, 25.0, 100.0])))
+        got, want = api.generate_batches(boxes, target, gran), ro.generate_batches(boxes, target, gran)
+        assert same_batches(got, want), (case, n, target, gran)

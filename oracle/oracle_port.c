@@ -359,6 +359,17 @@ void orc_setup_quad(const OrcRasterizer* r, const uint32_t word[4], const float*
 }
 
 /* ---------------------------------------------------------------- block traversal, Rasterizer.cpp:1098-1292 */
+/* Optional work statistics of the block loop (tools/lane_model.py, planning only): block visits, visits the
+   reference's own HiZ test rejects, depth + HiZ updates, updates that leave every pixel unchanged, and updates a
+   per-block bound could have skipped exactly: the largest of the four corner samples (rows 0 / 9, pixels 0 / 7)
+   bounds every generated pixel -- all steps from the samples to the pixels are monotone, avg16 never exceeds its
+   larger operand -- so when it is <= the block's HiZ (the smallest stored pixel) the max-merge changes nothing. */
+static uint64_t g_stats[5];
+void orc_stats(uint64_t* out5, int reset) {
+  if (out5) memcpy(out5, g_stats, sizeof g_stats);
+  if (reset) memset(g_stats, 0, sizeof g_stats);
+}
+
 static void traverse(OrcRasterizer* r, const OrcPrim* P, int clipped) {
   const uint32_t blocksX = r->blocksX;
   /* _mm256_mullo_epi16 at :1054: the row offset wraps mod 65536 */
@@ -376,6 +387,8 @@ static void traverse(OrcRasterizer* r, const OrcPrim* P, int clipped) {
     for (int32_t bx = 0; bx < P->rangeX; ++bx) {
       size_t b = (size_t)firstBlock + (size_t)by * blocksX + (size_t)bx;
       uint32_t h = r->hiz[b];
+      ++g_stats[0];
+      if (!(h < P->maxZ)) ++g_stats[1];
       if (h < P->maxZ) {                                   /* :1148-1152 */
         uint64_t mask;
         int update;                                        /* does this visit write depth + HiZ? */
@@ -423,15 +436,26 @@ static void traverse(OrcRasterizer* r, const OrcPrim* P, int clipped) {
           }
           uint16_t* D = r->depth + 64 * b;
           uint32_t mn = 0xffffu;
+          int changed = 0;
+          {
+            uint32_t c0 = row[0][0], c1 = row[0][7], c2 = row[9][0], c3 = row[9][7];
+            uint32_t bound = c0 > c1 ? c0 : c1;
+            if (c2 > bound) bound = c2;
+            if (c3 > bound) bound = c3;
+            ++g_stats[2];
+            if (h != 1 && bound <= h) ++g_stats[4];
+          }
           for (int yy = 0; yy < 8; ++yy)
             for (int px = 0; px < 8; ++px) {
               uint32_t bit = 8u * (uint32_t)px + ((yy & 1) ? 0u : 4u) + ((uint32_t)yy >> 1); /* :1257-1268 */
               uint32_t v = ((mask >> bit) & 1) ? row[yy][px] : 0u;
               if (h != 1) { uint32_t old = D[8 * yy + px]; if (old > v) v = old; } /* :1271-1278 */
+              if (h == 1 || D[8 * yy + px] != (uint16_t)v) changed = 1;
               D[8 * yy + px] = (uint16_t)v;
               if (v < mn) mn = v;
             }
           r->hiz[b] = (uint16_t)mn;                        /* :1287-1290 */
+          if (!changed) ++g_stats[3];
         }
       }
       for (int l = 0; l < 8; ++l) d[l] = P->dzdx + d[l];   /* :1145-1146, every block, hit or not */

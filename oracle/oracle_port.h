@@ -63,6 +63,9 @@ typedef struct {
   float nx[4], ny[4], off[4];
   uint32_t slope[4];        /* already << 6 */
 } OrcPrim;
+/* planning statistics of the block loop: visits, HiZ-rejected, updates, updates without any change, updates a
+   per-block corner bound would have skipped; reset != 0 clears them */
+void orc_stats(uint64_t* out5, int reset);
 void orc_setup_quad(const OrcRasterizer* r, const uint32_t word[4], const float* refMin4, const float* refMax4,
                     int possiblyNearClipped, OrcPrim* out);
 

@@ -50,7 +50,8 @@ def main():
     maps = {"t mod 32 (today)": t_all % 32, "(tx + 5 ty) mod 32": (tx_all + 5 * ty_all) % 32, "(3 tx + 7 ty) mod 32": (3 * tx_all + 7 * ty_all) % 32,
             "(tx + 8 ty) mod 32": (tx_all + 8 * ty_all) % 32,
             "random": rng.permutation(t_all.size) % 32}
-    for k in list(maps) + ["greedy by true cost", "greedy by speculative cost (all occluders in the frustum)"]:
+    for k in list(maps) + ["greedy by true cost", "greedy by speculative cost (all occluders in the frustum)",
+                           "snake deal by speculative cost", "snake deal by true cost"]:
         patterns[k] = []
     empty = po.PortRasterizer(w, h)  # never drawn into: its gate answers "in the frustum" only
     for v in pick:
@@ -125,6 +126,12 @@ def main():
             true_bins[b] += tile_work[t]
             fill[b] += 1
         patterns["greedy by speculative cost (all occluders in the frustum)"].append(float(true_bins.max() / max(true_bins.mean(), 1e-9)))
+        for label, costs in (("snake deal by speculative cost", tile_guess), ("snake deal by true cost", tile_work)):
+            rank = np.argsort(-costs, kind="stable")      # tiles by falling cost, dealt 0..31, 31..0, 0..31, ...
+            pos = np.arange(rank.size)
+            warp_of = np.where((pos // 32) % 2 == 0, pos % 32, 31 - pos % 32)
+            per_warp = np.bincount(warp_of, weights=tile_work[rank], minlength=32)
+            patterns[label].append(float(per_warp.max() / max(per_warp.mean(), 1e-9)))
         for c in imbalance:
             warps = 16 * c
             per_warp = np.bincount(np.arange(tile_work.size) % warps, weights=tile_work, minlength=warps)

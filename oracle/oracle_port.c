@@ -365,6 +365,10 @@ void orc_setup_quad(const OrcRasterizer* r, const uint32_t word[4], const float*
    bounds every generated pixel -- all steps from the samples to the pixels are monotone, avg16 never exceeds its
    larger operand -- so when it is <= the block's HiZ (the smallest stored pixel) the max-merge changes nothing. */
 static uint64_t g_stats[5];
+static int g_block_bound_skip = 0;
+/* Planning switch: skip the updates the corner bound proves to be no-ops.  The results must not
+   change -- tests/test_oracle_port.py runs the port with the switch on against the unmodified reference. */
+void orc_set_block_bound_skip(int on) { g_block_bound_skip = on; }
 void orc_stats(uint64_t* out5, int reset) {
   if (out5) memcpy(out5, g_stats, sizeof g_stats);
   if (reset) memset(g_stats, 0, sizeof g_stats);
@@ -443,7 +447,10 @@ static void traverse(OrcRasterizer* r, const OrcPrim* P, int clipped) {
             if (c2 > bound) bound = c2;
             if (c3 > bound) bound = c3;
             ++g_stats[2];
-            if (h != 1 && bound <= h) ++g_stats[4];
+            if (h != 1 && bound <= h) {
+              ++g_stats[4];
+              if (g_block_bound_skip) goto next_block;
+            }
           }
           for (int yy = 0; yy < 8; ++yy)
             for (int px = 0; px < 8; ++px) {
@@ -458,6 +465,7 @@ static void traverse(OrcRasterizer* r, const OrcPrim* P, int clipped) {
           if (!changed) ++g_stats[3];
         }
       }
+    next_block:
       for (int l = 0; l < 8; ++l) d[l] = P->dzdx + d[l];   /* :1145-1146, every block, hit or not */
       for (int e = 0; e < 4; ++e) o[e] = P->nx[e] + o[e];
     }

@@ -66,6 +66,7 @@ typedef struct {
 /* planning statistics of the block loop: visits, HiZ-rejected, updates, updates without any change, updates a
    per-block corner bound would have skipped; reset != 0 clears them */
 void orc_stats(uint64_t* out5, int reset);
+void orc_set_block_bound_skip(int on); /* planning switch: skip updates the per-block corner bound proves to be no-ops */
 void orc_setup_quad(const OrcRasterizer* r, const uint32_t word[4], const float* refMin4, const float* refMax4,
                     int possiblyNearClipped, OrcPrim* out);
 

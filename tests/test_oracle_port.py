@@ -177,3 +177,29 @@ def test_synthetic_city_and_soup(lut):
         boxes = ps.quad_boxes()[::3]
         assert np.array_equal(r.query_boxes(boxes), p.query_boxes(boxes))
         r.close(); p.close(); s.close()
+
+
+@needs_ref
+def test_block_bound_skip_changes_nothing(lut):
+    """Planning switch of the port: updates whose largest corner sample is not above the block's
+    HiZ are skipped -- a quarter of Sponza's updates -- and depth, HiZ, gates and queries still equal the reference."""
+    import ctypes as C
+
+    L = po.lib()
+    L.orc_set_block_bound_skip.argtypes, L.orc_stats.argtypes = [C.c_int], [C.c_void_p, C.c_int]
+    s = _ref_scene("Sponza")
+    packed = [s.packed(i) for i in range(s.n_occluders)]
+    c = cam.SPONZA_CAMERA
+    views = [(c["pos"], c["dir"]), ((2.0, -3.0, 4.0), (-0.6, 0.75, -0.1)), ((-6.0, 1.0, 2.5), (0.9, -0.2, 0.1))]
+    mvps = [cam.view_projection(p, d, c["up"], c["fov"], 1280, 720) for p, d in views]
+    poss = [np.array(p, np.float32) for p, _ in views]
+    L.orc_set_block_bound_skip(1)
+    L.orc_stats(None, 1)
+    try:
+        _compare_frames(s, packed, 1280, 720, mvps, poss, lut)
+        st = np.zeros(5, np.uint64)
+        L.orc_stats(st.ctypes.data_as(C.c_void_p), 1)
+        assert st[4] > 0.1 * st[2], "the bound should have skipped a good part of the updates"
+    finally:
+        L.orc_set_block_bound_skip(0)
+    s.close()

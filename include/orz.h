@@ -24,7 +24,7 @@ typedef struct orz_occluder orz_occluder;     /* one baked batch resident in HBM
 typedef struct orz_rasterizer orz_rasterizer; /* one view's depth + HiZ + matrices (Rasterizer.h:10-61) */
 typedef struct orz_scene orz_scene;           /* all baked batches + occludee boxes of a scene in HBM */
 
-enum { ORZ_OK = 0, ORZ_ERR_CUDA = 1, ORZ_ERR_ARG = 2, ORZ_ERR_NO_DEVICE = 3 };
+enum { ORZ_OK = 0, ORZ_ERR_CUDA = 1, ORZ_ERR_ARG = 2, ORZ_ERR_NO_DEVICE = 3, ORZ_ERR_NCCL = 4 };
 
 const char* orz_last_error(void);
 int orz_version(void);
@@ -37,6 +37,7 @@ int orz_context_create(int device, orz_context** out);
 void orz_context_destroy(orz_context* ctx);
 int orz_context_synchronize(orz_context* ctx);
 void* orz_context_stream(orz_context* ctx); /* cudaStream_t all work of this context is ordered on */
+int orz_context_device(orz_context* ctx);   /* CUDA device index the context was created on */
 /* Replace the probed rcpps model: table[i] = bits of rcpps(1.0 + i * 2^-bits), 2^bits entries. */
 int orz_context_set_rcp_table(orz_context* ctx, const uint32_t* table, int bits);
 int orz_context_get_rcp_table(orz_context* ctx, uint32_t* table, int* bits); /* table: room for 2^23 max; pass NULL to get bits */
@@ -195,6 +196,38 @@ int orz_context_set_cluster_views(orz_context* ctx, int maxViews);
 int orz_context_set_cluster_size(orz_context* ctx, int ctas);
 /* tuning: warps cooperating on one view in the batch kernel (1, 2, 4, 8, 16); 0 = automatic */
 int orz_context_set_group_warps(orz_context* ctx, int warps);
+
+/* ---- multi-GPU: batches of independent views sharded over GPUs (Main.cpp:181-206 per view) ----------
+ * The reference has no multi-device code; its unit of independent work is the view.  Every rank (one GPU, one
+ * context) renders its own slice of the view list with the static scene replicated -- orz_render_views_device with
+ * visBits in HBM -- and ONE collective, an NCCL all-gather of the per-view visibility bitmasks over NVLink,
+ * assembles the result on every rank; depth and HiZ stay on the GPU that produced them.  A single view has no useful
+ * split across GPUs (ordered, shared depth buffer): replicas only.  NCCL is bound at run time (libnccl.so.2, or the
+ * path in ORZ_NCCL_LIB); without it these calls fail with ORZ_ERR_NCCL and everything else keeps working.
+ *   one process per GPU:  rank 0 calls orz_comm_get_unique_id, hands the 128 bytes to the other ranks by its own means
+ *                         (MPI, a file, torch.distributed ...), every rank calls orz_comm_create;
+ *   one process, n GPUs:  orz_comm_create_all over n contexts; bracket the per-GPU orz_gather_bits calls of one
+ *                         collective with orz_comm_group_begin / orz_comm_group_end. */
+typedef struct orz_comm orz_comm;
+#define ORZ_COMM_ID_BYTES 128
+int orz_comm_get_unique_id(void* id128);                                                       /* ncclGetUniqueId */
+int orz_comm_create(orz_context* ctx, int nRanks, int rank, const void* id128, orz_comm** out); /* ncclCommInitRank */
+int orz_comm_create_all(orz_context* const* ctxs, int n, orz_comm** outs);                     /* ncclCommInitAll */
+void orz_comm_destroy(orz_comm* comm);
+int orz_comm_rank(const orz_comm* comm);
+int orz_comm_size(const orz_comm* comm);
+int orz_comm_group_begin(void);
+int orz_comm_group_end(void);
+/* localBits: wordsPerRank words in HBM (this rank's views x ceil(nBoxes/32), rows of views the rank does not own zero);
+ * allBits: nRanks x wordsPerRank words in HBM, rank r's rows at r * wordsPerRank.  Asynchronous on the context stream,
+ * after the render calls enqueued before it. */
+int orz_gather_bits(orz_comm* comm, const uint32_t* localBits, size_t wordsPerRank, uint32_t* allBits);
+/* The same on the communicator's own stream, beside whatever the context enqueues next (the next batch): the buffers
+ * must stay untouched until orz_comm_join (the context stream waits for the gathers issued so far) or
+ * orz_comm_synchronize (the host waits for both streams). */
+int orz_gather_bits_overlapped(orz_comm* comm, const uint32_t* localBits, size_t wordsPerRank, uint32_t* allBits);
+int orz_comm_join(orz_comm* comm);
+int orz_comm_synchronize(orz_comm* comm);
 
 #ifdef __cplusplus
 }

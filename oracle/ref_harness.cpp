@@ -343,4 +343,116 @@ double ref_bench_views(void* scene, uint32_t w, uint32_t h, const float* mvps, c
   return wall;
 }
 
+// ---- parity at benchmark sizes: render every view with the reference (fresh state, all host threads)
+// and compare with what the implementation under test produced.  Any `got*` pointer may be NULL.
+// mode bit0: no gate (every occluder submitted), bit1: with bit0, rasterize<true>.
+// mismatch[v] bits: 1 gate, 2 HiZ, 4 depth (canonical: cleared blocks read as zero), 8 visible bits,
+// 16 needsClipping bits, 32 quads submitted.  Returns the number of views with any mismatch.
+uint32_t ref_check_views(void* scene, uint32_t w, uint32_t h, const float* mvps, const uint32_t* orders, uint32_t nViews,
+                         uint32_t nOrder, const float* boxes, uint32_t nBoxes, uint32_t nThreads, uint32_t mode,
+                         const uint8_t* gotGate, const uint16_t* gotDepth, const uint16_t* gotHiz, const uint32_t* gotVis,
+                         const uint32_t* gotClip, const uint32_t* gotQuads, uint32_t* mismatch) {
+  auto* S = static_cast<RefScene*>(scene);
+  if (nThreads == 0) nThreads = 1;
+  nThreads = std::min<uint32_t>(nThreads, std::max<uint32_t>(nViews, 1u));
+  const size_t blocks = size_t(w / 8) * (h / 8), words = (size_t(nBoxes) + 31) / 32;
+  std::atomic<uint32_t> next{0}, bad{0};
+  auto work = [&]() {
+    Rasterizer R(w, h);
+    std::vector<uint8_t> gate(nOrder);
+    std::vector<uint16_t> depth(blocks * 64);
+    std::vector<uint32_t> vis(words), clip(words);
+    for (;;) {
+      const uint32_t v = next.fetch_add(1);
+      if (v >= nViews) break;
+      const float* mvp = mvps + 16 * size_t(v);
+      const uint32_t* order = orders + size_t(nOrder) * v;
+      uint64_t quads = 0;
+      if (mode & 1u) {
+        ref_rast_submit_all(&R, S, mvp, order, nOrder, (mode & 2u) ? 1 : 0, 1);
+        for (uint32_t i = 0; i < nOrder; ++i) quads += 2 * uint64_t(S->occluders[order[i]]->m_packetCount);
+        std::fill(gate.begin(), gate.end(), uint8_t(1));
+      } else {
+        quads = ref_rast_frame(&R, S, mvp, order, nOrder, 1, gate.data());
+      }
+      uint32_t m = 0;
+      if (gotGate && !(mode & 1u) && memcmp(gotGate + size_t(nOrder) * v, gate.data(), nOrder) != 0) m |= 1u;
+      if (gotHiz && memcmp(gotHiz + blocks * v, R.m_hiZ.data(), blocks * 2) != 0) m |= 2u;
+      if (gotDepth) {
+        ref_rast_get_depth(&R, depth.data(), 1);
+        if (memcmp(gotDepth + blocks * 64 * v, depth.data(), blocks * 128) != 0) m |= 4u;
+      }
+      if ((gotVis || gotClip) && nBoxes) {
+        std::fill(vis.begin(), vis.end(), 0u);
+        std::fill(clip.begin(), clip.end(), 0u);
+        for (uint32_t i = 0; i < nBoxes; ++i) {
+          const int q = ref_rast_query(&R, boxes + 8 * size_t(i), boxes + 8 * size_t(i) + 4);
+          if (q & 1) vis[i >> 5] |= 1u << (i & 31);
+          if (q & 2) clip[i >> 5] |= 1u << (i & 31);
+        }
+        if (gotVis && memcmp(gotVis + words * v, vis.data(), words * 4) != 0) m |= 8u;
+        if (gotClip && memcmp(gotClip + words * v, clip.data(), words * 4) != 0) m |= 16u;
+      }
+      if (gotQuads && gotQuads[v] != uint32_t(quads)) m |= 32u;
+      if (mismatch) mismatch[v] = m;
+      if (m) bad.fetch_add(1);
+    }
+  };
+  std::vector<std::thread> th;
+  for (uint32_t t = 1; t < nThreads; ++t) th.emplace_back(work);
+  work();
+  for (auto& x : th) x.join();
+  return bad.load();
+}
+
+// ---- persistent bench pool: one Rasterizer per thread, built once (each constructor builds the 520 ms
+// edge-mask table, Rasterizer.cpp:547-604) and in parallel; ref_pool_bench times the stock path like
+// ref_bench_views on the pool's warm threads' rasterizers.
+struct RefPool {
+  uint32_t w, h;
+  std::vector<std::unique_ptr<Rasterizer>> rast;
+};
+void* ref_pool_create(uint32_t w, uint32_t h, uint32_t nThreads) {
+  auto* P = new RefPool{w, h, {}};
+  if (nThreads == 0) nThreads = 1;
+  P->rast.resize(nThreads);
+  std::vector<std::thread> th;
+  for (uint32_t t = 0; t < nThreads; ++t) th.emplace_back([P, t, w, h]() { P->rast[t] = std::make_unique<Rasterizer>(w, h); });
+  for (auto& x : th) x.join();
+  return P;
+}
+void ref_pool_free(void* p) { delete static_cast<RefPool*>(p); }
+double ref_pool_bench(void* pool, void* scene, const float* mvps, const uint32_t* orders, uint32_t nViews, uint32_t nOrder,
+                      const float* boxes, uint32_t nBoxes, uint32_t reps, double* out) {
+  auto* P = static_cast<RefPool*>(pool);
+  auto* S = static_cast<RefScene*>(scene);
+  const uint32_t nThreads = uint32_t(P->rast.size());
+  std::vector<double> frameSec(nThreads, 0.0), querySec(nThreads, 0.0);
+  std::vector<uint64_t> quads(nThreads, 0), visible(nThreads, 0);
+  auto t0 = std::chrono::steady_clock::now();
+  auto work = [&](uint32_t t) {
+    Rasterizer* R = P->rast[t].get();
+    for (uint32_t rep = 0; rep < reps; ++rep)
+      for (uint32_t v = t; v < nViews; v += nThreads) {
+        auto a = std::chrono::steady_clock::now();
+        quads[t] += ref_rast_frame(R, S, mvps + 16 * size_t(v), orders + size_t(nOrder) * v, nOrder, 0, nullptr);
+        auto b = std::chrono::steady_clock::now();
+        uint64_t vis = 0;
+        for (uint32_t i = 0; i < nBoxes; ++i) vis += ref_rast_query(R, boxes + 8 * size_t(i), boxes + 8 * size_t(i) + 4) & 1;
+        auto c = std::chrono::steady_clock::now();
+        visible[t] += vis;
+        frameSec[t] += std::chrono::duration<double>(b - a).count();
+        querySec[t] += std::chrono::duration<double>(c - b).count();
+      }
+  };
+  std::vector<std::thread> th;
+  for (uint32_t t = 1; t < nThreads; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+  const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  out[0] = out[1] = out[2] = out[3] = 0;
+  for (uint32_t t = 0; t < nThreads; ++t) { out[0] += frameSec[t]; out[1] += querySec[t]; out[2] += double(quads[t]); out[3] += double(visible[t]); }
+  return wall;
+}
+
 }  // extern "C"

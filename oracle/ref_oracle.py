@@ -61,6 +61,10 @@ def lib():
             "ref_rcp_ps": (None, [vp, vp, C.c_size_t]),
             "ref_rsqrt_ps": (None, [vp, vp, C.c_size_t]),
             "ref_bench_views": (C.c_double, [vp, u32, u32, vp, vp, u32, u32, vp, u32, u32, u32, vp]),
+            "ref_check_views": (u32, [vp, u32, u32, vp, vp, u32, u32, vp, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp]),
+            "ref_pool_create": (vp, [u32, u32, u32]),
+            "ref_pool_free": (None, [vp]),
+            "ref_pool_bench": (C.c_double, [vp, vp, vp, vp, u32, u32, vp, u32, u32, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -252,6 +256,67 @@ def bench_views(scene: RefScene, w, h, mvps, orders, boxes, n_threads=1, reps=1)
     out = np.zeros(4, np.float64)
     wall = lib().ref_bench_views(scene.h, w, h, _p(mvps), _p(orders), mvps.shape[0], orders.shape[1], _p(boxes), boxes.shape[0], n_threads, reps, _p(out))
     return wall, out
+
+
+MISMATCH_NAMES = {1: "gate", 2: "hiz", 4: "depth", 8: "vis", 16: "clip", 32: "quads"}
+
+
+def check_views(scene: RefScene, w, h, mvps, orders, boxes=None, n_threads=0, mode=0, gate=None, depth=None, hiz=None, vis=None, clip=None,
+                quads=None):
+    """Render every view with the unmodified reference (fresh state per view, `n_threads` host threads, 0 = all) and
+    compare bit for bit with the arrays given (any may be None): gate [n, nOcc] u8, depth [n, w*h] u16 (canonical),
+    hiz [n, blocks] u16, vis / clip [n, ceil(nBoxes/32)] u32, quads [n] u32.  mode: 1 = no gate, 3 = no gate +
+    rasterize<true>.  Returns the per-view mismatch masks (see MISMATCH_NAMES); all zero = parity."""
+    mvps = np.ascontiguousarray(mvps, np.float32).reshape(-1, 16)
+    n = mvps.shape[0]
+    orders = np.ascontiguousarray(orders, np.uint32).reshape(n, -1)
+    boxes = np.zeros((0, 8), np.float32) if boxes is None else np.ascontiguousarray(boxes, np.float32).reshape(-1, 8)
+    blocks = (w // 8) * (h // 8)
+    words = (boxes.shape[0] + 31) // 32
+
+    def arr(a, dt, cols):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a).view(dt) if np.asarray(a).dtype.itemsize == np.dtype(dt).itemsize else np.ascontiguousarray(a, dt)
+        assert a.size == n * cols, (a.shape, n, cols)
+        return a
+
+    keep = [arr(gate, np.uint8, orders.shape[1]), arr(depth, np.uint16, blocks * 64), arr(hiz, np.uint16, blocks), arr(vis, np.uint32, words),
+            arr(clip, np.uint32, words), arr(quads, np.uint32, 1)]
+    mism = np.zeros(n, np.uint32)
+    import os as _os
+    lib().ref_check_views(scene.h, w, h, _p(mvps), _p(orders), n, orders.shape[1], _p(boxes), boxes.shape[0], n_threads or (_os.cpu_count() or 1), mode,
+                          *[None if a is None else _p(a) for a in keep], _p(mism))
+    return mism
+
+
+def describe_mismatch(mism) -> str:
+    bad = np.nonzero(mism)[0]
+    if bad.size == 0:
+        return "parity"
+    kinds = sorted({name for bit, name in MISMATCH_NAMES.items() if (np.bitwise_or.reduce(mism) & bit)})
+    return f"{bad.size} of {len(mism)} views differ ({', '.join(kinds)}); first views {bad[:8].tolist()} masks {mism[bad[:8]].tolist()}"
+
+
+class RefPool:
+    """One reference Rasterizer per host thread, built once and in parallel (bench.py --impl reference)."""
+
+    def __init__(self, w, h, n_threads):
+        self.n_threads = n_threads
+        self.p = lib().ref_pool_create(w, h, n_threads)
+
+    def bench(self, scene: RefScene, mvps, orders, boxes, reps=1):
+        mvps = np.ascontiguousarray(mvps, np.float32).reshape(-1, 16)
+        orders = np.ascontiguousarray(orders, np.uint32).reshape(mvps.shape[0], -1)
+        boxes = np.ascontiguousarray(boxes, np.float32).reshape(-1, 8)
+        out = np.zeros(4, np.float64)
+        wall = lib().ref_pool_bench(self.p, scene.h, _p(mvps), _p(orders), mvps.shape[0], orders.shape[1], _p(boxes), boxes.shape[0], reps, _p(out))
+        return wall, out
+
+    def close(self):
+        if self.p:
+            lib().ref_pool_free(self.p)
+            self.p = None
 
 
 def fnv1a64(a: np.ndarray) -> str:

@@ -98,7 +98,21 @@ EXPORTS = {
     "orz_scene_destroy": (None, [C.c_void_p]),
     "orz_render_views": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(ViewBatch)]),
     "orz_render_views_device": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(ViewBatch)]),
+    "orz_context_device": (C.c_int, [C.c_void_p]),
+    "orz_comm_get_unique_id": (C.c_int, [C.c_void_p]),
+    "orz_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "orz_comm_create_all": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]),
+    "orz_comm_destroy": (None, [C.c_void_p]),
+    "orz_comm_rank": (C.c_int, [C.c_void_p]),
+    "orz_comm_size": (C.c_int, [C.c_void_p]),
+    "orz_comm_group_begin": (C.c_int, []),
+    "orz_comm_group_end": (C.c_int, []),
+    "orz_gather_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "orz_gather_bits_overlapped": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "orz_comm_join": (C.c_int, [C.c_void_p]),
+    "orz_comm_synchronize": (C.c_int, [C.c_void_p]),
 }
+COMM_ID_BYTES = 128
 
 
 def lib():
@@ -506,6 +520,42 @@ class Scene:
     def render_views_raw(self, batch: ViewBatch, device: bool):
         fn = lib().orz_render_views_device if device else lib().orz_render_views
         _check(fn(self.ctx.h, self.h, C.byref(batch)))
+
+
+class Comm:
+    """NCCL communicator of the view-batch path behind the C ABI (orz_comm_*): one rank per (process, GPU).
+    `unique_id()` on rank 0, the 128 bytes reach the other ranks by the caller's means, then every rank constructs."""
+
+    def __init__(self, ctx: Context, n_ranks: int, rank: int, unique_id: bytes):
+        assert len(unique_id) == COMM_ID_BYTES
+        self.ctx = ctx
+        buf = C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        h = C.c_void_p()
+        _check(lib().orz_comm_create(ctx.h, n_ranks, rank, buf, C.byref(h)))
+        self.h = h
+        self.n_ranks, self.rank = n_ranks, rank
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        _check(lib().orz_comm_get_unique_id(buf))
+        return buf.raw
+
+    def gather_bits(self, local_ptr: int, words_per_rank: int, all_ptr: int, overlapped: bool = False):
+        """Device pointers: local [words_per_rank] u32 -> all [n_ranks x words_per_rank] u32 (orz_gather_bits[_overlapped])."""
+        fn = lib().orz_gather_bits_overlapped if overlapped else lib().orz_gather_bits
+        _check(fn(self.h, local_ptr, words_per_rank, all_ptr))
+
+    def join(self):
+        _check(lib().orz_comm_join(self.h))
+
+    def synchronize(self):
+        _check(lib().orz_comm_synchronize(self.h))
+
+    def close(self):
+        if self.h:
+            lib().orz_comm_destroy(self.h)
+            self.h = None
 
 
 def unpack_bits(words: np.ndarray, n: int) -> np.ndarray:

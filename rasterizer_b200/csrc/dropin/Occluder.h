@@ -34,4 +34,5 @@ struct Occluder
 	uint32_t m_packetCount = 0;
 
 	mutable orz_occluder* m_device = nullptr;   // HBM-resident copy (one 16-byte record per quad)
+	mutable std::shared_ptr<void> m_context;    // context that owns m_device, kept alive until the destructor has run
 };

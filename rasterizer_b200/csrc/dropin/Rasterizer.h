@@ -7,7 +7,8 @@
 // Differences a caller can observe (both documented in DESIGN.md):
 //   * clear() also zeroes the depth buffer ("fresh" state): the reference leaves stale depth
 //     behind cleared blocks, which query2D then reads (Rasterizer.cpp:107-121 vs 310-343).
-//   * rasterizeViews(): batch entry point for many independent views (Main.cpp:181-206 per view).
+//   * many independent views (Main.cpp:181-206 per view) go through the C ABI's orz_render_views (include/orz.h);
+//     this class keeps the reference's one-view interface.
 #pragma once
 
 #include <immintrin.h>
@@ -46,10 +47,11 @@ public:
 	void queryVisibilityBatch(const float* boxesMinMax, uint32_t count, uint8_t* out);
 	// raw buffers in the reference layout: depth u16 [block][row][px], HiZ u16 [block]
 	void download(uint16_t* depth, uint16_t* hiZ) const;
-	static orz_context* context();   // per-thread context the drop-in classes share
+	static orz_context* context();   // the calling thread's context (created on first use, shared by the objects it creates)
 
 private:
 	orz_rasterizer* m_impl;
 	uint32_t m_width;
 	uint32_t m_height;
+	std::shared_ptr<void> m_context;   // keeps the creating thread's context alive for as long as this object lives
 };

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "../../../include/orz.h"
 
@@ -23,18 +24,30 @@ void check(int code, const char* what) {
 }
 }  // namespace
 
-orz_context* Rasterizer::context() {
-  struct Holder {
-    orz_context* ctx = nullptr;
-    ~Holder() { if (ctx) orz_context_destroy(ctx); }
-  };
-  static thread_local Holder h;
-  if (!h.ctx) {
+// One context per host thread (a context is one stream + scratch and is not re-entrant), shared by every drop-in object
+// the thread creates and REFERENCE COUNTED by them: the reference application keeps its Rasterizer and Occluders in
+// static-duration globals (Main.cpp:41-44), which outlive the main thread's thread_locals, and objects may be handed to
+// or destroyed on another thread -- the context dies with its last user, not with the thread that made it.
+namespace {
+struct ContextHolder {
+  orz_context* ctx = nullptr;
+  ~ContextHolder() { if (ctx) orz_context_destroy(ctx); }
+};
+std::shared_ptr<void> threadContext() {
+  static thread_local std::shared_ptr<ContextHolder> tl;
+  if (!tl) {
+    auto h = std::make_shared<ContextHolder>();
     const char* dev = std::getenv("ORZ_DEVICE");
-    check(orz_context_create(dev ? std::atoi(dev) : 0, &h.ctx), "orz_context_create");
+    check(orz_context_create(dev ? std::atoi(dev) : 0, &h->ctx), "orz_context_create");
+    tl = std::move(h);
   }
-  return h.ctx;
+  return tl;
 }
+orz_context* raw(const std::shared_ptr<void>& holder) { return static_cast<ContextHolder*>(holder.get())->ctx; }
+std::mutex g_uploadMutex;  // lazy device copies of occluders shared between threads (const Occluder& is shareable in the reference)
+}  // namespace
+
+orz_context* Rasterizer::context() { return raw(threadContext()); }
 
 std::unique_ptr<Occluder> Occluder::bake(const std::vector<__m128>& vertices, __m128 refMin, __m128 refMax) {
   auto occ = std::make_unique<Occluder>();
@@ -61,22 +74,26 @@ Occluder::~Occluder() {
   std::free(m_vertexData);
 }
 
-Rasterizer::Rasterizer(uint32_t width, uint32_t height) : m_impl(nullptr), m_width(width), m_height(height) {
-  check(orz_rasterizer_create(context(), width, height, &m_impl), "orz_rasterizer_create");
+Rasterizer::Rasterizer(uint32_t width, uint32_t height) : m_impl(nullptr), m_width(width), m_height(height), m_context(threadContext()) {
+  check(orz_rasterizer_create(raw(m_context), width, height, &m_impl), "orz_rasterizer_create");
 }
-Rasterizer::~Rasterizer() { orz_rasterizer_destroy(m_impl); }
+Rasterizer::~Rasterizer() { orz_rasterizer_destroy(m_impl); }  // m_context is released afterwards (member order)
 
 void Rasterizer::setModelViewProjection(const float* matrix) { check(orz_rasterizer_set_mvp(m_impl, matrix), "orz_rasterizer_set_mvp"); }
 void Rasterizer::clear() { check(orz_rasterizer_clear(m_impl), "orz_rasterizer_clear"); }
 
 template <bool possiblyNearClipped>
 void Rasterizer::rasterize(const Occluder& occluder) {
-  if (!occluder.m_device) {
-    float mn[4], mx[4];
-    _mm_storeu_ps(mn, occluder.m_refMin);
-    _mm_storeu_ps(mx, occluder.m_refMax);
-    check(orz_occluder_create(context(), reinterpret_cast<const uint32_t*>(occluder.m_vertexData), occluder.m_packetCount, mn, mx,
-                              &occluder.m_device), "orz_occluder_create");
+  {
+    std::lock_guard<std::mutex> lock(g_uploadMutex);
+    if (!occluder.m_device) {  // the copy lives in (and keeps alive) the context of the rasterizer that first used it
+      float mn[4], mx[4];
+      _mm_storeu_ps(mn, occluder.m_refMin);
+      _mm_storeu_ps(mx, occluder.m_refMax);
+      occluder.m_context = m_context;
+      check(orz_occluder_create(raw(m_context), reinterpret_cast<const uint32_t*>(occluder.m_vertexData), occluder.m_packetCount, mn, mx,
+                                &occluder.m_device), "orz_occluder_create");
+    }
   }
   check(orz_rasterizer_rasterize(m_impl, occluder.m_device, possiblyNearClipped ? 1 : 0), "orz_rasterizer_rasterize");
 }

@@ -171,6 +171,9 @@ __device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) {
   asm volatile("ld.relaxed.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
   return v;
 }
+// the same word as ONE value for the whole warp: every lane's load races with remote stores on its own, so control flow
+// that contains full-mask collectives branches on lane 0's observation only
+__device__ __forceinline__ uint32_t ld_flag_warp(const uint32_t* p) { return __shfl_sync(kFull, ld_flag(p), 0); }
 __device__ __forceinline__ void st_flag_remote(uint32_t* localPtr, uint32_t ctaRank, uint32_t val) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(localPtr)), "r"(ctaRank));
@@ -427,24 +430,24 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
       const uint32_t bx0 = minX >> 3, bx1 = maxX >> 3, by0 = minY >> 3, by1 = maxY >> 3;
       const uint32_t* vis = s_vis + s;
       uint32_t tm = tiles_meeting(bx0, bx1, by0, by1);
-      if (tm && !ld_flag(vis)) {
+      if (tm && !ld_flag_warp(vis)) {
         bool found = false;
         for (; tm; tm &= tm - 1u) {
           const uint32_t k = (uint32_t)__ffs((int)tm) - 1u;
           const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
-          if (ld_flag(vis)) break;  // another warp already found a visible pixel
+          if (ld_flag_warp(vis)) break;  // another warp already found a visible pixel
           const bool hit = bx >= bx0 && bx <= bx1 && by >= by0 && by <= by1 && bx < T.blocksX && by < T.blocksY &&
                            query_block_h(T, bx, by, (uint32_t)myHiz[32u * k], minX, maxX, minY, maxY, maxZ);
           if (__any_sync(kFull, hit)) { found = true; break; }
         }
         if (found) { if (lane < C) st_flag_remote(s_vis + s, (uint32_t)lane, 1u); }
-        else if (!ld_flag(vis)) answer_no(s);
+        else if (!ld_flag_warp(vis)) answer_no(s);
       }
       // visible as soon as ONE warp says so, invisible when all 16 C warps have said no
       const uint32_t* done = s_doneCta + s;
       for (;;) {
-        if (ld_flag(vis)) break;
-        if (ld_flag(done) >= (uint32_t)C) { visible = ld_flag(vis) != 0u; break; }
+        if (ld_flag_warp(vis)) break;
+        if (ld_flag_warp(done) >= (uint32_t)C) { visible = ld_flag_warp(vis) != 0u; break; }
 #if ORZ_SPIN_NAP
         __nanosleep(ORZ_SPIN_NAP);  // (a longer or growing nap was measured slower: the wake-up delay sits on the dependency chain)
 #endif

@@ -79,6 +79,7 @@ struct FrameParams {
   uint32_t* viewCost;   // nViews: quads of the occluders that survive the frustum test (scheduling estimate)
   uint32_t* viewOrder;  // nViews: views sorted by descending cost (longest first), or NULL
   uint32_t viewBase, groupViews;  // this launch handles sorted ranks [viewBase, viewBase + groupViews)
+  uint32_t queryChunks;           // k_query_views: CTAs (of 256 boxes) per view
   int exportDepth;      // 1: the caller reads depth back -> zero-fill blocks that stayed cleared
   uint32_t clusterK;    // cluster kernel: tiles per warp
   // cluster path: speculative setup output per view (k_setup_views)

@@ -106,6 +106,10 @@ struct orz_context {
   cudaStream_t aux[kGroups] = {nullptr};
   cudaEvent_t evFork = nullptr, evJoin[kGroups] = {nullptr};
   size_t arenaBudget = size_t(8) << 30;  // bytes of internal per-view depth+HiZ targets (views are chunked to fit)
+  // dynamic shared memory already granted to a kernel instantiation on this context's device (cudaFuncSetAttribute is
+  // per device and idempotent: keeping the record per context avoids process-wide mutable state)
+  size_t smemViews[2][5] = {{0}};   // [traversal - 1][log2 GW]
+  size_t smemCluster[5] = {0};      // [log2 C]
 };
 struct orz_occluder {
   orz_context* ctx;
@@ -185,13 +189,15 @@ extern "C" void orz_context_destroy(orz_context* ctx) {
   delete ctx;
 }
 extern "C" int orz_context_synchronize(orz_context* ctx) {
+  if (!ctx) return fail(ORZ_ERR_ARG, "orz_context_synchronize: context is NULL");
   ORZ_CUDA(cudaStreamSynchronize(ctx->stream));
   return ORZ_OK;
 }
 extern "C" void* orz_context_stream(orz_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int orz_context_device(orz_context* ctx) { return ctx ? ctx->device : -1; }
 extern "C" uint64_t orz_context_launch_count(orz_context* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int orz_context_set_group_warps(orz_context* ctx, int warps) {
-  if (warps != 0 && warps != 1 && warps != 2 && warps != 4 && warps != 8 && warps != 16) return fail(ORZ_ERR_ARG, "group warps must be 0, 1, 2, 4, 8 or 16");
+  if (!ctx || (warps != 0 && warps != 1 && warps != 2 && warps != 4 && warps != 8 && warps != 16)) return fail(ORZ_ERR_ARG, "group warps must be 0, 1, 2, 4, 8 or 16");
   ctx->groupWarps = warps;
   return ORZ_OK;
 }
@@ -250,7 +256,7 @@ static void relayout_packets(const uint32_t* packets, uint32_t packetCount, uint
 
 extern "C" int orz_occluder_create(orz_context* ctx, const uint32_t* packets, uint32_t packetCount, const float* refMin4,
                                    const float* refMax4, orz_occluder** out) {
-  if (!ctx || !packets || !out || packetCount % 4 != 0) return fail(ORZ_ERR_ARG, "orz_occluder_create: bad arguments");
+  if (!ctx || !packets || !refMin4 || !refMax4 || !out || packetCount % 4 != 0) return fail(ORZ_ERR_ARG, "orz_occluder_create: bad arguments");
   ORZ_CUDA(cudaSetDevice(ctx->device));
   orz_occluder* o = new orz_occluder();
   o->ctx = ctx;
@@ -514,14 +520,16 @@ extern "C" int orz_scene_bake(orz_context* ctx, const float* vertices, const uin
 extern "C" int orz_scene_set_occludees(orz_scene* s, const float* boxes, uint32_t n) {
   if (!s || (n && !boxes)) return fail(ORZ_ERR_ARG, "orz_scene_set_occludees: bad arguments");
   ORZ_CUDA(cudaSetDevice(s->ctx->device));
-  ORZ_CUDA(cudaStreamSynchronize(s->ctx->stream));
-  cudaFree(s->d_boxes);
-  s->d_boxes = nullptr;
-  s->nBoxes = n;
+  // the new set is complete in HBM before the old one is released: a failure leaves the scene as it was
+  float4* fresh = nullptr;
   if (n) {
-    ORZ_CUDA(cudaMalloc(&s->d_boxes, (size_t)n * 32));
-    ORZ_CUDA(cudaMemcpy(s->d_boxes, boxes, (size_t)n * 32, cudaMemcpyHostToDevice));
+    ORZ_CUDA(cudaMalloc(&fresh, (size_t)n * 32));
+    ORZ_CUDA_OR(cudaFree(fresh), cudaMemcpy(fresh, boxes, (size_t)n * 32, cudaMemcpyHostToDevice));
   }
+  ORZ_CUDA_OR(cudaFree(fresh), cudaStreamSynchronize(s->ctx->stream));  // queries in flight still read the old boxes
+  cudaFree(s->d_boxes);
+  s->d_boxes = fresh;
+  s->nBoxes = n;
   return ORZ_OK;
 }
 extern "C" int orz_scene_get_occluders(orz_scene* s, uint32_t* nOccluders, float* centers, float* boundsMin, float* boundsMax,
@@ -639,12 +647,29 @@ extern "C" void orz_scene_destroy(orz_scene* s) {
   delete s;
 }
 
+// queryVisibility of every occludee box for views [pg.viewBase, pg.viewBase + pg.groupViews) of the (sorted) batch:
+// 1-D grids of (view, 256-box chunk) CTAs, in slabs of views when one grid cannot hold them all
+static int launch_query(orz_context* ctx, FrameParams pg, uint32_t nBoxes, cudaStream_t st) {
+  pg.queryChunks = (nBoxes + 255u) / 256u;
+  if (pg.queryChunks == 0u || pg.groupViews == 0u) return ORZ_OK;
+  const uint32_t slab = std::max<uint32_t>(1u, 0x7fffffffu / pg.queryChunks);
+  const uint32_t first = pg.viewBase, last = pg.viewBase + pg.groupViews;
+  for (uint32_t v = first; v < last; v += slab) {
+    pg.viewBase = v;
+    pg.groupViews = std::min(slab, last - v);
+    k_query_views<<<pg.groupViews * pg.queryChunks, 256, 0, st>>>(pg);
+    ctx->launches++;
+    ORZ_CUDA(cudaGetLastError());
+  }
+  return ORZ_OK;
+}
+
 template <int GW, int kTrav>
 static int launch_views_t(orz_context* ctx, const FrameParams& p, uint32_t grid, cudaStream_t st) {
-  static bool configured[64] = {false};
-  if (!configured[ctx->device & 63]) {
+  constexpr int kLog = GW == 1 ? 0 : GW == 2 ? 1 : GW == 4 ? 2 : GW == 8 ? 3 : 4;
+  if (!ctx->smemViews[kTrav - 1][kLog]) {
     ORZ_CUDA(cudaFuncSetAttribute(k_render_views<GW, kTrav>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FrameSmem<GW, kTrav>::kBytes));
-    configured[ctx->device & 63] = true;
+    ctx->smemViews[kTrav - 1][kLog] = FrameSmem<GW, kTrav>::kBytes;
   }
   k_render_views<GW, kTrav><<<grid, GW * 32, FrameSmem<GW, kTrav>::kBytes, st>>>(p);
   ctx->launches++;
@@ -696,11 +721,11 @@ template <int C>
 static int launch_cluster_t(orz_context* ctx, FrameParams p, uint32_t nViews, uint32_t nTiles, cudaStream_t st) {
   p.clusterK = (nTiles + (uint32_t)(C * kClusterGW) - 1u) / (uint32_t)(C * kClusterGW);
   const size_t smem = ClusterSmem::bytes(p.clusterK, p.nOcc);
-  static size_t configured[64] = {0};
-  if (configured[ctx->device & 63] < smem) {
+  constexpr int kLog = C == 1 ? 0 : C == 2 ? 1 : C == 4 ? 2 : C == 8 ? 3 : 4;
+  if (ctx->smemCluster[kLog] < smem) {
     ORZ_CUDA(cudaFuncSetAttribute(k_raster_views_cluster<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (C > 8) ORZ_CUDA(cudaFuncSetAttribute(k_raster_views_cluster<C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    configured[ctx->device & 63] = smem;
+    ctx->smemCluster[kLog] = smem;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
@@ -739,11 +764,25 @@ static int launch_cluster(orz_context* ctx, const FrameParams& p, uint32_t nView
   }
 }
 
+// Error paths between the fork of the auxiliary streams and their join must not leave work running on them that later
+// calls (which reuse or free the scratch buffers) know nothing about: the guard drains them unless the join was reached.
+namespace {
+struct AuxDrain {
+  orz_context* ctx;
+  bool armed = false;
+  ~AuxDrain() {
+    if (!armed) return;
+    for (int g = 0; g < orz_context::kGroups; ++g) cudaStreamSynchronize(ctx->aux[g]);
+  }
+};
+}  // namespace
+
 // Device-pointer entry: three launches per chunk of views (prepare, render, query).  When the
 // caller does not ask for depth/HiZ, per-view targets live in an internal arena and the batch is
 // processed in chunks that fit the arena budget.
 extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const orz_view_batch* b) {
   if (!ctx || !scene || !b || !b->mvps || (!b->orders && !b->camPos)) return fail(ORZ_ERR_ARG, "orz_render_views_device: bad arguments");
+  if (scene->ctx != ctx) return fail(ORZ_ERR_ARG, "orz_render_views_device: the scene belongs to another context");
   if (b->width == 0 || b->height == 0 || b->width % 8 || b->height % 8) return fail(ORZ_ERR_ARG, "width and height must be positive multiples of 8");
   if ((b->depth != nullptr) != (b->hiz != nullptr)) return fail(ORZ_ERR_ARG, "depth and hiz outputs must be requested together");
   if (b->nViews == 0) return ORZ_OK;
@@ -817,7 +856,7 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
     const bool wide = (b->flags & ORZ_BATCH_NO_GATE) && ((b->flags & ORZ_BATCH_WIDE) || (nv <= 8u && scene->totalQuads >= 65536u));
     // (targets above 32 tiles per warp of a 16-CTA cluster -- beyond ~8K x 4K -- stay on the batch kernel)
     // measured crossover with the batch kernel: ~2000 views at 1920x1080, ~1500 at 512x256 (profiles/r1_few_views_*)
-    const uint32_t clusterLimit = (uint32_t)ctx->clusterViews;
+    const uint32_t clusterLimit = std::min<uint32_t>((uint32_t)ctx->clusterViews, 65535u);  // k_setup_views puts the view on grid.y
     const size_t nTilesC = (size_t)((b->width / 8 + kTileW - 1) / kTileW) * ((b->height / 8 + kTileH - 1) / kTileH);
     const bool clusterPath = !wide && ctx->clusterViews > 0 && nv <= clusterLimit && nTilesC <= 32u * 16u * kClusterGW && nOcc <= kClusterMaxOcc &&
                              (size_t)nv * scene->totalQuads * (blocks > 65536u ? 2 : 1) * (kRecStride * 4 + 8) <= (size_t(8) << 30);
@@ -860,9 +899,7 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
       if (p.visBits || p.clipBits) {
         FrameParams pq = p;
         pq.viewOrder = nullptr; pq.viewBase = 0; pq.groupViews = nv;
-        k_query_views<<<dim3((scene->nBoxes + 255) / 256, nv), 256, 0, ctx->stream>>>(pq);
-        ctx->launches++;
-        ORZ_CUDA(cudaGetLastError());
+        if ((e = launch_query(ctx, pq, scene->nBoxes, ctx->stream))) return e;
       }
       continue;
     }
@@ -886,6 +923,7 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
       const bool wantQ = p.visBits || p.clipBits;
       const int groupsC = (pc.viewOrder && wantQ && nv >= 256u) ? orz_context::kGroups : 1;
       if (groupsC > 1) ORZ_CUDA(cudaEventRecord(ctx->evFork, ctx->stream));
+      AuxDrain drain{ctx, groupsC > 1};
       for (int g = 0; g < groupsC; ++g) {
         cudaStream_t st = groupsC > 1 ? ctx->aux[g] : ctx->stream;
         if (groupsC > 1) ORZ_CUDA(cudaStreamWaitEvent(st, ctx->evFork, 0));
@@ -893,16 +931,13 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
         pg.viewBase = (uint32_t)((uint64_t)nv * g / groupsC);
         pg.groupViews = (uint32_t)((uint64_t)nv * (g + 1) / groupsC) - pg.viewBase;
         if ((e = launch_cluster(ctx, pg, pg.groupViews, nv, st))) return e;
-        if (wantQ) {
-          k_query_views<<<dim3((scene->nBoxes + 255) / 256, pg.groupViews), 256, 0, st>>>(pg);
-          ctx->launches++;
-          ORZ_CUDA(cudaGetLastError());
-        }
+        if (wantQ && (e = launch_query(ctx, pg, scene->nBoxes, st))) return e;
         if (groupsC > 1) {
           ORZ_CUDA(cudaEventRecord(ctx->evJoin[g], st));
           ORZ_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evJoin[g], 0));
         }
       }
+      drain.armed = false;
       continue;
     }
     // Sub-batches (by descending cost) on auxiliary streams: the query kernel of a finished
@@ -912,6 +947,7 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
     const int groups = (p.viewOrder && nv >= 64u) ? orz_context::kGroups : 1;
     ORZ_CUDA(cudaMemsetAsync(ctx->d_counter, 0, 4 * orz_context::kGroups, ctx->stream));
     if (groups > 1) ORZ_CUDA(cudaEventRecord(ctx->evFork, ctx->stream));
+    AuxDrain drain{ctx, groups > 1};
     for (int g = 0; g < groups; ++g) {
       cudaStream_t st = groups > 1 ? ctx->aux[g] : ctx->stream;
       if (groups > 1) ORZ_CUDA(cudaStreamWaitEvent(st, ctx->evFork, 0));
@@ -922,16 +958,13 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
       const uint32_t grid = std::min<uint32_t>(pg.groupViews, (uint32_t)(ctx->numSMs * perSM));
       e = launch_views(ctx, GW, trav, pg, grid, st);
       if (e) return e;
-      if (wantQuery) {
-        k_query_views<<<dim3((scene->nBoxes + 255) / 256, pg.groupViews), 256, 0, st>>>(pg);
-        ctx->launches++;
-        ORZ_CUDA(cudaGetLastError());
-      }
+      if (wantQuery && (e = launch_query(ctx, pg, scene->nBoxes, st))) return e;
       if (groups > 1) {
         ORZ_CUDA(cudaEventRecord(ctx->evJoin[g], st));
         ORZ_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evJoin[g], 0));
       }
     }
+    drain.armed = false;
   }
   return ORZ_OK;
 }
@@ -939,6 +972,7 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
 // Host-pointer variant: stage inputs to HBM, render, bring the requested outputs back.
 extern "C" int orz_render_views(orz_context* ctx, orz_scene* scene, const orz_view_batch* hb) {
   if (!ctx || !scene || !hb || !hb->mvps || (!hb->orders && !hb->camPos)) return fail(ORZ_ERR_ARG, "orz_render_views: bad arguments");
+  if (scene->ctx != ctx) return fail(ORZ_ERR_ARG, "orz_render_views: the scene belongs to another context");
   if (hb->nViews == 0) return ORZ_OK;
   ORZ_CUDA(cudaSetDevice(ctx->device));
   const size_t nV = hb->nViews, nOcc = scene->nOcc, blocks = (size_t)(hb->width / 8) * (hb->height / 8);
@@ -989,3 +1023,6 @@ extern "C" int orz_render_views(orz_context* ctx, orz_scene* scene, const orz_vi
   ORZ_CUDA(cudaStreamSynchronize(ctx->stream));
   return ORZ_OK;
 }
+
+// ---- multi-GPU: NCCL all-gather of the per-view visibility bitmasks behind the C ABI
+#include "orz_comm.inl"

@@ -136,7 +136,9 @@ __device__ __forceinline__ void query2d_coop(const Target& T, uint32_t minX, uin
 // queryVisibility for every (view, occludee box) on the finished buffers; Rasterizer.cpp:123-349
 __global__ void __launch_bounds__(256) k_query_views(const FrameParams p) {
   __shared__ ViewMatrices s_vm;
-  const uint32_t view = p.viewOrder ? p.viewOrder[p.viewBase + blockIdx.y] : p.viewBase + blockIdx.y, tid = threadIdx.x;
+  // 1-D grid, view major (grid.y would cap a batch at 65 535 views): CTA = (rank of the view in this launch, chunk of 256 boxes)
+  const uint32_t vrank = blockIdx.x / p.queryChunks, chunk = blockIdx.x - vrank * p.queryChunks;
+  const uint32_t view = p.viewOrder ? p.viewOrder[p.viewBase + vrank] : p.viewBase + vrank, tid = threadIdx.x;
   if (tid < 32) reinterpret_cast<float*>(&s_vm)[tid] = reinterpret_cast<const float*>(p.vmBuf + view)[tid];
   __syncthreads();
   const RcpTable rt{p.rcp, p.rcpShift};
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(256) k_query_views(const FrameParams p) {
   T.width = p.width; T.height = p.height; T.blocksX = p.width >> 3; T.blocksY = p.height >> 3;
   T.depth = p.depth + (size_t)view * p.depthStride;
   T.hiz = p.hiz + (size_t)view * p.hizStride;
-  const uint32_t i = blockIdx.x * blockDim.x + tid;
+  const uint32_t i = chunk * blockDim.x + tid;
   BoxFront f;
   f.status = kBoxCulled; f.minX = f.maxX = f.minY = f.maxY = f.maxZ = 0;
   if (i < p.nBoxes) {

@@ -39,6 +39,48 @@ def interleaved_rows(n_views: int, rank: int, world: int):
     return np.arange(rank, n_views, world), per
 
 
+def make_comm(ctx):
+    """The product's own NCCL communicator (C ABI: orz_comm_create) for this rank's context.  torch.distributed is
+    only the rendezvous: rank 0's 128-byte NCCL id travels through broadcast_object_list."""
+    import torch.distributed as dist
+
+    from . import api
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [api.Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return api.Comm(ctx, world, rank, box[0])
+
+
+def render_views_gathered(scene, comm, width, height, mvps, cam_pos, flags=0, overlapped=False):
+    """Device-resident flavour of render_views_sharded through the C ABI only: views dealt round-robin, rendered with
+    orz_render_views_device into a torch buffer, gathered with orz_gather_bits (NCCL all-gather on the context stream,
+    or beside it when `overlapped`).  Returns a torch int32 tensor [n_views, words] on the GPU, identical on all ranks."""
+    import torch
+
+    from . import api
+
+    rank, world = comm.rank, comm.n_ranks
+    dev = torch.device("cuda", scene.ctx.device)
+    mvps = np.ascontiguousarray(mvps, np.float32).reshape(-1, 16)
+    n = mvps.shape[0]
+    idx, per = interleaved_rows(n, rank, world)
+    words = (scene.n_boxes + 31) // 32
+    d_mvp = torch.from_numpy(np.ascontiguousarray(mvps[idx])).to(dev)
+    d_pos = torch.from_numpy(np.ascontiguousarray(np.asarray(cam_pos, np.float32).reshape(-1, 3)[idx])).to(dev)
+    local = torch.zeros((per, words), dtype=torch.int32, device=dev)
+    gathered = torch.empty((world, per, words), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize(dev)
+    if idx.size:
+        b = api.ViewBatch()
+        b.width, b.height, b.nViews, b.flags = width, height, int(idx.size), flags
+        b.mvps, b.camPos, b.visBits = d_mvp.data_ptr(), d_pos.data_ptr(), local.data_ptr()
+        scene.render_views_raw(b, device=True)
+    comm.gather_bits(local.data_ptr(), per * words, gathered.data_ptr(), overlapped=overlapped)
+    comm.synchronize()
+    return gathered.transpose(0, 1).reshape(per * world, words)[:n].contiguous()  # row r * per + i holds view i * world + r
+
+
 def render_views_sharded(scene, width, height, mvps, cam_pos=None, orders=None, flags=0, device=None, balance="contiguous"):
     """Render rank's slice of `mvps` through the C ABI and gather every view's visibility bitmask.
     Returns a torch int32 tensor [n_views, words] identical on all ranks.  balance="interleaved"

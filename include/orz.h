@@ -223,10 +223,12 @@ int orz_comm_group_end(void);
  * after the render calls enqueued before it. */
 int orz_gather_bits(orz_comm* comm, const uint32_t* localBits, size_t wordsPerRank, uint32_t* allBits);
 /* The same on the communicator's own stream, beside whatever the context enqueues next (the next batch): the buffers
- * must stay untouched until orz_comm_join (the context stream waits for the gathers issued so far) or
+ * must stay untouched until orz_comm_join (the context stream waits for the gathers issued so far), orz_comm_join_older
+ * (... for all but the most recent one: call it before rendering into a buffer pair again when two pairs rotate) or
  * orz_comm_synchronize (the host waits for both streams). */
 int orz_gather_bits_overlapped(orz_comm* comm, const uint32_t* localBits, size_t wordsPerRank, uint32_t* allBits);
 int orz_comm_join(orz_comm* comm);
+int orz_comm_join_older(orz_comm* comm);
 int orz_comm_synchronize(orz_comm* comm);
 
 #ifdef __cplusplus

@@ -110,6 +110,7 @@ EXPORTS = {
     "orz_gather_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "orz_gather_bits_overlapped": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "orz_comm_join": (C.c_int, [C.c_void_p]),
+    "orz_comm_join_older": (C.c_int, [C.c_void_p]),
     "orz_comm_synchronize": (C.c_int, [C.c_void_p]),
 }
 COMM_ID_BYTES = 128
@@ -548,6 +549,9 @@ class Comm:
 
     def join(self):
         _check(lib().orz_comm_join(self.h))
+
+    def join_older(self):
+        _check(lib().orz_comm_join_older(self.h))
 
     def synchronize(self):
         _check(lib().orz_comm_synchronize(self.h))

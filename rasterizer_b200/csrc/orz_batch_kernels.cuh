@@ -89,6 +89,38 @@ __global__ void __launch_bounds__(128) k_prepare_views(const FrameParams p) {
   if (tid == 0) p.viewCost[view] = s_cost;
 }
 
+// Front-to-back order for scenes with many occluders (config 4: ~10 000 batches): the rank sort of k_prepare_views is
+// quadratic inside ONE CTA per view, so it is spread over the GPU instead -- keys once, then one thread per
+// (view, occluder) counts the keys in front of it from shared-memory tiles.  Same key arithmetic, same tie rule.
+__global__ void __launch_bounds__(256) k_order_keys(const FrameParams p, float* __restrict__ keys) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)p.nViews * p.nOcc) return;
+  const uint32_t view = (uint32_t)(i / p.nOcc), o = (uint32_t)(i - (size_t)view * p.nOcc);
+  const float cx = p.camPos[3 * (size_t)view + 0], cy = p.camPos[3 * (size_t)view + 1], cz = p.camPos[3 * (size_t)view + 2];
+  const float* c = p.occ[o].center;
+  const float dx = c[0] - cx, dy = c[1] - cy, dz = c[2] - cz;
+  keys[i] = (dx * dx + dy * dy) + dz * dz;
+}
+__global__ void __launch_bounds__(256) k_order_rank(const FrameParams p, const float* __restrict__ keys, uint32_t chunksPerView) {
+  __shared__ float s_keys[1024];
+  const uint32_t view = blockIdx.x / chunksPerView, chunk = blockIdx.x - view * chunksPerView, tid = threadIdx.x;
+  const float* vk = keys + (size_t)view * p.nOcc;
+  const uint32_t i = chunk * 256u + tid;
+  const float ki = i < p.nOcc ? vk[i] : 0.0f;
+  uint32_t rank = 0;
+  for (uint32_t j0 = 0; j0 < p.nOcc; j0 += 1024u) {
+    const uint32_t n = min(1024u, p.nOcc - j0);
+    __syncthreads();
+    for (uint32_t j = tid; j < n; j += 256u) s_keys[j] = vk[j0 + j];
+    __syncthreads();
+    for (uint32_t j = 0; j < n; ++j) {
+      const float kj = s_keys[j];
+      rank += (kj < ki || (kj == ki && j0 + j < i)) ? 1u : 0u;
+    }
+  }
+  if (i < p.nOcc) p.orderBuf[(size_t)view * p.nOcc + rank] = i;
+}
+
 // views by descending cost, ties by index (rank sort; nViews is at most a few thousand per chunk)
 __global__ void __launch_bounds__(256) k_sort_views(const uint32_t* __restrict__ cost, uint32_t n, uint32_t* __restrict__ order) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -54,12 +54,16 @@ constexpr uint32_t kStageCap = 32;           // records a warp stages at a time
 constexpr uint32_t kClusterMaxOcc = 2048;    // occluders per scene the cluster path accepts (shared-memory decision arrays)
 constexpr uint32_t kHeadWords = 6;           // status, minX, maxX, minY, maxY, maxZ of kFrontWords
 
+constexpr uint32_t kTileWords = 32u * 32u;     // the open tile's depth: 32 blocks x 128 B, [block][item (rr, i), swizzled][row pair k]
+constexpr uint32_t kTileAuxWords = 64u + 32u + 8u;  // + per block: 64-bit coverage mask of the current primitive, HiZ after the update; covered blocks in order (bytes)
+
 struct ClusterSmem {
   static constexpr uint32_t kLutWords = ORZ_CLUSTER_LUT_SMEM ? 4096 * 2 : 0;
+  static constexpr uint32_t kTileAllWords = kClusterGW * (kTileWords + kTileAuxWords);
   static constexpr uint32_t kStageWords = kClusterGW * kStageCap * kRecStride;
   static constexpr uint32_t kIdxWords = kClusterGW * kStageCap;
   static constexpr uint32_t kChainWords = kClusterGW * 12 * kChainStride;
-  static constexpr uint32_t kFixedWords = kLutWords + kStageWords + kIdxWords + kChainWords;
+  static constexpr uint32_t kFixedWords = kLutWords + kTileAllWords + kStageWords + kIdxWords + kChainWords;
   // + [nOcc][6] gate heads, 3 x [nOcc] decision words, [GW][K][32] u16 HiZ mirror
   static size_t bytes(uint32_t tilesPerWarp, uint32_t nOcc) {
     return (size_t)(kFixedWords + nOcc * (kHeadWords + 3u)) * 4 + (size_t)kClusterGW * tilesPerWarp * 32 * 2;
@@ -213,7 +217,7 @@ __device__ __forceinline__ void step_chain(float cur, const float incX, const fl
 // blocks).  d[8] / h are the lane's block and its HiZ, kept in registers between primitives.
 __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, const int lane, const uint32_t x0, const uint32_t y0,
                                           const uint32_t x1, const uint32_t y1, const uint2* __restrict__ lut, float* __restrict__ sm,
-                                          uint4 (&d)[8], uint32_t& h, bool& dirty) {
+                                          uint4* __restrict__ tile, uint32_t* __restrict__ aux, uint32_t& h, bool& dirty) {
   const uint32_t w0 = rec[0], w1 = rec[1], w2 = rec[2];
   const uint32_t minX = w0 & 0xffffu, minY = w0 >> 16, maxZ = w2 & 0xffffu, mode = w2 >> 16;
   const uint32_t xa = max(minX, x0), xb = min(minX + (w1 & 0xffffu), x1), ya = max(minY, y0), yb = min(minY + (w1 >> 16), y1);
@@ -269,6 +273,10 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
     }
   }
   const uint32_t updMask = __ballot_sync(kFull, upd);
+  if (upd) {
+    reinterpret_cast<uint2*>(aux)[lane] = mk;  // the eight lanes that will share this block read their half of it
+    reinterpret_cast<uint8_t*>(aux + 96u)[__popc(updMask & ((1u << lane) - 1u))] = (uint8_t)lane;  // covered blocks, compacted
+  }
   __syncwarp();  // orders this primitive's reads of the edge slots before the next primitive's writes (free: the warp is converged)
   if (!updMask) return;
   {  // the eight depth lanes (Rasterizer.cpp:1103-1112) at the covered blocks
@@ -282,50 +290,46 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
     step_chain(cur, dzdx, dzdy, y0 + rLo - minY, r - rLo, x0 + cA - minX + rec[20], cA, cB, active, sm + (4u + l) * kChainStride + r * 8u);
   }
   __syncwarp();
-  // ---- depth rows, merge into the registers, HiZ (Rasterizer.cpp:1241-1290)
-  if (upd) {
-    const float* smd = sm + 4 * kChainStride + lane;
-    const uint32_t keep = h != 1u ? 0xffffffffu : 0u;  // a cleared block is overwritten (:1271-1278)
-    uint32_t r0[2][4], r4[2][4], r8[2][4];
+  // ---- depth rows, merge, HiZ (Rasterizer.cpp:1241-1290): the covered blocks of the tile FOUR AT A TIME, eight lanes
+  // per block -- lane (rr, i) of a group builds pixels 2i, 2i+1 of rows rr, 2+rr, 4+rr, 6+rr (orz_pixel.h: the eight
+  // items of a block share no arithmetic), so a primitive that covers n blocks costs ceil(n / 4) short passes at
+  // (nearly) full width instead of one long pass with 32 - n idle lanes
+  {
+    const uint32_t it = (uint32_t)lane & 7u, g = (uint32_t)lane >> 3, rr = it >> 2, i = it & 3u;
+    const float* c0 = sm + (4u + item_lane0(rr, i)) * kChainStride;
+    const float* c1 = sm + (4u + item_lane1(rr, i)) * kChainStride;
+    const uint32_t shift = item_mask_shift(rr, i), half = i >> 1;
+    uint32_t* hNew = aux + 64u;
+    const uint8_t* covered = reinterpret_cast<const uint8_t*>(aux + 96u);
+    const uint32_t n = (uint32_t)__popc(updMask);
+    for (uint32_t j = g; j < n + g; j += 4u) {  // (n + g: every group makes the same number of passes -- the shuffles below are full width)
+      const uint32_t b = j < n ? (uint32_t)covered[j] : 32u;  // block (= owner lane) this group of eight lanes takes in this pass
+      uint32_t mn = 0xffffffffu;
+      if (b < 32u) {
+        uint4* slot = tile + b * 8u + (it ^ (b & 7u));
+        uint4 d = *slot;
+        mn = update_item(c0[b], c1[b], dzdx, dzdy, i >= 2u, aux[2u * b + half] >> shift, d.x, d.y, d.z, d.w);
+        *slot = d;
+      }
+      mn = __vminu2(mn, __shfl_xor_sync(kFull, mn, 1));
+      mn = __vminu2(mn, __shfl_xor_sync(kFull, mn, 2));
+      mn = __vminu2(mn, __shfl_xor_sync(kFull, mn, 4));
+      if (it == 0u && b < 32u) hNew[b] = min(mn & 0xffffu, mn >> 16);  // Rasterizer.cpp:1287-1290
+    }
+    __syncwarp();
+    if (upd) {
+      h = hNew[lane];
+      dirty = true;
+      // HiZ 1 is the cleared marker: the reference's next update of such a block overwrites it (Rasterizer.cpp:1271-1278),
+      // which for the max-merge means its stored depth is zero from now on
+      if (h == 1u) {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      float dv[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) dv[k] = smd[(4 * rr + k) * kChainStride];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float a = dv[(2 * i) & 3], b = dv[(2 * i + 1) & 3];
-        if (i >= 2) { a = ORZ_FMA(dzdx, 0.5f, a); b = ORZ_FMA(dzdx, 0.5f, b); }  // depth1, :1243
-        const float a8 = dzdy + a, b8 = dzdy + b;                                // depth8/9, :1244-1245
-        r0[rr][i] = pack16(a) | (pack16(b) << 16);  // (a run-time "finite plane" shortcut for the NaN guard was measured slower)
-        r8[rr][i] = pack16(a8) | (pack16(b8) << 16);
-        r4[rr][i] = avg_u16x2(r0[rr][i], r8[rr][i]);                             // :1252
+        for (uint32_t t = 0; t < 8u; ++t) tile[(uint32_t)lane * 8u + t] = z;
       }
     }
-    uint32_t mnAcc = 0xffffffffu;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int y = 2 * k + rr;
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          w[i] = k == 0 ? r0[rr][i] : k == 2 ? r4[rr][i] : k == 1 ? avg_u16x2(r0[rr][i], r4[rr][i]) : avg_u16x2(r4[rr][i], r8[rr][i]);  // :1253-1254
-        const int ky = (rr ? 0 : 4) + k;  // pixel px of row y <-> bit 8 px + ky (:1257-1268)
-        const uint32_t lo = ((mk.x >> ky) & 0x01010101u) * 0xffu, hi = ((mk.y >> ky) & 0x01010101u) * 0xffu;
-        uint4 v;
-        v.x = __vmaxu2(w[0] & __byte_perm(lo, 0u, 0x1100), d[y].x & keep);
-        v.y = __vmaxu2(w[1] & __byte_perm(lo, 0u, 0x3322), d[y].y & keep);
-        v.z = __vmaxu2(w[2] & __byte_perm(hi, 0u, 0x1100), d[y].z & keep);
-        v.w = __vmaxu2(w[3] & __byte_perm(hi, 0u, 0x3322), d[y].w & keep);
-        d[y] = v;
-        mnAcc = __vminu2(mnAcc, __vminu2(__vminu2(v.x, v.y), __vminu2(v.z, v.w)));
-      }
-    h = min(mnAcc & 0xffffu, mnAcc >> 16);  // Rasterizer.cpp:1287-1290
-    dirty = true;
   }
-  __syncwarp();  // chain slots are rewritten by the next primitive
+  __syncwarp();  // chain slots, masks and the tile are rewritten / read by the next primitive
 }
 
 template <int C>
@@ -337,7 +341,8 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
   constexpr uint32_t GW = kClusterGW, NT = GW * 32, kWarps = C * GW;
   extern __shared__ __align__(16) uint32_t s_dyn[];
   uint2* s_lut = reinterpret_cast<uint2*>(s_dyn);
-  uint32_t* s_stageAll = s_dyn + ClusterSmem::kLutWords;
+  uint32_t* s_tileAll = s_dyn + ClusterSmem::kLutWords;  // [GW] tiles (16-byte aligned), then [GW] mask / HiZ scratch
+  uint32_t* s_stageAll = s_tileAll + ClusterSmem::kTileAllWords;
   uint32_t* s_idxAll = s_stageAll + ClusterSmem::kStageWords;
   float* s_chain = reinterpret_cast<float*>(s_idxAll + ClusterSmem::kIdxWords);
   uint32_t* s_head = s_dyn + ClusterSmem::kFixedWords;     // [nOcc][6]: status + gate rectangle of every order slot
@@ -373,6 +378,8 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
   float* myChain = s_chain + warp * (12 * kChainStride);
   uint32_t* myStage = s_stageAll + (uint32_t)warp * kStageCap * kRecStride;
   uint32_t* myIdx = s_idxAll + (uint32_t)warp * kStageCap;
+  uint4* myTile = reinterpret_cast<uint4*>(s_tileAll + (uint32_t)warp * kTileWords);
+  uint32_t* myAux = s_tileAll + (uint32_t)GW * kTileWords + (uint32_t)warp * kTileAuxWords;
   const uint32_t lx = (uint32_t)lane & 7u, ly = (uint32_t)lane >> 3;
   const bool reporter = rank == 0u && warp == 0 && lane == 0;  // writes the per-slot outputs of the view
 
@@ -489,24 +496,44 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
         }
         uint32_t hits = __ballot_sync(kFull, touches);
         if (!hits) continue;
-        // bring the tile into registers
+        // open the tile: its depth goes to shared memory, one block per lane, as 8 items (rr, i) of 4 row pairs each
+        // (item slot swizzled by the block so that both this lane-per-block pass and the eight-lanes-per-block
+        // update passes are bank-conflict free); cleared blocks (HiZ 1) enter as zero
         const uint32_t bx = x0 + lx, by = y0 + ly;
         const bool inScreen = bx < x1 && by < y1;
         uint4* dp = reinterpret_cast<uint4*>(T.depth) + (size_t)(by * T.blocksX + bx) * 8u;
         uint32_t h = inScreen ? (uint32_t)myHiz[32u * k] : 0xffffu;  // off-screen lanes never pass
         const bool load = inScreen && h != 1u;
-        uint4 d[8];
+        uint4* mine = myTile + (uint32_t)lane * 8u;
+        const uint32_t sw = (uint32_t)lane & 7u;
 #pragma unroll
-        for (int y = 0; y < 8; ++y) d[y] = load ? dp[y] : make_uint4(0u, 0u, 0u, 0u);
+        for (uint32_t rr = 0; rr < 2u; ++rr) {
+          uint4 R[4];
+#pragma unroll
+          for (uint32_t kk = 0; kk < 4u; ++kk) R[kk] = load ? dp[2u * kk + rr] : make_uint4(0u, 0u, 0u, 0u);
+          mine[(rr * 4u + 0u) ^ sw] = make_uint4(R[0].x, R[1].x, R[2].x, R[3].x);
+          mine[(rr * 4u + 1u) ^ sw] = make_uint4(R[0].y, R[1].y, R[2].y, R[3].y);
+          mine[(rr * 4u + 2u) ^ sw] = make_uint4(R[0].z, R[1].z, R[2].z, R[3].z);
+          mine[(rr * 4u + 3u) ^ sw] = make_uint4(R[0].w, R[1].w, R[2].w, R[3].w);
+        }
+        __syncwarp();
         bool dirty = false;
         for (; hits; hits &= hits - 1u)
-          tile_prim(myStage + ((uint32_t)__ffs((int)hits) - 1u) * kRecStride, lane, x0, y0, x1, y1, ORZ_CLUSTER_LUT_SMEM ? s_lut : p.lut, myChain, d, h, dirty);
-        if (dirty) {
+          tile_prim(myStage + ((uint32_t)__ffs((int)hits) - 1u) * kRecStride, lane, x0, y0, x1, y1, ORZ_CLUSTER_LUT_SMEM ? s_lut : p.lut, myChain, myTile,
+                    myAux, h, dirty);
+        if (dirty) {  // close: the blocks this occluder changed go back to HBM / L2 in the reference's row layout
 #pragma unroll
-          for (int y = 0; y < 8; ++y) dp[y] = d[y];
+          for (uint32_t rr = 0; rr < 2u; ++rr) {
+            const uint4 I0 = mine[(rr * 4u + 0u) ^ sw], I1 = mine[(rr * 4u + 1u) ^ sw], I2 = mine[(rr * 4u + 2u) ^ sw], I3 = mine[(rr * 4u + 3u) ^ sw];
+            dp[0u + rr] = make_uint4(I0.x, I1.x, I2.x, I3.x);
+            dp[2u + rr] = make_uint4(I0.y, I1.y, I2.y, I3.y);
+            dp[4u + rr] = make_uint4(I0.z, I1.z, I2.z, I3.z);
+            dp[6u + rr] = make_uint4(I0.w, I1.w, I2.w, I3.w);
+          }
           myHiz[32u * k] = (uint16_t)h;
           T.hiz[by * T.blocksX + bx] = (uint16_t)h;
         }
+        __syncwarp();  // the next tile's open overwrites the slots other lanes may still be reading
       }
       __syncwarp();
       nStaged = 0;

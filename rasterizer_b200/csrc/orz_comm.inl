@@ -76,13 +76,14 @@ struct orz_comm {
   NcclComm comm;
   int nRanks, rank;
   cudaStream_t side = nullptr;            // overlapped gathers run here
-  cudaEvent_t evReady = nullptr, evDone = nullptr;
-  bool pending = false;                   // an overlapped gather has been issued since the last join
+  cudaEvent_t evReady = nullptr, evDone[2] = {nullptr, nullptr};  // completion of overlapped gather k: evDone[k & 1]
+  uint64_t issued = 0, joined = 0;        // overlapped gathers issued / the context stream already waits for
 };
 static int comm_streams(orz_comm* c) {
   ORZ_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
   ORZ_CUDA(cudaEventCreateWithFlags(&c->evReady, cudaEventDisableTiming));
-  ORZ_CUDA(cudaEventCreateWithFlags(&c->evDone, cudaEventDisableTiming));
+  ORZ_CUDA(cudaEventCreateWithFlags(&c->evDone[0], cudaEventDisableTiming));
+  ORZ_CUDA(cudaEventCreateWithFlags(&c->evDone[1], cudaEventDisableTiming));
   return ORZ_OK;
 }
 
@@ -129,7 +130,8 @@ extern "C" void orz_comm_destroy(orz_comm* c) {
   cudaStreamSynchronize(c->ctx->stream);
   if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
   if (c->evReady) cudaEventDestroy(c->evReady);
-  if (c->evDone) cudaEventDestroy(c->evDone);
+  if (c->evDone[0]) cudaEventDestroy(c->evDone[0]);
+  if (c->evDone[1]) cudaEventDestroy(c->evDone[1]);
   if (c->comm && nccl_api().handle) nccl_api().CommDestroy(c->comm);
   delete c;
 }
@@ -165,23 +167,32 @@ extern "C" int orz_gather_bits_overlapped(orz_comm* c, const uint32_t* localBits
   ORZ_CUDA(cudaEventRecord(c->evReady, c->ctx->stream));
   ORZ_CUDA(cudaStreamWaitEvent(c->side, c->evReady, 0));
   ORZ_NCCL(nccl_api().AllGather(localBits, allBits, wordsPerRank, 3 /* ncclUint32 */, c->comm, c->side));
-  ORZ_CUDA(cudaEventRecord(c->evDone, c->side));
-  c->pending = true;
+  ORZ_CUDA(cudaEventRecord(c->evDone[c->issued & 1u], c->side));
+  c->issued++;
+  return ORZ_OK;
+}
+// the context stream waits for the overlapped gathers issued so far -- all of them, or (keepNewest) all but the most
+// recent one: with two buffer pairs in rotation, "join older" before rendering into a pair again is all the ordering needed
+static int comm_join(orz_comm* c, uint64_t upTo) {
+  if (upTo <= c->joined) return ORZ_OK;
+  ORZ_CUDA(cudaSetDevice(c->ctx->device));
+  ORZ_CUDA(cudaStreamWaitEvent(c->ctx->stream, c->evDone[(upTo - 1u) & 1u], 0));  // the side stream is in order: gather upTo-1 done => all earlier done
+  c->joined = upTo;
   return ORZ_OK;
 }
 extern "C" int orz_comm_join(orz_comm* c) {
   if (!c) return fail(ORZ_ERR_ARG, "orz_comm_join: communicator is NULL");
-  if (!c->pending) return ORZ_OK;
-  ORZ_CUDA(cudaSetDevice(c->ctx->device));
-  ORZ_CUDA(cudaStreamWaitEvent(c->ctx->stream, c->evDone, 0));
-  c->pending = false;
-  return ORZ_OK;
+  return comm_join(c, c->issued);
+}
+extern "C" int orz_comm_join_older(orz_comm* c) {
+  if (!c) return fail(ORZ_ERR_ARG, "orz_comm_join_older: communicator is NULL");
+  return c->issued ? comm_join(c, c->issued - 1u) : ORZ_OK;
 }
 extern "C" int orz_comm_synchronize(orz_comm* c) {
   if (!c) return fail(ORZ_ERR_ARG, "orz_comm_synchronize: communicator is NULL");
   ORZ_CUDA(cudaSetDevice(c->ctx->device));
   ORZ_CUDA(cudaStreamSynchronize(c->side));
   ORZ_CUDA(cudaStreamSynchronize(c->ctx->stream));
-  c->pending = false;
+  c->joined = c->issued;
   return ORZ_OK;
 }

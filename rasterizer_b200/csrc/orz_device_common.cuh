@@ -45,8 +45,7 @@ __device__ __forceinline__ void prefetch_line(const void* p) {
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// avg_epu16 on two packed halves: (a + b + 1) >> 1 without overflow
-__device__ __forceinline__ uint32_t avg_u16x2(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) >> 1) & 0x7fff7fffu); }
+// (avg_u16x2 and the other packed-u16 helpers: orz_pixel.h)
 
 
 constexpr int kFrontWords = 20;  // status, minX, maxX, minY, maxY, maxZ, CallMatrix (14 floats)

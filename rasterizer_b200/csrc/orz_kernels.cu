@@ -26,6 +26,7 @@
 
 #include "../../include/orz.h"
 #include "orz_core.h"
+#include "orz_pixel.h"
 #include "orz_host.h"
 
 #ifndef ORZ_PREFETCH_LEVEL
@@ -86,6 +87,7 @@ int orz::set_error(int code, const std::string& msg) { return fail(code, msg); }
 struct orz_context {
   int device = 0;
   int numSMs = 0;
+  size_t maxSmemOptin = 0;  // largest dynamic shared memory a CTA may ask for on this device
   cudaStream_t stream = nullptr;
   uint2* d_lut = nullptr;
   uint32_t* d_rcp = nullptr;
@@ -156,6 +158,7 @@ extern "C" int orz_context_create(int device, orz_context** out) {
   cudaDeviceProp prop;
   ORZ_CUDA_OR(orz_context_destroy(ctx), cudaGetDeviceProperties(&prop, device));
   ctx->numSMs = prop.multiProcessorCount;
+  ctx->maxSmemOptin = prop.sharedMemPerBlockOptin;
   ctx->arenaBudget = std::min<size_t>(size_t(24) << 30, prop.totalGlobalMem / 6);
   ORZ_CUDA_OR(orz_context_destroy(ctx), cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ORZ_CUDA_OR(orz_context_destroy(ctx), cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
@@ -743,19 +746,29 @@ static int launch_cluster_t(orz_context* ctx, FrameParams p, uint32_t nViews, ui
   return ORZ_OK;
 }
 // one cluster per view.  Cluster size: as many CTAs as the view can use (one tile per warp) while all
-// views of the batch still fit the GPU in one wave; at least enough that a warp owns <= 32 tiles.
-static int launch_cluster(orz_context* ctx, const FrameParams& p, uint32_t nViews, uint32_t nBatch, cudaStream_t st) {
-  const uint32_t nTiles = (((p.width >> 3) + kTileW - 1u) / kTileW) * (((p.height >> 3) + kTileH - 1u) / kTileH);
+// views of the batch still fit the GPU in one wave; at least enough that a warp owns <= 32 tiles and the CTA's
+// shared memory (tables, staging, the open tiles, decision words of every occluder, HiZ mirror) fits.
+// Returns 0 when no cluster size works: the caller stays on the large-batch kernel.
+static uint32_t pick_cluster_size(const orz_context* ctx, uint32_t width, uint32_t height, uint32_t nOcc, uint32_t nBatch) {
+  const uint32_t nTiles = (((width >> 3) + kTileW - 1u) / kTileW) * (((height >> 3) + kTileH - 1u) / kTileH);
+  auto tilesPerWarp = [&](uint32_t c) { return (nTiles + c * kClusterGW - 1u) / (c * kClusterGW); };
+  auto fits = [&](uint32_t c) { return tilesPerWarp(c) <= 32u && ClusterSmem::bytes(tilesPerWarp(c), nOcc) <= ctx->maxSmemOptin; };
   uint32_t c = 1;
   while (c < 16u && c * kClusterGW < nTiles && nBatch * c * 2u <= (uint32_t)ctx->numSMs) c *= 2u;
-  while (c < 16u && (nTiles + c * kClusterGW - 1u) / (c * kClusterGW) > 32u) c *= 2u;
   if (ctx->clusterSize) c = (uint32_t)ctx->clusterSize;
-  if ((nTiles + c * kClusterGW - 1u) / (c * kClusterGW) > 32u) return fail(ORZ_ERR_ARG, "cluster path: target too large for this cluster size");
+  else while (c < 16u && !fits(c)) c *= 2u;
+  return fits(c) ? c : 0u;
+}
+static int launch_cluster(orz_context* ctx, const FrameParams& p, uint32_t nViews, uint32_t nBatch, cudaStream_t st) {
+  const uint32_t nTiles = (((p.width >> 3) + kTileW - 1u) / kTileW) * (((p.height >> 3) + kTileH - 1u) / kTileH);
+  const uint32_t c = pick_cluster_size(ctx, p.width, p.height, p.nOcc, nBatch);
+  if (!c) return fail(ORZ_ERR_ARG, "cluster path: target too large (or too many occluders) for this cluster size");
   switch (c) {
     case 16:  // non-portable cluster size: when the device (e.g. a partitioned one) cannot place it, use 8
       if (launch_cluster_t<16>(ctx, p, nViews, nTiles, st) == ORZ_OK) return ORZ_OK;
       (void)cudaGetLastError();
-      if ((nTiles + 8u * kClusterGW - 1u) / (8u * kClusterGW) > 32u) return fail(ORZ_ERR_CUDA, "cluster path: 16-CTA clusters are not available on this device");
+      if ((nTiles + 8u * kClusterGW - 1u) / (8u * kClusterGW) > 32u || ClusterSmem::bytes((nTiles + 8u * kClusterGW - 1u) / (8u * kClusterGW), p.nOcc) > ctx->maxSmemOptin)
+        return fail(ORZ_ERR_CUDA, "cluster path: 16-CTA clusters are not available on this device");
       return launch_cluster_t<8>(ctx, p, nViews, nTiles, st);
     case 8: return launch_cluster_t<8>(ctx, p, nViews, nTiles, st);
     case 4: return launch_cluster_t<4>(ctx, p, nViews, nTiles, st);
@@ -859,8 +872,20 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
     const uint32_t clusterLimit = std::min<uint32_t>((uint32_t)ctx->clusterViews, 65535u);  // k_setup_views puts the view on grid.y
     const size_t nTilesC = (size_t)((b->width / 8 + kTileW - 1) / kTileW) * ((b->height / 8 + kTileH - 1) / kTileH);
     const bool clusterPath = !wide && ctx->clusterViews > 0 && nv <= clusterLimit && nTilesC <= 32u * 16u * kClusterGW && nOcc <= kClusterMaxOcc &&
+                             pick_cluster_size(ctx, b->width, b->height, (uint32_t)nOcc, nv) != 0u &&
                              (size_t)nv * scene->totalQuads * (blocks > 65536u ? 2 : 1) * (kRecStride * 4 + 8) <= (size_t(8) << 30);
     p.viewOrder = (nv <= 16384u && !(clusterPath && nv * 2u <= (uint32_t)ctx->numSMs)) ? p.viewCost + chunk : nullptr;
+    if (!p.orders && nOcc > 1024u) {  // many occluders: order them on the whole GPU (keys live in the front buffer until k_prepare_views overwrites it)
+      float* keys = reinterpret_cast<float*>(p.frontBuf);
+      const size_t nKeys = (size_t)nv * nOcc;
+      const uint32_t chunksPerView = (uint32_t)((nOcc + 255u) / 256u);
+      if (nKeys / 256u + 1u > 0x7fffffffull || (size_t)nv * chunksPerView > 0x7fffffffull) return fail(ORZ_ERR_ARG, "batch too large for the device-side occluder sort");
+      k_order_keys<<<(uint32_t)((nKeys + 255u) / 256u), 256, 0, ctx->stream>>>(p, keys);
+      k_order_rank<<<nv * chunksPerView, 256, 0, ctx->stream>>>(p, keys, chunksPerView);
+      ctx->launches += 2;
+      ORZ_CUDA(cudaGetLastError());
+      p.orders = p.orderBuf;
+    }
     k_prepare_views<<<nv, 128, 0, ctx->stream>>>(p);
     ctx->launches++;
     ORZ_CUDA(cudaGetLastError());

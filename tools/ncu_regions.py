@@ -15,7 +15,7 @@ marks = [
     ("tile_prim: HiZ test + chain set-up", "__device__ __forceinline__ void tile_prim("),
     ("tile_prim: coverage (edge masks)", "// ---- coverage (Rasterizer.cpp:1155-1239)"),
     ("tile_prim: depth chains set-up", "const uint32_t updMask = "),
-    ("tile_prim: depth rows + merge + HiZ", "// ---- depth rows, merge into the registers"),
+    ("tile_prim: depth rows + merge + HiZ", "// ---- depth rows, merge, HiZ (Rasterizer.cpp:1241-1290)"),
     ("kernel prologue (tables, clear)", "k_raster_views_cluster(const FrameParams p) {"),
     ("pre-announce loop", "// ---- candidates whose rectangle does not touch my tiles"),
     ("walk: slot bookkeeping", "  uint32_t quadsSubmitted = 0;"),
@@ -23,7 +23,7 @@ marks = [
     ("decision wait (spin)", "// visible as soon as ONE warp says so"),
     ("occluder prologue (info, box)", "// ---- rasterize<clipped>(occluder): the records k_setup_views wrote"),
     ("flush: gather + tile loop", "    auto flush = [&]() {"),
-    ("flush: tile open (load)", "// bring the tile into registers"),
+    ("flush: tile open (load)", "// open the tile: its depth goes to shared memory"),
     ("flush: tile close (store)", "        if (dirty) {"),
     ("header scan + staging", "    for (uint32_t r0 = 0; r0 < cnt; r0 += 32u) {"),
     ("epilogue (zero fill, final barrier)", "  if (p.quadsSubmitted && reporter)"),

@@ -44,13 +44,28 @@
 #ifndef ORZ_CLUSTER_CTAS_PER_SM
 #define ORZ_CLUSTER_CTAS_PER_SM 0  // > 0: compile with __launch_bounds__(threads, this) instead of the register cap
 #endif
+#ifndef ORZ_TILE_SMEM
+#define ORZ_TILE_SMEM 1  // 1: the open tile lives in shared memory, eight lanes per covered block; 0: in registers, one lane per block
+#endif
+#ifndef ORZ_TILE_PREFETCH
+#define ORZ_TILE_PREFETCH 1  // flush: prefetch the next tile's depth blocks into L1 while the current tile is processed
+#endif
+#ifndef ORZ_FLAG_VOTE
+#define ORZ_FLAG_VOTE 1  // decision words are observed through a warp vote (uniform control flow around the collectives)
+#endif
+#ifndef ORZ_HDR_PREFETCH_EARLY
+#define ORZ_HDR_PREFETCH_EARLY 1  // record headers of a candidate are prefetched before its gate test (0: after the decision)
+#endif
 #ifndef ORZ_CLUSTER_REGS
-#define ORZ_CLUSTER_REGS 96  // 16 warps x 96 registers leave room for one CTA of the query kernel on the same SM
+#define ORZ_CLUSTER_REGS 128  // 16 warps x 128 registers = the whole register file: measured faster than leaving room for a query CTA (96) in every case (profiles/r2_variants.txt)
 #endif
 constexpr int kClusterGW = ORZ_CLUSTER_GW;  // warps per CTA of the cluster kernel; registers per thread capped so that they fit one SM
 constexpr uint32_t kTileW = 8, kTileH = 4;   // blocks per tile: lane = 8 * (row in tile) + column in tile
 constexpr uint32_t kChainStride = 33;        // words between two chains' slots: the publishing lanes (chain, tile row) hit 32 different banks
-constexpr uint32_t kStageCap = 32;           // records a warp stages at a time
+#ifndef ORZ_STAGE_CAP
+#define ORZ_STAGE_CAP 32
+#endif
+constexpr uint32_t kStageCap = ORZ_STAGE_CAP;  // records a warp stages at a time (<= 32: one lane per staged record)
 constexpr uint32_t kClusterMaxOcc = 2048;    // occluders per scene the cluster path accepts (shared-memory decision arrays)
 constexpr uint32_t kHeadWords = 6;           // status, minX, maxX, minY, maxY, maxZ of kFrontWords
 
@@ -59,7 +74,7 @@ constexpr uint32_t kTileAuxWords = 64u + 32u + 8u;  // + per block: 64-bit cover
 
 struct ClusterSmem {
   static constexpr uint32_t kLutWords = ORZ_CLUSTER_LUT_SMEM ? 4096 * 2 : 0;
-  static constexpr uint32_t kTileAllWords = kClusterGW * (kTileWords + kTileAuxWords);
+  static constexpr uint32_t kTileAllWords = ORZ_TILE_SMEM ? kClusterGW * (kTileWords + kTileAuxWords) : 0;
   static constexpr uint32_t kStageWords = kClusterGW * kStageCap * kRecStride;
   static constexpr uint32_t kIdxWords = kClusterGW * kStageCap;
   static constexpr uint32_t kChainWords = kClusterGW * 12 * kChainStride;
@@ -74,12 +89,17 @@ struct ClusterSmem {
 __global__ void __launch_bounds__(256) k_setup_views(const FrameParams p) {
   __shared__ uint32_t s_cnt[8];
   __shared__ uint32_t s_box[4];
-  const uint32_t slot = blockIdx.x, view = blockIdx.y, tid = threadIdx.x;
+  // grid: (order slot, rank of the view in this launch's group of the cost-sorted batch)
+  const uint32_t slot = blockIdx.x, vrank = p.viewBase + blockIdx.y, tid = threadIdx.x;
+  const uint32_t view = p.viewOrder ? p.viewOrder[vrank] : vrank;
   const int warp = (int)(tid >> 5), lane = (int)(tid & 31u);
   const uint32_t* fr = p.frontBuf + ((size_t)view * p.nOcc + slot) * kFrontWords;
   const uint32_t status = fr[0];
   if (status == kBoxCulled) {
-    if (tid == 0) p.recInfo[((size_t)view * p.nOcc + slot) * 2u] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) {
+      p.recInfo[((size_t)view * p.nOcc + slot) * 2u] = make_uint4(0u, 0u, 0u, 0u);
+      if (p.occBox) p.occBox[(size_t)view * p.nOcc + slot] = make_uint2(0xffffffffu, 0u);
+    }
     return;
   }
   const bool useGate = (p.flags & ORZ_BATCH_NO_GATE) == 0u;
@@ -162,6 +182,7 @@ __global__ void __launch_bounds__(256) k_setup_views(const FrameParams p) {
     p.recInfo[((size_t)view * p.nOcc + slot) * 2u] = make_uint4(written, slotBase, om.quadCount, 0u);
     // block rectangle that holds every primitive of the occluder, half open (lo > hi when there is none)
     p.recInfo[((size_t)view * p.nOcc + slot) * 2u + 1u] = make_uint4(s_box[0], s_box[1], s_box[2], s_box[3]);
+    if (p.occBox) p.occBox[(size_t)view * p.nOcc + slot] = written ? make_uint2(s_box[0] | (s_box[1] << 16), s_box[2] | (s_box[3] << 16)) : make_uint2(0xffffffffu, 0u);
   }
 }
 
@@ -178,6 +199,14 @@ __device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) {
 // the same word as ONE value for the whole warp: every lane's load races with remote stores on its own, so control flow
 // that contains full-mask collectives branches on lane 0's observation only
 __device__ __forceinline__ uint32_t ld_flag_warp(const uint32_t* p) { return __shfl_sync(kFull, ld_flag(p), 0); }
+// ... and as warp votes (one instruction): the words only grow, so "some lane saw it" is a valid observation for all
+#if ORZ_FLAG_VOTE
+__device__ __forceinline__ bool flag_set_warp(const uint32_t* p) { return __any_sync(kFull, ld_flag(p) != 0u); }
+__device__ __forceinline__ bool flag_reached_warp(const uint32_t* p, uint32_t c) { return __any_sync(kFull, ld_flag(p) >= c); }
+#else  // (measurement only: every lane branches on its own load)
+__device__ __forceinline__ bool flag_set_warp(const uint32_t* p) { return ld_flag(p) != 0u; }
+__device__ __forceinline__ bool flag_reached_warp(const uint32_t* p, uint32_t c) { return ld_flag(p) >= c; }
+#endif
 __device__ __forceinline__ void st_flag_remote(uint32_t* localPtr, uint32_t ctaRank, uint32_t val) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(localPtr)), "r"(ctaRank));
@@ -213,6 +242,7 @@ __device__ __forceinline__ void step_chain(float cur, const float incX, const fl
   }
 }
 
+#if ORZ_TILE_SMEM
 // One primitive on the tile a warp has open (Rasterizer.cpp:1098-1292 restricted to the tile's
 // blocks).  d[8] / h are the lane's block and its HiZ, kept in registers between primitives.
 __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, const int lane, const uint32_t x0, const uint32_t y0,
@@ -332,6 +362,310 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
   __syncwarp();  // chain slots, masks and the tile are rewritten / read by the next primitive
 }
 
+#else  // register-resident tile, one lane per block (round-1 form, kept for A/B measurements)
+// One primitive on the tile a warp has open (Rasterizer.cpp:1098-1292 restricted to the tile's
+// blocks).  d[8] / h are the lane's block and its HiZ, kept in registers between primitives.
+__device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, const int lane, const uint32_t x0, const uint32_t y0,
+                                          const uint32_t x1, const uint32_t y1, const uint2* __restrict__ lut, float* __restrict__ sm,
+                                          uint4 (&d)[8], uint32_t& h, bool& dirty) {
+  const uint32_t w0 = rec[0], w1 = rec[1], w2 = rec[2];
+  const uint32_t minX = w0 & 0xffffu, minY = w0 >> 16, maxZ = w2 & 0xffffu, mode = w2 >> 16;
+  const uint32_t xa = max(minX, x0), xb = min(minX + (w1 & 0xffffu), x1), ya = max(minY, y0), yb = min(minY + (w1 >> 16), y1);
+  const uint32_t bx = x0 + ((uint32_t)lane & 7u), by = y0 + ((uint32_t)lane >> 3);
+  const bool pass = bx >= xa && bx < xb && by >= ya && by < yb && h < maxZ;  // Rasterizer.cpp:1148-1152
+  const uint32_t passMask = __ballot_sync(kFull, pass);
+  if (!passMask) return;  // the whole tile is behind its HiZ: no chain has to be stepped at all
+
+  // ---- the iterated add chains, stepped exactly as the reference does: y chain from the
+  // primitive's first row (Rasterizer.cpp:1130), x chain restarted at every row start (:1136,
+  // :1145).  One lane per (chain, tile row): first the 4 edge offsets x 4 rows (16 lanes); the
+  // 8 depth chains x 4 rows (32 lanes) only when some block is really covered.
+  const float dzdx = u2f(rec[3]), dzdy = u2f(rec[4]);
+  const uint32_t rFirst = ya - y0;
+  {
+    const uint32_t rLast = (31u - (uint32_t)__clz((int)passMask)) >> 3;
+    const uint32_t cols = (passMask | (passMask >> 8) | (passMask >> 16) | (passMask >> 24)) & 0xffu;
+    const uint32_t cA = (uint32_t)__ffs((int)cols) - 1u, cB = 31u - (uint32_t)__clz((int)cols);
+    const uint32_t r = (uint32_t)lane >> 2, e = (uint32_t)lane & 3u;
+    const bool active = lane < 16 && r >= rFirst && r <= rLast;
+    float cur = 0.0f, incX = 0.0f, incY = 0.0f;
+    if (active) { cur = u2f(rec[14 + e]); incX = u2f(rec[6 + e]); incY = u2f(rec[10 + e]); }
+    step_chain(cur, incX, incY, ya - minY, r - rFirst, x0 + cA - minX + rec[20], cA, cB, active, sm + e * kChainStride + r * 8u);
+  }
+  __syncwarp();
+
+  // ---- coverage (Rasterizer.cpp:1155-1239)
+  bool upd = false;
+  uint2 mk = make_uint2(0u, 0u);
+  if (pass) {
+    const float o0 = sm[0 * kChainStride + lane], o1 = sm[1 * kChainStride + lane], o2 = sm[2 * kChainStride + lane], o3 = sm[3 * kChainStride + lane];
+    const uint32_t slope01 = rec[18], slope23 = rec[19];
+    const uint32_t s0 = slope01 & 0xffffu, s1 = slope01 >> 16, s2 = slope23 & 0xffffu, s3 = slope23 >> 16;
+    if (mode == kConvex) {
+      if (!(o0 >= 63.0f || o1 >= 63.0f || o2 >= 63.0f || o3 >= 63.0f)) {
+        const uint2 A = lut[s0 | (uint32_t)__float2int_rz(fmaxf(o0, 0.0f))], B = lut[s1 | (uint32_t)__float2int_rz(fmaxf(o1, 0.0f))];
+        const uint2 C2 = lut[s2 | (uint32_t)__float2int_rz(fmaxf(o2, 0.0f))], D = lut[s3 | (uint32_t)__float2int_rz(fmaxf(o3, 0.0f))];
+        mk.x = (A.x & B.x) & (C2.x & D.x); mk.y = (A.y & B.y) & (C2.y & D.y);
+        upd = true;  // no empty-mask test on this path (Rasterizer.cpp:1186)
+      }
+    } else {
+      const uint32_t q0 = o0 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o0, 0.0f), 63.0f)) : 0u;
+      const uint32_t q1 = o1 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o1, 0.0f), 63.0f)) : 0u;
+      const uint32_t q2 = o2 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o2, 0.0f), 63.0f)) : 0u;
+      const uint32_t q3 = o3 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o3, 0.0f), 63.0f)) : 0u;
+      const uint2 A = lut[s0 | q0], B = lut[s1 | q1], C2 = lut[s2 | q2], D = lut[s3 | q3];
+      if (mode == kTriangle0) { mk.x = A.x & B.x & C2.x; mk.y = A.y & B.y & C2.y; }
+      else if (mode == kTriangle1) { mk.x = A.x & C2.x & D.x; mk.y = A.y & C2.y & D.y; }
+      else if (mode == kConcaveRight) { mk.x = (A.x | D.x) & (B.x & C2.x); mk.y = (A.y | D.y) & (B.y & C2.y); }
+      else if (mode == kConcaveCenter) { mk.x = (A.x & B.x) | (C2.x & D.x); mk.y = (A.y & B.y) | (C2.y & D.y); }
+      else { mk.x = (A.x & D.x) & (B.x | C2.x); mk.y = (A.y & D.y) & (B.y | C2.y); }
+      upd = (mk.x | mk.y) != 0u;
+    }
+  }
+  const uint32_t updMask = __ballot_sync(kFull, upd);
+  __syncwarp();  // orders this primitive's reads of the edge slots before the next primitive's writes (free: the warp is converged)
+  if (!updMask) return;
+  {  // the eight depth lanes (Rasterizer.cpp:1103-1112) at the covered blocks
+    const uint32_t rLast = (31u - (uint32_t)__clz((int)updMask)) >> 3, rLo = ((uint32_t)__ffs((int)updMask) - 1u) >> 3;
+    const uint32_t cols = (updMask | (updMask >> 8) | (updMask >> 16) | (updMask >> 24)) & 0xffu;
+    const uint32_t cA = (uint32_t)__ffs((int)cols) - 1u, cB = 31u - (uint32_t)__clz((int)cols);
+    const uint32_t r = (uint32_t)lane >> 3, l = (uint32_t)lane & 7u;
+    const bool active = r >= rLo && r <= rLast;
+    const float s = -0.5f + 1.0f / 16.0f;
+    const float cur = ORZ_FMA(dzdx, s + 0.125f * (float)(l & 3u), ORZ_FMA(dzdy, (l >> 2) ? s + 0.125f : s, u2f(rec[5])));
+    step_chain(cur, dzdx, dzdy, y0 + rLo - minY, r - rLo, x0 + cA - minX + rec[20], cA, cB, active, sm + (4u + l) * kChainStride + r * 8u);
+  }
+  __syncwarp();
+  // ---- depth rows, merge into the registers, HiZ (Rasterizer.cpp:1241-1290)
+  if (upd) {
+    const float* smd = sm + 4 * kChainStride + lane;
+    const uint32_t keep = h != 1u ? 0xffffffffu : 0u;  // a cleared block is overwritten (:1271-1278)
+    uint32_t r0[2][4], r4[2][4], r8[2][4];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      float dv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dv[k] = smd[(4 * rr + k) * kChainStride];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a = dv[(2 * i) & 3], b = dv[(2 * i + 1) & 3];
+        if (i >= 2) { a = ORZ_FMA(dzdx, 0.5f, a); b = ORZ_FMA(dzdx, 0.5f, b); }  // depth1, :1243
+        const float a8 = dzdy + a, b8 = dzdy + b;                                // depth8/9, :1244-1245
+        r0[rr][i] = pack16(a) | (pack16(b) << 16);  // (a run-time "finite plane" shortcut for the NaN guard was measured slower)
+        r8[rr][i] = pack16(a8) | (pack16(b8) << 16);
+        r4[rr][i] = avg_u16x2(r0[rr][i], r8[rr][i]);                             // :1252
+      }
+    }
+    uint32_t mnAcc = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int y = 2 * k + rr;
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          w[i] = k == 0 ? r0[rr][i] : k == 2 ? r4[rr][i] : k == 1 ? avg_u16x2(r0[rr][i], r4[rr][i]) : avg_u16x2(r4[rr][i], r8[rr][i]);  // :1253-1254
+        const int ky = (rr ? 0 : 4) + k;  // pixel px of row y <-> bit 8 px + ky (:1257-1268)
+        const uint32_t lo = ((mk.x >> ky) & 0x01010101u) * 0xffu, hi = ((mk.y >> ky) & 0x01010101u) * 0xffu;
+        uint4 v;
+        v.x = __vmaxu2(w[0] & __byte_perm(lo, 0u, 0x1100), d[y].x & keep);
+        v.y = __vmaxu2(w[1] & __byte_perm(lo, 0u, 0x3322), d[y].y & keep);
+        v.z = __vmaxu2(w[2] & __byte_perm(hi, 0u, 0x1100), d[y].z & keep);
+        v.w = __vmaxu2(w[3] & __byte_perm(hi, 0u, 0x3322), d[y].w & keep);
+        d[y] = v;
+        mnAcc = __vminu2(mnAcc, __vminu2(__vminu2(v.x, v.y), __vminu2(v.z, v.w)));
+      }
+    h = min(mnAcc & 0xffffu, mnAcc >> 16);  // Rasterizer.cpp:1287-1290
+    dirty = true;
+  }
+  __syncwarp();  // chain slots are rewritten by the next primitive
+}
+
+#endif
+
+// Per-warp state of the tile-major traversal: the tiles a warp owns (lane k keeps tile k) and its slices of the CTA's
+// shared memory.  Shared by the cluster kernel (one view per cluster, gated) and k_raster_tiles (one ungated view over
+// the whole GPU): both hand an occluder's records to rasterize().
+struct TileWalker {
+  Target T;
+  int lane;
+  uint32_t lx, ly;          // my block inside a tile
+  uint32_t tileX0, tileY0;  // lane k: origin (in blocks) of my k-th tile; 0xffff = none
+  uint32_t allTiles;        // mask over k of the tiles that exist
+  uint16_t* myHiz;          // + 32 k: HiZ mirror of my block in tile k
+  float* myChain;
+  uint32_t* myStage;
+  uint32_t* myIdx;
+  uint4* myTile;
+  uint32_t* myAux;
+  const uint2* lut;
+
+  // tile t belongs to warp t mod nWarps of the group that shares the view
+  __device__ __forceinline__ void own_tiles(uint32_t gw, uint32_t nWarps, uint32_t K) {
+    const uint32_t tilesX = (T.blocksX + kTileW - 1u) / kTileW, tilesY = (T.blocksY + kTileH - 1u) / kTileH, nTiles = tilesX * tilesY;
+    tileX0 = 0xffffu; tileY0 = 0xffffu;
+    if ((uint32_t)lane < K) {
+      const uint32_t t = gw + (uint32_t)lane * nWarps;
+      if (t < nTiles) { const uint32_t ty = t / tilesX; tileX0 = (t - ty * tilesX) * kTileW; tileY0 = ty * kTileH; }
+    }
+    allTiles = __ballot_sync(kFull, tileX0 != 0xffffu);
+  }
+  // clear (Rasterizer.cpp:107-121): HiZ := 1 on my tiles; depth is overwritten by the first update
+  __device__ __forceinline__ void clear_tiles() {
+    for (uint32_t m = allTiles; m; m &= m - 1u) {
+      const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+      const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
+      myHiz[32u * k] = 1;
+      if (bx < T.blocksX && by < T.blocksY) T.hiz[by * T.blocksX + bx] = 1;
+    }
+    __syncwarp();
+  }
+  // my tiles that meet the block rectangle [bx0, bx1] x [by0, by1] (inclusive), as a mask over k
+  __device__ __forceinline__ uint32_t tiles_meeting(uint32_t bx0, uint32_t bx1, uint32_t by0, uint32_t by1) const {
+    return __ballot_sync(kFull, tileX0 != 0xffffu && tileX0 <= bx1 && tileX0 + kTileW > bx0 && tileY0 <= by1 && tileY0 + kTileH > by0);
+  }
+  // canonical depth for the caller: blocks that stayed cleared read as zero
+  __device__ __forceinline__ void zero_cleared_tiles() {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t m = allTiles; m; m &= m - 1u) {
+      const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+      const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
+      if (bx < T.blocksX && by < T.blocksY && myHiz[32u * k] == 1) {
+        uint4* d4 = reinterpret_cast<uint4*>(T.depth) + (size_t)(by * T.blocksX + bx) * 8u;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) d4[y] = z;
+      }
+    }
+  }
+  // rasterize<clipped>(occluder) restricted to my tiles: `cnt` records (k_setup_views) with their bounding-box headers;
+  // tmOcc = my tiles that meet the occluder's block rectangle
+  __device__ __forceinline__ void rasterize(const uint32_t* __restrict__ recs, const uint2* __restrict__ hdrs, const uint32_t cnt, const uint32_t tmOcc) {
+    uint32_t nStaged = 0;
+    // staged records -> my tiles, tile-major, each tile's primitives in order
+    auto flush = [&]() {
+      __syncwarp();
+#pragma unroll 8
+      for (uint32_t i = 0; i < nStaged; ++i)
+        if (lane < kRecStride) myStage[i * kRecStride + lane] = recs[(size_t)myIdx[i] * kRecStride + lane];
+      __syncwarp();
+      // which staged records touch which of my tiles: lane k keeps the answer for tile k
+      uint32_t myHits = 0u;
+      for (uint32_t m = tmOcc; m; m &= m - 1u) {
+        const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+        const uint32_t x0 = __shfl_sync(kFull, tileX0, (int)k), y0 = __shfl_sync(kFull, tileY0, (int)k);
+        const uint32_t x1 = min(x0 + kTileW, T.blocksX), y1 = min(y0 + kTileH, T.blocksY);
+        bool touches = false;
+        if ((uint32_t)lane < nStaged) {
+          const uint32_t a = myStage[lane * kRecStride], b = myStage[lane * kRecStride + 1];
+          const uint32_t minX = a & 0xffffu, minY = a >> 16;
+          touches = minX < x1 && minX + (b & 0xffffu) > x0 && minY < y1 && minY + (b >> 16) > y0;
+        }
+        const uint32_t hitsK = __ballot_sync(kFull, touches);
+        if ((uint32_t)lane == k) myHits = hitsK;
+      }
+      for (uint32_t m = __ballot_sync(kFull, myHits != 0u); m;) {
+        const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+        m &= m - 1u;
+        uint32_t hits = __shfl_sync(kFull, myHits, (int)k);
+        const uint32_t x0 = __shfl_sync(kFull, tileX0, (int)k), y0 = __shfl_sync(kFull, tileY0, (int)k);
+        const uint32_t x1 = min(x0 + kTileW, T.blocksX), y1 = min(y0 + kTileH, T.blocksY);
+#if ORZ_TILE_PREFETCH
+        if (m) {  // the NEXT tile's stored depth starts its way from L2 / HBM while this one is worked on
+          const uint32_t k2 = (uint32_t)__ffs((int)m) - 1u;
+          const uint32_t bxn = __shfl_sync(kFull, tileX0, (int)k2) + lx, byn = __shfl_sync(kFull, tileY0, (int)k2) + ly;
+          if (bxn < T.blocksX && byn < T.blocksY && myHiz[32u * k2] != 1) prefetch_l1(reinterpret_cast<uint4*>(T.depth) + (size_t)(byn * T.blocksX + bxn) * 8u);
+        }
+#endif
+#if ORZ_TILE_SMEM
+        // open the tile: its depth goes to shared memory, one block per lane, as 8 items (rr, i) of 4 row pairs each
+        // (item slot swizzled by the block so that both this lane-per-block pass and the eight-lanes-per-block
+        // update passes are bank-conflict free); cleared blocks (HiZ 1) enter as zero
+        const uint32_t bx = x0 + lx, by = y0 + ly;
+        const bool inScreen = bx < x1 && by < y1;
+        uint4* dp = reinterpret_cast<uint4*>(T.depth) + (size_t)(by * T.blocksX + bx) * 8u;
+        uint32_t h = inScreen ? (uint32_t)myHiz[32u * k] : 0xffffu;  // off-screen lanes never pass
+        const bool load = inScreen && h != 1u;
+        uint4* mine = myTile + (uint32_t)lane * 8u;
+        const uint32_t sw = (uint32_t)lane & 7u;
+#pragma unroll
+        for (uint32_t rr = 0; rr < 2u; ++rr) {
+          uint4 R[4];
+#pragma unroll
+          for (uint32_t kk = 0; kk < 4u; ++kk) R[kk] = load ? dp[2u * kk + rr] : make_uint4(0u, 0u, 0u, 0u);
+          mine[(rr * 4u + 0u) ^ sw] = make_uint4(R[0].x, R[1].x, R[2].x, R[3].x);
+          mine[(rr * 4u + 1u) ^ sw] = make_uint4(R[0].y, R[1].y, R[2].y, R[3].y);
+          mine[(rr * 4u + 2u) ^ sw] = make_uint4(R[0].z, R[1].z, R[2].z, R[3].z);
+          mine[(rr * 4u + 3u) ^ sw] = make_uint4(R[0].w, R[1].w, R[2].w, R[3].w);
+        }
+        __syncwarp();
+        bool dirty = false;
+        for (; hits; hits &= hits - 1u)
+          tile_prim(myStage + ((uint32_t)__ffs((int)hits) - 1u) * kRecStride, lane, x0, y0, x1, y1, lut, myChain, myTile,
+                    myAux, h, dirty);
+        if (dirty) {  // close: the blocks this occluder changed go back to HBM / L2 in the reference's row layout
+#pragma unroll
+          for (uint32_t rr = 0; rr < 2u; ++rr) {
+            const uint4 I0 = mine[(rr * 4u + 0u) ^ sw], I1 = mine[(rr * 4u + 1u) ^ sw], I2 = mine[(rr * 4u + 2u) ^ sw], I3 = mine[(rr * 4u + 3u) ^ sw];
+            dp[0u + rr] = make_uint4(I0.x, I1.x, I2.x, I3.x);
+            dp[2u + rr] = make_uint4(I0.y, I1.y, I2.y, I3.y);
+            dp[4u + rr] = make_uint4(I0.z, I1.z, I2.z, I3.z);
+            dp[6u + rr] = make_uint4(I0.w, I1.w, I2.w, I3.w);
+          }
+          myHiz[32u * k] = (uint16_t)h;
+          T.hiz[by * T.blocksX + bx] = (uint16_t)h;
+        }
+        __syncwarp();  // the next tile's open overwrites the slots other lanes may still be reading
+      #else
+        // bring the tile into registers
+        const uint32_t bx = x0 + lx, by = y0 + ly;
+        const bool inScreen = bx < x1 && by < y1;
+        uint4* dp = reinterpret_cast<uint4*>(T.depth) + (size_t)(by * T.blocksX + bx) * 8u;
+        uint32_t h = inScreen ? (uint32_t)myHiz[32u * k] : 0xffffu;  // off-screen lanes never pass
+        const bool load = inScreen && h != 1u;
+        uint4 d[8];
+#pragma unroll
+        for (int y = 0; y < 8; ++y) d[y] = load ? dp[y] : make_uint4(0u, 0u, 0u, 0u);
+        bool dirty = false;
+        for (; hits; hits &= hits - 1u)
+          tile_prim(myStage + ((uint32_t)__ffs((int)hits) - 1u) * kRecStride, lane, x0, y0, x1, y1, lut, myChain, d, h, dirty);
+        if (dirty) {
+#pragma unroll
+          for (int y = 0; y < 8; ++y) dp[y] = d[y];
+          myHiz[32u * k] = (uint16_t)h;
+          T.hiz[by * T.blocksX + bx] = (uint16_t)h;
+        }
+      #endif
+      }
+      __syncwarp();
+      nStaged = 0;
+    };
+    for (uint32_t r0 = 0; r0 < cnt; r0 += 32u) {
+      uint32_t hx0 = 0, hx1 = 0, hy0 = 0, hy1 = 0;  // empty
+      if (r0 + (uint32_t)lane < cnt) {
+        const uint2 hdr = hdrs[r0 + (uint32_t)lane];
+        hx0 = hdr.x & 0xffffu; hy0 = hdr.x >> 16; hx1 = hx0 + (hdr.y & 0xffffu); hy1 = hy0 + (hdr.y >> 16);
+      }
+      bool touches = false;
+      for (uint32_t m = tmOcc; m; m &= m - 1u) {
+        const int k = __ffs((int)m) - 1;
+        const uint32_t x0 = __shfl_sync(kFull, tileX0, k), y0 = __shfl_sync(kFull, tileY0, k);
+        touches = touches || (hx0 < x0 + kTileW && hx1 > x0 && hy0 < y0 + kTileH && hy1 > y0);
+      }
+      uint32_t hits = __ballot_sync(kFull, touches);
+      while (hits) {
+        const uint32_t take = min(kStageCap - nStaged, (uint32_t)__popc(hits));
+        const uint32_t myRank = (uint32_t)__popc(hits & ((1u << lane) - 1u));
+        if (((hits >> lane) & 1u) && myRank < take) myIdx[nStaged + myRank] = r0 + (uint32_t)lane;
+        for (uint32_t i = 0; i < take; ++i) hits &= hits - 1u;
+        nStaged += take;
+        if (nStaged == kStageCap) flush();
+      }
+    }
+    if (nStaged) flush();
+  }
+};
+
 template <int C>
 #if ORZ_CLUSTER_CTAS_PER_SM
 __global__ void __launch_bounds__(kClusterGW * 32, ORZ_CLUSTER_CTAS_PER_SM) k_raster_views_cluster(const FrameParams p) {
@@ -370,7 +704,6 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
   T.width = p.width; T.height = p.height; T.blocksX = p.width >> 3; T.blocksY = p.height >> 3;
   T.depth = p.depth + (size_t)view * p.depthStride;
   T.hiz = p.hiz + (size_t)view * p.hizStride;
-  const uint32_t tilesX = (T.blocksX + kTileW - 1u) / kTileW, tilesY = (T.blocksY + kTileH - 1u) / kTileH, nTiles = tilesX * tilesY;
   const bool useGate = (p.flags & ORZ_BATCH_NO_GATE) == 0u;
   const bool forceClip = (p.flags & ORZ_BATCH_FORCE_CLIPPED) != 0u;
   const uint4* recInfo = p.recInfo + (size_t)view * nOcc * 2u;
@@ -383,21 +716,13 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
   const uint32_t lx = (uint32_t)lane & 7u, ly = (uint32_t)lane >> 3;
   const bool reporter = rank == 0u && warp == 0 && lane == 0;  // writes the per-slot outputs of the view
 
-  // lane k keeps the origin (in blocks) of my k-th tile; 0xffff = none
-  uint32_t tileX0 = 0xffffu, tileY0 = 0xffffu;
-  if ((uint32_t)lane < K) {
-    const uint32_t t = gw + (uint32_t)lane * kWarps;
-    if (t < nTiles) { const uint32_t ty = t / tilesX; tileX0 = (t - ty * tilesX) * kTileW; tileY0 = ty * kTileH; }
-  }
-  const uint32_t allTiles = __ballot_sync(kFull, tileX0 != 0xffffu);
-  // clear (Rasterizer.cpp:107-121): HiZ := 1 on my tiles; depth is overwritten by the first update
-  for (uint32_t m = allTiles; m; m &= m - 1u) {
-    const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
-    const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
-    myHiz[32u * k] = 1;
-    if (bx < T.blocksX && by < T.blocksY) T.hiz[by * T.blocksX + bx] = 1;
-  }
-  __syncwarp();
+  TileWalker tw;
+  tw.T = T; tw.lane = lane; tw.lx = lx; tw.ly = ly;
+  tw.myHiz = myHiz; tw.myChain = myChain; tw.myStage = myStage; tw.myIdx = myIdx; tw.myTile = myTile; tw.myAux = myAux;
+  tw.lut = ORZ_CLUSTER_LUT_SMEM ? s_lut : p.lut;
+  tw.own_tiles(gw, kWarps, K);
+  tw.clear_tiles();
+  const uint32_t tileX0 = tw.tileX0, tileY0 = tw.tileY0;
   cluster.sync();  // tables staged, decision words zero in every CTA before the first remote access
 
   // "no visible pixel on my tiles" for candidate s: per-CTA count, forwarded by the CTA's last warp
@@ -407,10 +732,7 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
     old = __shfl_sync(kFull, old, 0);
     if (old == GW - 1u && lane < C) atomicAdd(cluster.map_shared_rank(&s_doneCta[s], (unsigned)lane), 1u);
   };
-  // my tiles that meet the block rectangle [bx0, bx1] x [by0, by1] (inclusive), as a mask over k
-  auto tiles_meeting = [&](uint32_t bx0, uint32_t bx1, uint32_t by0, uint32_t by1) -> uint32_t {
-    return __ballot_sync(kFull, tileX0 != 0xffffu && tileX0 <= bx1 && tileX0 + kTileW > bx0 && tileY0 <= by1 && tileY0 + kTileH > by0);
-  };
+  auto tiles_meeting = [&](uint32_t bx0, uint32_t bx1, uint32_t by0, uint32_t by1) -> uint32_t { return tw.tiles_meeting(bx0, bx1, by0, by1); };
 
   // ---- candidates whose rectangle does not touch my tiles: answered before the walk starts
   for (uint32_t s = 0; s < nOcc; ++s) {
@@ -420,14 +742,25 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
   }
 
   uint32_t quadsSubmitted = 0;
+  uint4 infoNext = recInfo[0], boxNext = recInfo[1];  // {records, first slot, quads}, {block rectangle}: fetched one slot ahead of the walk
   for (uint32_t s = 0; s < nOcc; ++s) {
     const uint32_t* hd = s_head + s * kHeadWords;
     const uint32_t status = hd[0];
+    const uint4 info = infoNext, box = boxNext;
+    if (s + 1u < nOcc) { infoNext = recInfo[2u * s + 2u]; boxNext = recInfo[2u * s + 3u]; }
     if (status == kBoxCulled) {
       if (p.gate && reporter) p.gate[(size_t)view * nOcc + s] = 0;
       continue;
     }
-    const uint4 info = recInfo[2u * s], box = recInfo[2u * s + 1u];  // requested now, needed after the gate
+    // my tiles that the occluder's primitives can touch; their record headers start their way to the SM now, so that
+    // the gate test and the wait for the decision hide the L2 round trip (wasted on the candidates the gate rejects)
+    uint32_t tmOcc = 0u;
+    if (info.x != 0u && box.x < box.z) tmOcc = tiles_meeting(box.x, box.z - 1u, box.y, box.w - 1u);
+    const size_t recBase = (size_t)view * p.totalQuads + info.y;
+    const uint2* hdrs = p.hdrBuf + recBase;
+#if ORZ_HDR_PREFETCH_EARLY
+    if (tmOcc && (uint32_t)lane * 16u < info.x) prefetch_l1(hdrs + (uint32_t)lane * 16u);  // <= 504 headers = 32 lines
+#endif
     bool visible = true, clipped = false;
     if (status == kBoxNearClip) {
       clipped = useGate ? true : forceClip;
@@ -437,24 +770,24 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
       const uint32_t bx0 = minX >> 3, bx1 = maxX >> 3, by0 = minY >> 3, by1 = maxY >> 3;
       const uint32_t* vis = s_vis + s;
       uint32_t tm = tiles_meeting(bx0, bx1, by0, by1);
-      if (tm && !ld_flag_warp(vis)) {
+      if (tm && !flag_set_warp(vis)) {
         bool found = false;
         for (; tm; tm &= tm - 1u) {
           const uint32_t k = (uint32_t)__ffs((int)tm) - 1u;
           const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
-          if (ld_flag_warp(vis)) break;  // another warp already found a visible pixel
+          if (flag_set_warp(vis)) break;  // another warp already found a visible pixel
           const bool hit = bx >= bx0 && bx <= bx1 && by >= by0 && by <= by1 && bx < T.blocksX && by < T.blocksY &&
                            query_block_h(T, bx, by, (uint32_t)myHiz[32u * k], minX, maxX, minY, maxY, maxZ);
           if (__any_sync(kFull, hit)) { found = true; break; }
         }
         if (found) { if (lane < C) st_flag_remote(s_vis + s, (uint32_t)lane, 1u); }
-        else if (!ld_flag_warp(vis)) answer_no(s);
+        else if (!flag_set_warp(vis)) answer_no(s);
       }
       // visible as soon as ONE warp says so, invisible when all 16 C warps have said no
       const uint32_t* done = s_doneCta + s;
       for (;;) {
-        if (ld_flag_warp(vis)) break;
-        if (ld_flag_warp(done) >= (uint32_t)C) { visible = ld_flag_warp(vis) != 0u; break; }
+        if (flag_set_warp(vis)) break;
+        if (flag_reached_warp(done, (uint32_t)C)) { visible = flag_set_warp(vis); break; }
 #if ORZ_SPIN_NAP
         __nanosleep(ORZ_SPIN_NAP);  // (a longer or growing nap was measured slower: the wake-up delay sits on the dependency chain)
 #endif
@@ -467,113 +800,90 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
     if (!visible || info.x == 0u) continue;
 
     // ---- rasterize<clipped>(occluder): the records k_setup_views wrote, on my tiles
-    uint32_t tmOcc = 0u;
-    if (box.x < box.z) tmOcc = tiles_meeting(box.x, box.z - 1u, box.y, box.w - 1u);
     if (!tmOcc) continue;
     const uint32_t cnt = info.x;
-    const size_t recBase = (size_t)view * p.totalQuads + info.y;
     const uint32_t* recs = p.recBuf + recBase * kRecStride;
-    const uint2* hdrs = p.hdrBuf + recBase;
+#if !ORZ_HDR_PREFETCH_EARLY
     if ((uint32_t)lane * 16u < cnt) prefetch_l1(hdrs + (uint32_t)lane * 16u);  // <= 504 headers = 32 lines
+#endif
 
-    uint32_t nStaged = 0;
-    // staged records -> my tiles, tile-major, each tile's primitives in order
-    auto flush = [&]() {
-      __syncwarp();
-#pragma unroll 8
-      for (uint32_t i = 0; i < nStaged; ++i)
-        if (lane < kRecStride) myStage[i * kRecStride + lane] = recs[(size_t)myIdx[i] * kRecStride + lane];
-      __syncwarp();
-      for (uint32_t m = tmOcc; m; m &= m - 1u) {
-        const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
-        const uint32_t x0 = __shfl_sync(kFull, tileX0, (int)k), y0 = __shfl_sync(kFull, tileY0, (int)k);
-        const uint32_t x1 = min(x0 + kTileW, T.blocksX), y1 = min(y0 + kTileH, T.blocksY);
-        bool touches = false;
-        if ((uint32_t)lane < nStaged) {
-          const uint32_t a = myStage[lane * kRecStride], b = myStage[lane * kRecStride + 1];
-          const uint32_t minX = a & 0xffffu, minY = a >> 16;
-          touches = minX < x1 && minX + (b & 0xffffu) > x0 && minY < y1 && minY + (b >> 16) > y0;
-        }
-        uint32_t hits = __ballot_sync(kFull, touches);
-        if (!hits) continue;
-        // open the tile: its depth goes to shared memory, one block per lane, as 8 items (rr, i) of 4 row pairs each
-        // (item slot swizzled by the block so that both this lane-per-block pass and the eight-lanes-per-block
-        // update passes are bank-conflict free); cleared blocks (HiZ 1) enter as zero
-        const uint32_t bx = x0 + lx, by = y0 + ly;
-        const bool inScreen = bx < x1 && by < y1;
-        uint4* dp = reinterpret_cast<uint4*>(T.depth) + (size_t)(by * T.blocksX + bx) * 8u;
-        uint32_t h = inScreen ? (uint32_t)myHiz[32u * k] : 0xffffu;  // off-screen lanes never pass
-        const bool load = inScreen && h != 1u;
-        uint4* mine = myTile + (uint32_t)lane * 8u;
-        const uint32_t sw = (uint32_t)lane & 7u;
-#pragma unroll
-        for (uint32_t rr = 0; rr < 2u; ++rr) {
-          uint4 R[4];
-#pragma unroll
-          for (uint32_t kk = 0; kk < 4u; ++kk) R[kk] = load ? dp[2u * kk + rr] : make_uint4(0u, 0u, 0u, 0u);
-          mine[(rr * 4u + 0u) ^ sw] = make_uint4(R[0].x, R[1].x, R[2].x, R[3].x);
-          mine[(rr * 4u + 1u) ^ sw] = make_uint4(R[0].y, R[1].y, R[2].y, R[3].y);
-          mine[(rr * 4u + 2u) ^ sw] = make_uint4(R[0].z, R[1].z, R[2].z, R[3].z);
-          mine[(rr * 4u + 3u) ^ sw] = make_uint4(R[0].w, R[1].w, R[2].w, R[3].w);
-        }
-        __syncwarp();
-        bool dirty = false;
-        for (; hits; hits &= hits - 1u)
-          tile_prim(myStage + ((uint32_t)__ffs((int)hits) - 1u) * kRecStride, lane, x0, y0, x1, y1, ORZ_CLUSTER_LUT_SMEM ? s_lut : p.lut, myChain, myTile,
-                    myAux, h, dirty);
-        if (dirty) {  // close: the blocks this occluder changed go back to HBM / L2 in the reference's row layout
-#pragma unroll
-          for (uint32_t rr = 0; rr < 2u; ++rr) {
-            const uint4 I0 = mine[(rr * 4u + 0u) ^ sw], I1 = mine[(rr * 4u + 1u) ^ sw], I2 = mine[(rr * 4u + 2u) ^ sw], I3 = mine[(rr * 4u + 3u) ^ sw];
-            dp[0u + rr] = make_uint4(I0.x, I1.x, I2.x, I3.x);
-            dp[2u + rr] = make_uint4(I0.y, I1.y, I2.y, I3.y);
-            dp[4u + rr] = make_uint4(I0.z, I1.z, I2.z, I3.z);
-            dp[6u + rr] = make_uint4(I0.w, I1.w, I2.w, I3.w);
-          }
-          myHiz[32u * k] = (uint16_t)h;
-          T.hiz[by * T.blocksX + bx] = (uint16_t)h;
-        }
-        __syncwarp();  // the next tile's open overwrites the slots other lanes may still be reading
-      }
-      __syncwarp();
-      nStaged = 0;
-    };
-    for (uint32_t r0 = 0; r0 < cnt; r0 += 32u) {
-      uint32_t hx0 = 0, hx1 = 0, hy0 = 0, hy1 = 0;  // empty
-      if (r0 + (uint32_t)lane < cnt) {
-        const uint2 hdr = hdrs[r0 + (uint32_t)lane];
-        hx0 = hdr.x & 0xffffu; hy0 = hdr.x >> 16; hx1 = hx0 + (hdr.y & 0xffffu); hy1 = hy0 + (hdr.y >> 16);
-      }
-      bool touches = false;
-      for (uint32_t m = tmOcc; m; m &= m - 1u) {
-        const int k = __ffs((int)m) - 1;
-        const uint32_t x0 = __shfl_sync(kFull, tileX0, k), y0 = __shfl_sync(kFull, tileY0, k);
-        touches = touches || (hx0 < x0 + kTileW && hx1 > x0 && hy0 < y0 + kTileH && hy1 > y0);
-      }
-      uint32_t hits = __ballot_sync(kFull, touches);
-      while (hits) {
-        const uint32_t take = min(kStageCap - nStaged, (uint32_t)__popc(hits));
-        const uint32_t myRank = (uint32_t)__popc(hits & ((1u << lane) - 1u));
-        if (((hits >> lane) & 1u) && myRank < take) myIdx[nStaged + myRank] = r0 + (uint32_t)lane;
-        for (uint32_t i = 0; i < take; ++i) hits &= hits - 1u;
-        nStaged += take;
-        if (nStaged == kStageCap) flush();
-      }
-    }
-    if (nStaged) flush();
+    tw.rasterize(recs, hdrs, cnt, tmOcc);
   }
   if (p.quadsSubmitted && reporter) p.quadsSubmitted[view] = quadsSubmitted;
-  if (p.exportDepth) {  // canonical depth for the caller: blocks that stayed cleared read as zero
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    for (uint32_t m = allTiles; m; m &= m - 1u) {
-      const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
-      const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
-      if (bx < T.blocksX && by < T.blocksY && myHiz[32u * k] == 1) {
-        uint4* d4 = reinterpret_cast<uint4*>(T.depth) + (size_t)(by * T.blocksX + bx) * 8u;
-#pragma unroll
-        for (int y = 0; y < 8; ++y) d4[y] = z;
-      }
+  if (p.exportDepth) tw.zero_cleared_tiles();
+  cluster.sync();  // no CTA may leave while another one can still write its decision words
+}
+
+// ---------------------------------------------------------------------------------------------
+// One UNGATED view split over the whole GPU (BASELINE config 4: millions of quads in thousands of batches, every
+// batch through rasterize<clipped>, no queryVisibility gate).  Without the gate no decision is shared between warps,
+// so there is no cluster and no barrier after the prologue: tile t of the screen belongs to warp t mod (all warps of
+// the grid) for the whole view, and every warp walks the occluders front to back on its own tiles with the same
+// tile-major traversal as the cluster kernel (TileWalker::rasterize).  The walk over thousands of occluders is itself
+// lane parallel: 32 packed block rectangles (k_setup_views: occBox) per step, a ballot picks the occluders that meet
+// my tiles, and only those are opened -- in order.
+struct TilesSmem {
+  static constexpr uint32_t kFixedWords = ClusterSmem::kLutWords + ClusterSmem::kTileAllWords + ClusterSmem::kStageWords + ClusterSmem::kIdxWords +
+                                          ClusterSmem::kChainWords;
+  static size_t bytes(uint32_t tilesPerWarp) { return (size_t)kFixedWords * 4 + (size_t)kClusterGW * tilesPerWarp * 32 * 2; }
+};
+
+__global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_tiles(const FrameParams p, const uint32_t view, const uint32_t quadsTotal) {
+  constexpr uint32_t GW = kClusterGW, NT = GW * 32;
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  uint2* s_lut = reinterpret_cast<uint2*>(s_dyn);
+  uint32_t* s_tileAll = s_dyn + ClusterSmem::kLutWords;
+  uint32_t* s_stageAll = s_tileAll + ClusterSmem::kTileAllWords;
+  uint32_t* s_idxAll = s_stageAll + ClusterSmem::kStageWords;
+  float* s_chain = reinterpret_cast<float*>(s_idxAll + ClusterSmem::kIdxWords);
+  uint16_t* s_hiz = reinterpret_cast<uint16_t*>(s_dyn + TilesSmem::kFixedWords);  // [GW][K][32]
+  const uint32_t tid = threadIdx.x;
+  const int warp = (int)(tid >> 5), lane = (int)(tid & 31u);
+  const uint32_t K = p.clusterK, nOcc = p.nOcc;
+  if (ORZ_CLUSTER_LUT_SMEM) for (uint32_t i = tid; i < 4096u; i += NT) s_lut[i] = p.lut[i];
+
+  TileWalker tw;
+  tw.T.width = p.width; tw.T.height = p.height; tw.T.blocksX = p.width >> 3; tw.T.blocksY = p.height >> 3;
+  tw.T.depth = p.depth + (size_t)view * p.depthStride;
+  tw.T.hiz = p.hiz + (size_t)view * p.hizStride;
+  tw.lane = lane; tw.lx = (uint32_t)lane & 7u; tw.ly = (uint32_t)lane >> 3;
+  tw.myHiz = s_hiz + (size_t)warp * K * 32u + lane;
+  tw.myChain = s_chain + warp * (12 * kChainStride);
+  tw.myStage = s_stageAll + (uint32_t)warp * kStageCap * kRecStride;
+  tw.myIdx = s_idxAll + (uint32_t)warp * kStageCap;
+  tw.myTile = reinterpret_cast<uint4*>(s_tileAll + (uint32_t)warp * kTileWords);
+  tw.myAux = s_tileAll + (uint32_t)GW * kTileWords + (uint32_t)warp * kTileAuxWords;
+  tw.lut = ORZ_CLUSTER_LUT_SMEM ? s_lut : p.lut;
+  // consecutive tiles go to the warps of one CTA, then to the next CTA: a CTA's tiles are short horizontal runs all over the screen
+  tw.own_tiles(blockIdx.x * GW + (uint32_t)warp, gridDim.x * GW, K);
+  tw.clear_tiles();
+  __syncthreads();  // table staged
+  if (blockIdx.x == 0 && tid == 0 && p.quadsSubmitted) p.quadsSubmitted[view] = quadsTotal;
+
+  const uint4* recInfo = p.recInfo + (size_t)view * nOcc * 2u;
+  const uint2* occBox = p.occBox + (size_t)view * nOcc;
+  for (uint32_t s0 = 0; s0 < nOcc; s0 += 32u) {
+    uint32_t bx0 = 1u, by0 = 1u, bx1 = 0u, by1 = 0u;  // empty
+    if (s0 + (uint32_t)lane < nOcc) {
+      const uint2 b = occBox[s0 + (uint32_t)lane];
+      bx0 = b.x & 0xffffu; by0 = b.x >> 16; bx1 = b.y & 0xffffu; by1 = b.y >> 16;  // half open; {0xffff, 0xffff, 0, 0}: none
+    }
+    bool meets = false;
+    for (uint32_t m = tw.allTiles; m; m &= m - 1u) {
+      const int k = __ffs((int)m) - 1;
+      const uint32_t x0 = __shfl_sync(kFull, tw.tileX0, k), y0 = __shfl_sync(kFull, tw.tileY0, k);
+      meets = meets || (bx0 < x0 + kTileW && bx1 > x0 && by0 < y0 + kTileH && by1 > y0);
+    }
+    for (uint32_t cand = __ballot_sync(kFull, meets); cand; cand &= cand - 1u) {  // in order: Main.cpp:192-206
+      const uint32_t s = s0 + (uint32_t)__ffs((int)cand) - 1u;
+      const uint4 info = recInfo[2u * s], box = recInfo[2u * s + 1u];
+      const uint32_t tmOcc = tw.tiles_meeting(box.x, box.z - 1u, box.y, box.w - 1u);
+      if (!tmOcc || info.x == 0u) continue;
+      const size_t recBase = (size_t)view * p.totalQuads + info.y;
+      const uint2* hdrs = p.hdrBuf + recBase;
+      if ((uint32_t)lane * 16u < info.x) prefetch_l1(hdrs + (uint32_t)lane * 16u);
+      tw.rasterize(p.recBuf + recBase * kRecStride, hdrs, info.x, tmOcc);
     }
   }
-  cluster.sync();  // no CTA may leave while another one can still write its decision words
+  if (p.exportDepth) tw.zero_cleared_tiles();
 }

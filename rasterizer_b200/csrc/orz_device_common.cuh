@@ -85,5 +85,6 @@ struct FrameParams {
   uint32_t* recBuf;     // [nViews][totalQuads][kRecStride] records, each occluder's at its quadOffset
   uint2* hdrBuf;        // [nViews][totalQuads] bounding boxes of the records
   uint4* recInfo;       // [nViews][nOcc][2]: {records, first record slot, quadCount, -}, {block rectangle of all records, half open}
+  uint2* occBox;        // [nViews][nOcc]: the same block rectangle packed {x0 | y0 << 16, x1 | y1 << 16}, {~0, 0} when there are no records
   uint32_t totalQuads;  // record slots per view (2 per quad above 65 536 blocks: index wrap)
 };

@@ -112,6 +112,7 @@ struct orz_context {
   // per device and idempotent: keeping the record per context avoids process-wide mutable state)
   size_t smemViews[2][5] = {{0}};   // [traversal - 1][log2 GW]
   size_t smemCluster[5] = {0};      // [log2 C]
+  size_t smemTiles = 0;             // k_raster_tiles
 };
 struct orz_occluder {
   orz_context* ctx;
@@ -866,15 +867,20 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
     }
     p.viewCounter = ctx->d_counter;
     p.viewCost = (uint32_t*)(prep + chunk * sizeof(ViewMatrices) + chunk * nOcc * 4 + chunk * nOcc * kFrontWords * 4);
-    const bool wide = (b->flags & ORZ_BATCH_NO_GATE) && ((b->flags & ORZ_BATCH_WIDE) || (nv <= 8u && scene->totalQuads >= 65536u));
+    // few ungated views over very many quads (BASELINE config 4): ONE view at a time over the whole GPU, tile major
+    // (k_raster_tiles); ORZ_BATCH_WIDE keeps the round-1 row walk (k_raster_wide) selectable for comparison
+    const bool wide = (b->flags & ORZ_BATCH_NO_GATE) && (b->flags & ORZ_BATCH_WIDE);
+    const bool tilesPath = (b->flags & ORZ_BATCH_NO_GATE) && !wide && nv <= 8u && scene->totalQuads >= 65536u &&
+                           ((size_t)((b->width / 8 + kTileW - 1) / kTileW) * ((b->height / 8 + kTileH - 1) / kTileH) + (size_t)ctx->numSMs * kClusterGW - 1) /
+                                   ((size_t)ctx->numSMs * kClusterGW) <= 32u;
     // (targets above 32 tiles per warp of a 16-CTA cluster -- beyond ~8K x 4K -- stay on the batch kernel)
     // measured crossover with the batch kernel: ~2000 views at 1920x1080, ~1500 at 512x256 (profiles/r1_few_views_*)
     const uint32_t clusterLimit = std::min<uint32_t>((uint32_t)ctx->clusterViews, 65535u);  // k_setup_views puts the view on grid.y
     const size_t nTilesC = (size_t)((b->width / 8 + kTileW - 1) / kTileW) * ((b->height / 8 + kTileH - 1) / kTileH);
-    const bool clusterPath = !wide && ctx->clusterViews > 0 && nv <= clusterLimit && nTilesC <= 32u * 16u * kClusterGW && nOcc <= kClusterMaxOcc &&
+    const bool clusterPath = !wide && !tilesPath && ctx->clusterViews > 0 && nv <= clusterLimit && nTilesC <= 32u * 16u * kClusterGW && nOcc <= kClusterMaxOcc &&
                              pick_cluster_size(ctx, b->width, b->height, (uint32_t)nOcc, nv) != 0u &&
                              (size_t)nv * scene->totalQuads * (blocks > 65536u ? 2 : 1) * (kRecStride * 4 + 8) <= (size_t(8) << 30);
-    p.viewOrder = (nv <= 16384u && !(clusterPath && nv * 2u <= (uint32_t)ctx->numSMs)) ? p.viewCost + chunk : nullptr;
+    p.viewOrder = (nv <= 16384u && !tilesPath && !(clusterPath && nv * 2u <= (uint32_t)ctx->numSMs)) ? p.viewCost + chunk : nullptr;
     if (!p.orders && nOcc > 1024u) {  // many occluders: order them on the whole GPU (keys live in the front buffer until k_prepare_views overwrites it)
       float* keys = reinterpret_cast<float*>(p.frontBuf);
       const size_t nKeys = (size_t)nv * nOcc;
@@ -928,6 +934,43 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
       }
       continue;
     }
+    if (tilesPath) {
+      const size_t recSlots = (size_t)scene->totalQuads * (blocks > 65536u ? 2 : 1);  // a wrapped primitive is two records
+      const size_t recBytes = recSlots * kRecStride * 4, hdrBytes = (recSlots * 8 + 15) & ~size_t(15), infoBytes = nOcc * 32, boxBytes = (nOcc * 8 + 15) & ~size_t(15);
+      if ((e = ensure_scratch(ctx, 11, recBytes + hdrBytes + infoBytes + boxBytes + 64))) return e;
+      const uint32_t nTiles = (uint32_t)nTilesC;
+      const uint32_t grid = std::min<uint32_t>((uint32_t)ctx->numSMs, (nTiles + kClusterGW - 1u) / kClusterGW);
+      const uint32_t K = (nTiles + grid * kClusterGW - 1u) / (grid * kClusterGW);
+      const size_t smem = TilesSmem::bytes(K);
+      if (ctx->smemTiles < smem) {
+        ORZ_CUDA(cudaFuncSetAttribute(k_raster_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->smemTiles = smem;
+      }
+      for (uint32_t v = 0; v < nv; ++v) {  // the scratch holds ONE view's records: the views follow each other on the stream
+        FrameParams pv = p;
+        pv.nViews = 1; pv.viewOrder = nullptr; pv.viewBase = 0; pv.groupViews = 1; pv.clusterK = K;
+        pv.frontBuf = p.frontBuf + (size_t)v * nOcc * kFrontWords;
+        if (p.orders) pv.orders = p.orders + (size_t)v * nOcc; else pv.orderBuf = p.orderBuf + (size_t)v * nOcc;
+        pv.depth = p.depth + (size_t)v * p.depthStride; pv.hiz = p.hiz + (size_t)v * p.hizStride;
+        pv.quadsSubmitted = p.quadsSubmitted ? p.quadsSubmitted + v : nullptr;
+        pv.hdrBuf = (uint2*)ctx->d_scratch[11];
+        pv.recInfo = (uint4*)((uint8_t*)ctx->d_scratch[11] + hdrBytes);
+        pv.occBox = (uint2*)((uint8_t*)pv.recInfo + infoBytes);
+        pv.recBuf = (uint32_t*)((uint8_t*)pv.occBox + boxBytes);
+        pv.totalQuads = (uint32_t)recSlots;
+        k_setup_views<<<dim3(pv.nOcc, 1), 256, 0, ctx->stream>>>(pv);
+        k_raster_tiles<<<grid, kClusterGW * 32, smem, ctx->stream>>>(pv, 0u, scene->totalQuads);
+        ctx->launches += 2;
+        ORZ_CUDA(cudaGetLastError());
+      }
+      if (p.gate) ORZ_CUDA(cudaMemsetAsync(p.gate, 1, (size_t)nv * nOcc, ctx->stream));  // no gate: every occluder is submitted
+      if (p.visBits || p.clipBits) {
+        FrameParams pq = p;
+        pq.viewOrder = nullptr; pq.viewBase = 0; pq.groupViews = nv;
+        if ((e = launch_query(ctx, pq, scene->nBoxes, ctx->stream))) return e;
+      }
+      continue;
+    }
     // Few views: one thread-block cluster per view (latency path, BASELINE configs 1 and 2)
     if (clusterPath) {
       FrameParams pc = p;
@@ -939,12 +982,10 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
       pc.recInfo = (uint4*)((uint8_t*)ctx->d_scratch[11] + ((hdrBytes + 15) & ~size_t(15)));
       pc.recBuf = (uint32_t*)((uint8_t*)pc.recInfo + (size_t)nv * nOcc * 32);
       pc.totalQuads = (uint32_t)recSlots;
-      k_setup_views<<<dim3(pc.nOcc, nv), 256, 0, ctx->stream>>>(pc);
-      ctx->launches++;
-      ORZ_CUDA(cudaGetLastError());
+      pc.occBox = nullptr;
       // Large batches: sub-batches (by descending cost) on auxiliary streams, so that the occludee queries of a
-      // finished sub-batch share the SMs with the cluster kernel of the next one (it leaves room for one
-      // query CTA per SM and about half of its issue slots).
+      // finished sub-batch fill the SMs the cluster kernel of the next one leaves idle; each sub-batch sets up its
+      // own views first, so the heaviest views start rasterising after a quarter of the setup work.
       const bool wantQ = p.visBits || p.clipBits;
       const int groupsC = (pc.viewOrder && wantQ && nv >= 256u) ? orz_context::kGroups : 1;
       if (groupsC > 1) ORZ_CUDA(cudaEventRecord(ctx->evFork, ctx->stream));
@@ -955,6 +996,9 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
         FrameParams pg = pc;
         pg.viewBase = (uint32_t)((uint64_t)nv * g / groupsC);
         pg.groupViews = (uint32_t)((uint64_t)nv * (g + 1) / groupsC) - pg.viewBase;
+        k_setup_views<<<dim3(pg.nOcc, pg.groupViews), 256, 0, st>>>(pg);
+        ctx->launches++;
+        ORZ_CUDA(cudaGetLastError());
         if ((e = launch_cluster(ctx, pg, pg.groupViews, nv, st))) return e;
         if (wantQ && (e = launch_query(ctx, pg, scene->nBoxes, st))) return e;
         if (groupsC > 1) {

@@ -64,7 +64,7 @@ def test_castle_1080p_1024_views_default_path(ctx):
     sc = api.Scene.from_prepared(ctx, cs.ps)
     n0 = ctx.launch_count
     out = sc.render_views(w, h, mvps, cam_pos=poss, want=ALL)
-    assert ctx.launch_count - n0 == 3 + 2 * 4  # prepare, sort, setup, 4 x (cluster raster + queries): the benchmarked launch chain
+    assert ctx.launch_count - n0 == 2 + 3 * 4  # prepare, sort, 4 x (setup + cluster raster + queries): the benchmarked launch chain
     check(cs, w, h, mvps, poss, out, cs.boxes)
     # the bits-only call of the bench (internal depth arena) must give the same bits
     out2 = sc.render_views(w, h, mvps, cam_pos=poss, want=("vis", "gate"))
@@ -133,14 +133,15 @@ def test_batch_kernel_four_groups_1080p(ctx):
     sc.close()
 
 
-@pytest.mark.parametrize("n_quads", [5_000_000])
-def test_config4_soup_4k_near_clip(ctx, n_quads):
-    """BASELINE config 4 at its stated size: 5 M quads = 10 M triangles, 3840x2160, camera inside the geometry, every
-    batch through rasterize<true>, no gate; incl. the 16-bit first-block index wrap (Rasterizer.cpp:1054)."""
+@pytest.mark.parametrize("n_quads,size", [(131_072, (1280, 720)), (131_072, (3840, 2160)), (5_000_000, (3840, 2160))])
+def test_config4_soup_near_clip(ctx, n_quads, size):
+    """BASELINE config 4 (the last case at its stated size: 5 M quads = 10 M triangles, 3840x2160): camera inside the
+    geometry, every batch through rasterize<true>, no gate -- one view at a time over the whole GPU, tile major
+    (k_raster_tiles); 3840x2160 includes the 16-bit first-block index wrap (Rasterizer.cpp:1054)."""
     from rasterizer_b200 import camera as cam
 
-    ps = wl.synthetic_soup(n_quads)
-    w, h = 3840, 2160
+    ps = wl.synthetic_soup(n_quads, cube=200.0 if n_quads > 1_000_000 else 60.0)
+    w, h = size
     ref = ro.RefScene.from_batches(ps.batches, ps.ref_min, ps.ref_max)
     boxes = ps.quad_boxes()[::97]
     sc = api.Scene.bake_on_device(ctx, ps.batches, ps.ref_min, ps.ref_max, boxes)
@@ -150,10 +151,13 @@ def test_config4_soup_4k_near_clip(ctx, n_quads):
     poss = np.zeros((len(dirs), 3), np.float32)
     orders = wl.orders_for(ref.centers, poss)
     flags = api.BATCH_NO_GATE | api.BATCH_FORCE_CLIPPED
-    out = sc.render_views(w, h, mvps, orders=orders, flags=flags, want=("vis", "clip", "depth", "hiz", "quads"))
+    n0 = ctx.launch_count
+    out = sc.render_views(w, h, mvps, orders=orders, flags=flags, want=("vis", "clip", "depth", "hiz", "quads", "gate"))
+    assert ctx.launch_count - n0 == 1 + 2 * len(dirs) + 1  # prepare, per view (setup + k_raster_tiles), queries
     mism = ro.check_views(ref, w, h, mvps, orders, boxes, mode=3, depth=out["depth"], hiz=out["hiz"], vis=out["vis"], clip=out["clip"],
                           quads=out["quads"])
     assert not mism.any(), ro.describe_mismatch(mism)
+    assert out["gate"].all()
     # the order computed on the GPU gives the same frame
     out2 = sc.render_views(w, h, mvps, cam_pos=poss, flags=flags, want=("vis", "hiz"))
     assert np.array_equal(out2["vis"], out["vis"]) and np.array_equal(out2["hiz"], out["hiz"])

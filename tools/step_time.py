@@ -52,6 +52,7 @@ def main():
             scene.render_views_raw(b, device=True)
         torch.cuda.synchronize()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        n0 = ctx.launch_count
         for a, z in ev:
             a.record(stream)
             scene.render_views_raw(b, device=True)
@@ -59,7 +60,7 @@ def main():
         torch.cuda.synchronize()
         ms = sorted(a.elapsed_time(z) for a, z in ev)
         out[name] = {"ms_median": ms[len(ms) // 2], "ms_min": ms[0], "views_per_s": n / ms[len(ms) // 2] * 1e3,
-                     "vis_checksum": int(d_vis.to(torch.int64).sum().item())}
+                     "vis_checksum": int(d_vis.to(torch.int64).sum().item()), "launches_per_step": (ctx.launch_count - n0) / reps}
     print(json.dumps(out))
 
 

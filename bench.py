@@ -653,6 +653,9 @@ def run_ours(args):
 if __name__ == "__main__":
     # the contract is ONE JSON line on stdout: libraries (NCCL prints its version banner there when NCCL_DEBUG is
     # set) write to fd 1 directly, so fd 1 is pointed at stderr and the line goes to the original stdout
+    import faulthandler
+
+    faulthandler.enable()  # a crash inside a native library still leaves a Python traceback on stderr
     _real_stdout = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     sys.stdout = _real_stdout

@@ -287,6 +287,17 @@ void ref_rast_submit_all(void* r, void* scene, const float* mvp, const uint32_t*
   }
 }
 
+// 1 when this library's own (64-byte aligned) operator new is the one its code gets -- see -Bsymbolic in the Makefile
+int ref_selftest_alignment() {
+  bool ok = true;
+  for (int i = 0; i < 8; ++i) {
+    std::vector<__m128i>* v = new std::vector<__m128i>(size_t(1000 + 37 * i));
+    ok = ok && (reinterpret_cast<uintptr_t>(v->data()) % 64 == 0);
+    delete v;
+  }
+  return ok ? 1 : 0;
+}
+
 // ---- host instruction probes (rcpps / rsqrtps define the results) -----------
 void ref_rcp_ps(const float* in, float* out, size_t n) {
   for (size_t i = 0; i < n; ++i) _mm_store_ss(out + i, _mm_rcp_ss(_mm_load_ss(in + i)));

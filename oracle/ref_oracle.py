@@ -62,6 +62,7 @@ def lib():
             "ref_rsqrt_ps": (None, [vp, vp, C.c_size_t]),
             "ref_bench_views": (C.c_double, [vp, u32, u32, vp, vp, u32, u32, vp, u32, u32, u32, vp]),
             "ref_check_views": (u32, [vp, u32, u32, vp, vp, u32, u32, vp, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp]),
+            "ref_selftest_alignment": (C.c_int, []),
             "ref_pool_create": (vp, [u32, u32, u32]),
             "ref_pool_free": (None, [vp]),
             "ref_pool_bench": (C.c_double, [vp, vp, vp, vp, u32, u32, vp, u32, u32, vp]),
@@ -69,6 +70,8 @@ def lib():
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
+        if not L.ref_selftest_alignment():
+            raise RuntimeError("oracle/_ref: the harness' aligned operator new is not in effect in this process (rebuild with oracle/Makefile)")
         _lib = L
     return _lib
 

@@ -825,12 +825,17 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
   const bool ownTargets = b->depth == nullptr;
   if (!ownTargets && blocks % 8 != 0) return fail(ORZ_ERR_ARG, "per-view depth output needs (w/8)*(h/8) to be a multiple of 8");
 
-  // views per chunk: everything when the caller owns the targets, else what fits the arena budget
+  // views per chunk: everything when the caller owns the targets, else what fits the arena budget; batches that take the
+  // cluster path (speculative setup records of every view: ~2.3 MB per Castle view) also stay within the record budget
   size_t chunk = b->nViews;
+  const size_t recPerView = (size_t)scene->totalQuads * (blocks > 65536u ? 2 : 1) * (kRecStride * 4 + 8);
+  const size_t recBudget = size_t(8) << 30;
+  if (ctx->clusterViews > 0 && b->nViews <= (size_t)ctx->clusterViews && recPerView > 0 && recBudget / recPerView >= 256)
+    chunk = std::min<size_t>(chunk, recBudget / recPerView);
   if (ownTargets) {
     const size_t perView = blocks * 128 + hizStride * 2;
     const size_t budget = std::max<size_t>(ctx->arenaBudget, perView);
-    chunk = std::max<size_t>(1, std::min<size_t>(b->nViews, budget / perView));
+    chunk = std::max<size_t>(1, std::min<size_t>(chunk, budget / perView));
     if ((e = ensure_scratch(ctx, 4, chunk * blocks * 128))) return e;
     if ((e = ensure_scratch(ctx, 5, chunk * hizStride * 2))) return e;
   }
@@ -879,7 +884,7 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
     const size_t nTilesC = (size_t)((b->width / 8 + kTileW - 1) / kTileW) * ((b->height / 8 + kTileH - 1) / kTileH);
     const bool clusterPath = !wide && !tilesPath && ctx->clusterViews > 0 && nv <= clusterLimit && nTilesC <= 32u * 16u * kClusterGW && nOcc <= kClusterMaxOcc &&
                              pick_cluster_size(ctx, b->width, b->height, (uint32_t)nOcc, nv) != 0u &&
-                             (size_t)nv * scene->totalQuads * (blocks > 65536u ? 2 : 1) * (kRecStride * 4 + 8) <= (size_t(8) << 30);
+                             (size_t)nv * recPerView <= recBudget;
     p.viewOrder = (nv <= 16384u && !tilesPath && !(clusterPath && nv * 2u <= (uint32_t)ctx->numSMs)) ? p.viewCost + chunk : nullptr;
     if (!p.orders && nOcc > 1024u) {  // many occluders: order them on the whole GPU (keys live in the front buffer until k_prepare_views overwrites it)
       float* keys = reinterpret_cast<float*>(p.frontBuf);

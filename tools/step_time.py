@@ -10,7 +10,8 @@ from rasterizer_b200 import api, camera as cam, workloads as wl
 CASES = {"castle1024": ("castle", 1920, 1080, 1024, "path", True), "probes1024": ("castle", 512, 256, 1024, "probes", False),
          "probes8192": ("castle", 512, 256, 8192, "probes", False), "castle1": ("castle", 1920, 1080, 1, "default", True),
          "sponza256": ("sponza", 1920, 1080, 256, "path", True), "sponza1": ("sponza", 1920, 1080, 1, "default", True),
-         "castle64": ("castle", 1920, 1080, 64, "path", True), "castle256": ("castle", 1920, 1080, 256, "path", True)}
+         "castle64": ("castle", 1920, 1080, 64, "path", True), "castle256": ("castle", 1920, 1080, 256, "path", True),
+         "probes2048": ("castle", 512, 256, 2048, "probes", False), "probes4096": ("castle", 512, 256, 4096, "probes", False)}
 
 
 def main():
@@ -20,6 +21,8 @@ def main():
     ctx = api.Context(0)
     if os.environ.get("ORZ_CLUSTER_SIZE"):
         ctx.set_cluster_size(int(os.environ["ORZ_CLUSTER_SIZE"]))
+    if os.environ.get("ORZ_GROUP_WARPS"):
+        ctx.set_group_warps(int(os.environ["ORZ_GROUP_WARPS"]))
     if os.environ.get("ORZ_CLUSTER_VIEWS"):
         ctx.set_cluster_views(int(os.environ["ORZ_CLUSTER_VIEWS"]))
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
@@ -36,7 +39,12 @@ def main():
             mvps = cam.view_projection(c["pos"], c["dir"], c["up"], c["fov"], w, h)[None].astype(np.float32)
             poss = np.array(c["pos"], np.float32)[None]
         else:
-            mvps, poss = (wl.camera_path if kind == "path" else wl.probe_views)(ps, n, w, h)
+            stride = int(os.environ.get("ORZ_VIEW_STRIDE", "1"))  # probes: every stride-th view of the 8192 (what one of `stride` GPUs gets)
+            if kind == "probes" and stride > 1:
+                mvps, poss = wl.probe_views(ps, n * stride, w, h)
+                mvps, poss = np.ascontiguousarray(mvps[::stride]), np.ascontiguousarray(poss[::stride])
+            else:
+                mvps, poss = (wl.camera_path if kind == "path" else wl.probe_views)(ps, n, w, h)
         blocks, words = (w // 8) * (h // 8), (scene.n_boxes + 31) // 32
         d_mvps, d_pos = torch.from_numpy(mvps).to(dev), torch.from_numpy(poss).to(dev)
         d_vis = torch.zeros((n, words), dtype=torch.int32, device=dev)

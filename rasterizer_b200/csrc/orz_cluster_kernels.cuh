@@ -44,8 +44,8 @@
 #ifndef ORZ_CLUSTER_CTAS_PER_SM
 #define ORZ_CLUSTER_CTAS_PER_SM 0  // > 0: compile with __launch_bounds__(threads, this) instead of the register cap
 #endif
-#ifndef ORZ_TILE_SMEM
-#define ORZ_TILE_SMEM 1  // 1: the open tile lives in shared memory, eight lanes per covered block; 0: in registers, one lane per block
+#ifndef ORZ_BLOCK_BOUND_SKIP
+#define ORZ_BLOCK_BOUND_SKIP 0  // 1: skip the block updates whose corner bound proves they change nothing (exact, every parity suite passes; measured 1-2 % SLOWER on Castle and Sponza: the test costs more than the skipped passes save)
 #endif
 #ifndef ORZ_TILE_PREFETCH
 #define ORZ_TILE_PREFETCH 1  // flush: prefetch the next tile's depth blocks into L1 while the current tile is processed
@@ -74,7 +74,7 @@ constexpr uint32_t kTileAuxWords = 64u + 32u + 8u;  // + per block: 64-bit cover
 
 struct ClusterSmem {
   static constexpr uint32_t kLutWords = ORZ_CLUSTER_LUT_SMEM ? 4096 * 2 : 0;
-  static constexpr uint32_t kTileAllWords = ORZ_TILE_SMEM ? kClusterGW * (kTileWords + kTileAuxWords) : 0;
+  static constexpr uint32_t kTileAllWords = kClusterGW * (kTileWords + kTileAuxWords);
   static constexpr uint32_t kStageWords = kClusterGW * kStageCap * kRecStride;
   static constexpr uint32_t kIdxWords = kClusterGW * kStageCap;
   static constexpr uint32_t kChainWords = kClusterGW * 12 * kChainStride;
@@ -242,7 +242,6 @@ __device__ __forceinline__ void step_chain(float cur, const float incX, const fl
   }
 }
 
-#if ORZ_TILE_SMEM
 // One primitive on the tile a warp has open (Rasterizer.cpp:1098-1292 restricted to the tile's
 // blocks).  d[8] / h are the lane's block and its HiZ, kept in registers between primitives.
 __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, const int lane, const uint32_t x0, const uint32_t y0,
@@ -302,16 +301,12 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
       upd = (mk.x | mk.y) != 0u;
     }
   }
-  const uint32_t updMask = __ballot_sync(kFull, upd);
-  if (upd) {
-    reinterpret_cast<uint2*>(aux)[lane] = mk;  // the eight lanes that will share this block read their half of it
-    reinterpret_cast<uint8_t*>(aux + 96u)[__popc(updMask & ((1u << lane) - 1u))] = (uint8_t)lane;  // covered blocks, compacted
-  }
+  const uint32_t covMask = __ballot_sync(kFull, upd);
   __syncwarp();  // orders this primitive's reads of the edge slots before the next primitive's writes (free: the warp is converged)
-  if (!updMask) return;
+  if (!covMask) return;
   {  // the eight depth lanes (Rasterizer.cpp:1103-1112) at the covered blocks
-    const uint32_t rLast = (31u - (uint32_t)__clz((int)updMask)) >> 3, rLo = ((uint32_t)__ffs((int)updMask) - 1u) >> 3;
-    const uint32_t cols = (updMask | (updMask >> 8) | (updMask >> 16) | (updMask >> 24)) & 0xffu;
+    const uint32_t rLast = (31u - (uint32_t)__clz((int)covMask)) >> 3, rLo = ((uint32_t)__ffs((int)covMask) - 1u) >> 3;
+    const uint32_t cols = (covMask | (covMask >> 8) | (covMask >> 16) | (covMask >> 24)) & 0xffu;
     const uint32_t cA = (uint32_t)__ffs((int)cols) - 1u, cB = 31u - (uint32_t)__clz((int)cols);
     const uint32_t r = (uint32_t)lane >> 3, l = (uint32_t)lane & 7u;
     const bool active = r >= rLo && r <= rLast;
@@ -320,6 +315,28 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
     step_chain(cur, dzdx, dzdy, y0 + rLo - minY, r - rLo, x0 + cA - minX + rec[20], cA, cB, active, sm + (4u + l) * kChainStride + r * 8u);
   }
   __syncwarp();
+#if ORZ_BLOCK_BOUND_SKIP
+  // Exact early-out per block (the reference only tests the primitive's GLOBAL maximum against the HiZ, Rasterizer.cpp:1149):
+  // every pixel the update can produce is bounded by the largest of the block's four corner samples -- rows 0 and 9 at
+  // pixels 0 and 7: rounding is monotone, so the samples of a row are ordered like the plane in x (same increments, same
+  // number of steps in every lane) and rows 0 / 1 / 8 / 9 like the plane in y, and avg_epu16 never exceeds its larger
+  // operand -- so when that bound is <= the HiZ (the smallest stored pixel) the max-merge cannot change a pixel and the
+  // block is left alone.  Castle: 1.5 % of the updates, interiors (Sponza): a quarter (profiles/r1_update_stats.json).
+  if (upd && h != 1u) {
+    const float* smd = sm + 4u * kChainStride + lane;
+    const float d0 = smd[0], d3 = smd[3u * kChainStride], d4 = smd[4u * kChainStride], d7 = smd[7u * kChainStride];
+    const uint32_t ca = pack16x2(d0, ORZ_FMA(dzdx, 0.5f, d3)), cb = pack16x2(dzdy + d4, dzdy + ORZ_FMA(dzdx, 0.5f, d7));
+    const uint32_t m2 = __vmaxu2(ca, cb);
+    if (max(m2 & 0xffffu, m2 >> 16) <= h) upd = false;
+  }
+#endif
+  const uint32_t updMask = __ballot_sync(kFull, upd);
+  if (upd) {
+    reinterpret_cast<uint2*>(aux)[lane] = mk;  // the eight lanes that will share this block read their half of it
+    reinterpret_cast<uint8_t*>(aux + 96u)[__popc(updMask & ((1u << lane) - 1u))] = (uint8_t)lane;  // covered blocks, compacted
+  }
+  __syncwarp();
+  if (!updMask) return;
   // ---- depth rows, merge, HiZ (Rasterizer.cpp:1241-1290): the covered blocks of the tile FOUR AT A TIME, eight lanes
   // per block -- lane (rr, i) of a group builds pixels 2i, 2i+1 of rows rr, 2+rr, 4+rr, 6+rr (orz_pixel.h: the eight
   // items of a block share no arithmetic), so a primitive that covers n blocks costs ceil(n / 4) short passes at
@@ -361,128 +378,6 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
   }
   __syncwarp();  // chain slots, masks and the tile are rewritten / read by the next primitive
 }
-
-#else  // register-resident tile, one lane per block (round-1 form, kept for A/B measurements)
-// One primitive on the tile a warp has open (Rasterizer.cpp:1098-1292 restricted to the tile's
-// blocks).  d[8] / h are the lane's block and its HiZ, kept in registers between primitives.
-__device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, const int lane, const uint32_t x0, const uint32_t y0,
-                                          const uint32_t x1, const uint32_t y1, const uint2* __restrict__ lut, float* __restrict__ sm,
-                                          uint4 (&d)[8], uint32_t& h, bool& dirty) {
-  const uint32_t w0 = rec[0], w1 = rec[1], w2 = rec[2];
-  const uint32_t minX = w0 & 0xffffu, minY = w0 >> 16, maxZ = w2 & 0xffffu, mode = w2 >> 16;
-  const uint32_t xa = max(minX, x0), xb = min(minX + (w1 & 0xffffu), x1), ya = max(minY, y0), yb = min(minY + (w1 >> 16), y1);
-  const uint32_t bx = x0 + ((uint32_t)lane & 7u), by = y0 + ((uint32_t)lane >> 3);
-  const bool pass = bx >= xa && bx < xb && by >= ya && by < yb && h < maxZ;  // Rasterizer.cpp:1148-1152
-  const uint32_t passMask = __ballot_sync(kFull, pass);
-  if (!passMask) return;  // the whole tile is behind its HiZ: no chain has to be stepped at all
-
-  // ---- the iterated add chains, stepped exactly as the reference does: y chain from the
-  // primitive's first row (Rasterizer.cpp:1130), x chain restarted at every row start (:1136,
-  // :1145).  One lane per (chain, tile row): first the 4 edge offsets x 4 rows (16 lanes); the
-  // 8 depth chains x 4 rows (32 lanes) only when some block is really covered.
-  const float dzdx = u2f(rec[3]), dzdy = u2f(rec[4]);
-  const uint32_t rFirst = ya - y0;
-  {
-    const uint32_t rLast = (31u - (uint32_t)__clz((int)passMask)) >> 3;
-    const uint32_t cols = (passMask | (passMask >> 8) | (passMask >> 16) | (passMask >> 24)) & 0xffu;
-    const uint32_t cA = (uint32_t)__ffs((int)cols) - 1u, cB = 31u - (uint32_t)__clz((int)cols);
-    const uint32_t r = (uint32_t)lane >> 2, e = (uint32_t)lane & 3u;
-    const bool active = lane < 16 && r >= rFirst && r <= rLast;
-    float cur = 0.0f, incX = 0.0f, incY = 0.0f;
-    if (active) { cur = u2f(rec[14 + e]); incX = u2f(rec[6 + e]); incY = u2f(rec[10 + e]); }
-    step_chain(cur, incX, incY, ya - minY, r - rFirst, x0 + cA - minX + rec[20], cA, cB, active, sm + e * kChainStride + r * 8u);
-  }
-  __syncwarp();
-
-  // ---- coverage (Rasterizer.cpp:1155-1239)
-  bool upd = false;
-  uint2 mk = make_uint2(0u, 0u);
-  if (pass) {
-    const float o0 = sm[0 * kChainStride + lane], o1 = sm[1 * kChainStride + lane], o2 = sm[2 * kChainStride + lane], o3 = sm[3 * kChainStride + lane];
-    const uint32_t slope01 = rec[18], slope23 = rec[19];
-    const uint32_t s0 = slope01 & 0xffffu, s1 = slope01 >> 16, s2 = slope23 & 0xffffu, s3 = slope23 >> 16;
-    if (mode == kConvex) {
-      if (!(o0 >= 63.0f || o1 >= 63.0f || o2 >= 63.0f || o3 >= 63.0f)) {
-        const uint2 A = lut[s0 | (uint32_t)__float2int_rz(fmaxf(o0, 0.0f))], B = lut[s1 | (uint32_t)__float2int_rz(fmaxf(o1, 0.0f))];
-        const uint2 C2 = lut[s2 | (uint32_t)__float2int_rz(fmaxf(o2, 0.0f))], D = lut[s3 | (uint32_t)__float2int_rz(fmaxf(o3, 0.0f))];
-        mk.x = (A.x & B.x) & (C2.x & D.x); mk.y = (A.y & B.y) & (C2.y & D.y);
-        upd = true;  // no empty-mask test on this path (Rasterizer.cpp:1186)
-      }
-    } else {
-      const uint32_t q0 = o0 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o0, 0.0f), 63.0f)) : 0u;
-      const uint32_t q1 = o1 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o1, 0.0f), 63.0f)) : 0u;
-      const uint32_t q2 = o2 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o2, 0.0f), 63.0f)) : 0u;
-      const uint32_t q3 = o3 < 2147483648.0f ? (uint32_t)__float2int_rz(fminf(fmaxf(o3, 0.0f), 63.0f)) : 0u;
-      const uint2 A = lut[s0 | q0], B = lut[s1 | q1], C2 = lut[s2 | q2], D = lut[s3 | q3];
-      if (mode == kTriangle0) { mk.x = A.x & B.x & C2.x; mk.y = A.y & B.y & C2.y; }
-      else if (mode == kTriangle1) { mk.x = A.x & C2.x & D.x; mk.y = A.y & C2.y & D.y; }
-      else if (mode == kConcaveRight) { mk.x = (A.x | D.x) & (B.x & C2.x); mk.y = (A.y | D.y) & (B.y & C2.y); }
-      else if (mode == kConcaveCenter) { mk.x = (A.x & B.x) | (C2.x & D.x); mk.y = (A.y & B.y) | (C2.y & D.y); }
-      else { mk.x = (A.x & D.x) & (B.x | C2.x); mk.y = (A.y & D.y) & (B.y | C2.y); }
-      upd = (mk.x | mk.y) != 0u;
-    }
-  }
-  const uint32_t updMask = __ballot_sync(kFull, upd);
-  __syncwarp();  // orders this primitive's reads of the edge slots before the next primitive's writes (free: the warp is converged)
-  if (!updMask) return;
-  {  // the eight depth lanes (Rasterizer.cpp:1103-1112) at the covered blocks
-    const uint32_t rLast = (31u - (uint32_t)__clz((int)updMask)) >> 3, rLo = ((uint32_t)__ffs((int)updMask) - 1u) >> 3;
-    const uint32_t cols = (updMask | (updMask >> 8) | (updMask >> 16) | (updMask >> 24)) & 0xffu;
-    const uint32_t cA = (uint32_t)__ffs((int)cols) - 1u, cB = 31u - (uint32_t)__clz((int)cols);
-    const uint32_t r = (uint32_t)lane >> 3, l = (uint32_t)lane & 7u;
-    const bool active = r >= rLo && r <= rLast;
-    const float s = -0.5f + 1.0f / 16.0f;
-    const float cur = ORZ_FMA(dzdx, s + 0.125f * (float)(l & 3u), ORZ_FMA(dzdy, (l >> 2) ? s + 0.125f : s, u2f(rec[5])));
-    step_chain(cur, dzdx, dzdy, y0 + rLo - minY, r - rLo, x0 + cA - minX + rec[20], cA, cB, active, sm + (4u + l) * kChainStride + r * 8u);
-  }
-  __syncwarp();
-  // ---- depth rows, merge into the registers, HiZ (Rasterizer.cpp:1241-1290)
-  if (upd) {
-    const float* smd = sm + 4 * kChainStride + lane;
-    const uint32_t keep = h != 1u ? 0xffffffffu : 0u;  // a cleared block is overwritten (:1271-1278)
-    uint32_t r0[2][4], r4[2][4], r8[2][4];
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      float dv[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) dv[k] = smd[(4 * rr + k) * kChainStride];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float a = dv[(2 * i) & 3], b = dv[(2 * i + 1) & 3];
-        if (i >= 2) { a = ORZ_FMA(dzdx, 0.5f, a); b = ORZ_FMA(dzdx, 0.5f, b); }  // depth1, :1243
-        const float a8 = dzdy + a, b8 = dzdy + b;                                // depth8/9, :1244-1245
-        r0[rr][i] = pack16(a) | (pack16(b) << 16);  // (a run-time "finite plane" shortcut for the NaN guard was measured slower)
-        r8[rr][i] = pack16(a8) | (pack16(b8) << 16);
-        r4[rr][i] = avg_u16x2(r0[rr][i], r8[rr][i]);                             // :1252
-      }
-    }
-    uint32_t mnAcc = 0xffffffffu;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int y = 2 * k + rr;
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          w[i] = k == 0 ? r0[rr][i] : k == 2 ? r4[rr][i] : k == 1 ? avg_u16x2(r0[rr][i], r4[rr][i]) : avg_u16x2(r4[rr][i], r8[rr][i]);  // :1253-1254
-        const int ky = (rr ? 0 : 4) + k;  // pixel px of row y <-> bit 8 px + ky (:1257-1268)
-        const uint32_t lo = ((mk.x >> ky) & 0x01010101u) * 0xffu, hi = ((mk.y >> ky) & 0x01010101u) * 0xffu;
-        uint4 v;
-        v.x = __vmaxu2(w[0] & __byte_perm(lo, 0u, 0x1100), d[y].x & keep);
-        v.y = __vmaxu2(w[1] & __byte_perm(lo, 0u, 0x3322), d[y].y & keep);
-        v.z = __vmaxu2(w[2] & __byte_perm(hi, 0u, 0x1100), d[y].z & keep);
-        v.w = __vmaxu2(w[3] & __byte_perm(hi, 0u, 0x3322), d[y].w & keep);
-        d[y] = v;
-        mnAcc = __vminu2(mnAcc, __vminu2(__vminu2(v.x, v.y), __vminu2(v.z, v.w)));
-      }
-    h = min(mnAcc & 0xffffu, mnAcc >> 16);  // Rasterizer.cpp:1287-1290
-    dirty = true;
-  }
-  __syncwarp();  // chain slots are rewritten by the next primitive
-}
-
-#endif
 
 // Per-warp state of the tile-major traversal: the tiles a warp owns (lane k keeps tile k) and its slices of the CTA's
 // shared memory.  Shared by the cluster kernel (one view per cluster, gated) and k_raster_tiles (one ungated view over
@@ -577,7 +472,6 @@ struct TileWalker {
           if (bxn < T.blocksX && byn < T.blocksY && myHiz[32u * k2] != 1) prefetch_l1(reinterpret_cast<uint4*>(T.depth) + (size_t)(byn * T.blocksX + bxn) * 8u);
         }
 #endif
-#if ORZ_TILE_SMEM
         // open the tile: its depth goes to shared memory, one block per lane, as 8 items (rr, i) of 4 row pairs each
         // (item slot swizzled by the block so that both this lane-per-block pass and the eight-lanes-per-block
         // update passes are bank-conflict free); cleared blocks (HiZ 1) enter as zero
@@ -616,26 +510,6 @@ struct TileWalker {
           T.hiz[by * T.blocksX + bx] = (uint16_t)h;
         }
         __syncwarp();  // the next tile's open overwrites the slots other lanes may still be reading
-      #else
-        // bring the tile into registers
-        const uint32_t bx = x0 + lx, by = y0 + ly;
-        const bool inScreen = bx < x1 && by < y1;
-        uint4* dp = reinterpret_cast<uint4*>(T.depth) + (size_t)(by * T.blocksX + bx) * 8u;
-        uint32_t h = inScreen ? (uint32_t)myHiz[32u * k] : 0xffffu;  // off-screen lanes never pass
-        const bool load = inScreen && h != 1u;
-        uint4 d[8];
-#pragma unroll
-        for (int y = 0; y < 8; ++y) d[y] = load ? dp[y] : make_uint4(0u, 0u, 0u, 0u);
-        bool dirty = false;
-        for (; hits; hits &= hits - 1u)
-          tile_prim(myStage + ((uint32_t)__ffs((int)hits) - 1u) * kRecStride, lane, x0, y0, x1, y1, lut, myChain, d, h, dirty);
-        if (dirty) {
-#pragma unroll
-          for (int y = 0; y < 8; ++y) dp[y] = d[y];
-          myHiz[32u * k] = (uint16_t)h;
-          T.hiz[by * T.blocksX + bx] = (uint16_t)h;
-        }
-      #endif
       }
       __syncwarp();
       nStaged = 0;

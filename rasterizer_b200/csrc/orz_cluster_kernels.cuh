@@ -44,6 +44,12 @@
 #ifndef ORZ_CLUSTER_CTAS_PER_SM
 #define ORZ_CLUSTER_CTAS_PER_SM 0  // > 0: compile with __launch_bounds__(threads, this) instead of the register cap
 #endif
+#ifndef ORZ_ROUNDS_X2
+#define ORZ_ROUNDS_X2 0  // 1: the eight-lanes-per-block update takes two covered blocks per group and pass
+#endif
+#ifndef ORZ_CHAIN_MERGED
+#define ORZ_CHAIN_MERGED 1  // depth chains are stepped together with the edge chains: one pass, two independent add sequences per lane (0: depth chains only after the coverage test; measured 4-10 % slower, profiles/r2_variants.txt)
+#endif
 #ifndef ORZ_BLOCK_BOUND_SKIP
 #define ORZ_BLOCK_BOUND_SKIP 0  // 1: skip the block updates whose corner bound proves they change nothing (exact, every parity suite passes; measured 1-2 % SLOWER on Castle and Sponza: the test costs more than the skipped passes save)
 #endif
@@ -242,6 +248,24 @@ __device__ __forceinline__ void step_chain(float cur, const float incX, const fl
   }
 }
 
+// Two chains of the same (tile row, columns) per lane: independent add sequences that share the loop overhead and hide
+// each other's latency (ORZ_CHAIN_MERGED: depth chain l and, in the lanes with l < 4, edge chain l).
+__device__ __forceinline__ void step_chain2(float a, const float aX, const float aY, float b, const float bX, const float bY, const uint32_t nyCommon,
+                                            const uint32_t nyExtra, const uint32_t nPre, const uint32_t cA, const uint32_t cB, const bool actA,
+                                            const bool actB, float* outA, float* outB) {
+#pragma unroll kChainUnroll
+  for (uint32_t i = 0; i < nyCommon; ++i) { a = a + aY; b = b + bY; }  // Rasterizer.cpp:1130-1131
+#pragma unroll
+  for (uint32_t i = 0; i < kTileH - 1u; ++i) { a = i < nyExtra ? a + aY : a; b = i < nyExtra ? b + bY : b; }
+#pragma unroll kChainUnroll
+  for (uint32_t i = 0; i < nPre; ++i) { a = aX + a; b = bX + b; }      // Rasterizer.cpp:1145-1146
+  for (uint32_t c = cA; c <= cB; ++c) {
+    if (actA) outA[c] = a;
+    if (actB) outB[c] = b;
+    a = aX + a; b = bX + b;
+  }
+}
+
 // One primitive on the tile a warp has open (Rasterizer.cpp:1098-1292 restricted to the tile's
 // blocks).  d[8] / h are the lane's block and its HiZ, kept in registers between primitives.
 __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, const int lane, const uint32_t x0, const uint32_t y0,
@@ -261,6 +285,20 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
   // 8 depth chains x 4 rows (32 lanes) only when some block is really covered.
   const float dzdx = u2f(rec[3]), dzdy = u2f(rec[4]);
   const uint32_t rFirst = ya - y0;
+#if ORZ_CHAIN_MERGED
+  {  // all twelve chains in one pass: lane (row r, l) steps depth chain l and, for l < 4, edge chain l
+    const uint32_t rLast = (31u - (uint32_t)__clz((int)passMask)) >> 3;
+    const uint32_t cols = (passMask | (passMask >> 8) | (passMask >> 16) | (passMask >> 24)) & 0xffu;
+    const uint32_t cA = (uint32_t)__ffs((int)cols) - 1u, cB = 31u - (uint32_t)__clz((int)cols);
+    const uint32_t r = (uint32_t)lane >> 3, l = (uint32_t)lane & 7u, e = l & 3u;
+    const bool active = r >= rFirst && r <= rLast;
+    const float s = -0.5f + 1.0f / 16.0f;
+    const float curD = ORZ_FMA(dzdx, s + 0.125f * (float)(l & 3u), ORZ_FMA(dzdy, (l >> 2) ? s + 0.125f : s, u2f(rec[5])));
+    const float curE = u2f(rec[14 + e]), eX = u2f(rec[6 + e]), eY = u2f(rec[10 + e]);
+    step_chain2(curD, dzdx, dzdy, curE, eX, eY, ya - minY, r - rFirst, x0 + cA - minX + rec[20], cA, cB, active, active && l < 4u,
+                sm + (4u + l) * kChainStride + r * 8u, sm + e * kChainStride + r * 8u);
+  }
+#else
   {
     const uint32_t rLast = (31u - (uint32_t)__clz((int)passMask)) >> 3;
     const uint32_t cols = (passMask | (passMask >> 8) | (passMask >> 16) | (passMask >> 24)) & 0xffu;
@@ -271,6 +309,7 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
     if (active) { cur = u2f(rec[14 + e]); incX = u2f(rec[6 + e]); incY = u2f(rec[10 + e]); }
     step_chain(cur, incX, incY, ya - minY, r - rFirst, x0 + cA - minX + rec[20], cA, cB, active, sm + e * kChainStride + r * 8u);
   }
+#endif
   __syncwarp();
 
   // ---- coverage (Rasterizer.cpp:1155-1239)
@@ -304,6 +343,7 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
   const uint32_t covMask = __ballot_sync(kFull, upd);
   __syncwarp();  // orders this primitive's reads of the edge slots before the next primitive's writes (free: the warp is converged)
   if (!covMask) return;
+#if !ORZ_CHAIN_MERGED
   {  // the eight depth lanes (Rasterizer.cpp:1103-1112) at the covered blocks
     const uint32_t rLast = (31u - (uint32_t)__clz((int)covMask)) >> 3, rLo = ((uint32_t)__ffs((int)covMask) - 1u) >> 3;
     const uint32_t cols = (covMask | (covMask >> 8) | (covMask >> 16) | (covMask >> 24)) & 0xffu;
@@ -315,6 +355,7 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
     step_chain(cur, dzdx, dzdy, y0 + rLo - minY, r - rLo, x0 + cA - minX + rec[20], cA, cB, active, sm + (4u + l) * kChainStride + r * 8u);
   }
   __syncwarp();
+#endif
 #if ORZ_BLOCK_BOUND_SKIP
   // Exact early-out per block (the reference only tests the primitive's GLOBAL maximum against the HiZ, Rasterizer.cpp:1149):
   // every pixel the update can produce is bounded by the largest of the block's four corner samples -- rows 0 and 9 at
@@ -349,6 +390,25 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
     uint32_t* hNew = aux + 64u;
     const uint8_t* covered = reinterpret_cast<const uint8_t*>(aux + 96u);
     const uint32_t n = (uint32_t)__popc(updMask);
+#if ORZ_ROUNDS_X2
+    // two blocks per group and pass: the two updates are independent, so their shared-memory and ALU latencies overlap
+    for (uint32_t j = g; j < n + g; j += 8u) {  // (n + g: every group makes the same number of passes -- the shuffles below are full width)
+      const uint32_t bA = j < n ? (uint32_t)covered[j] : 32u, bB = j + 4u < n ? (uint32_t)covered[j + 4u] : 32u;
+      uint32_t mnA = 0xffffffffu, mnB = 0xffffffffu;
+      uint4 dA, dB;
+      uint4* slotA = tile + bA * 8u + (it ^ (bA & 7u));
+      uint4* slotB = tile + bB * 8u + (it ^ (bB & 7u));
+      if (bA < 32u) dA = *slotA;
+      if (bB < 32u) dB = *slotB;
+      if (bA < 32u) { mnA = update_item(c0[bA], c1[bA], dzdx, dzdy, i >= 2u, aux[2u * bA + half] >> shift, dA.x, dA.y, dA.z, dA.w); *slotA = dA; }
+      if (bB < 32u) { mnB = update_item(c0[bB], c1[bB], dzdx, dzdy, i >= 2u, aux[2u * bB + half] >> shift, dB.x, dB.y, dB.z, dB.w); *slotB = dB; }
+      mnA = __vminu2(mnA, __shfl_xor_sync(kFull, mnA, 1)); mnB = __vminu2(mnB, __shfl_xor_sync(kFull, mnB, 1));
+      mnA = __vminu2(mnA, __shfl_xor_sync(kFull, mnA, 2)); mnB = __vminu2(mnB, __shfl_xor_sync(kFull, mnB, 2));
+      mnA = __vminu2(mnA, __shfl_xor_sync(kFull, mnA, 4)); mnB = __vminu2(mnB, __shfl_xor_sync(kFull, mnB, 4));
+      if (it == 0u && bA < 32u) hNew[bA] = min(mnA & 0xffffu, mnA >> 16);  // Rasterizer.cpp:1287-1290
+      if (it == 0u && bB < 32u) hNew[bB] = min(mnB & 0xffffu, mnB >> 16);
+    }
+#else
     for (uint32_t j = g; j < n + g; j += 4u) {  // (n + g: every group makes the same number of passes -- the shuffles below are full width)
       const uint32_t b = j < n ? (uint32_t)covered[j] : 32u;  // block (= owner lane) this group of eight lanes takes in this pass
       uint32_t mn = 0xffffffffu;
@@ -363,6 +423,7 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
       mn = __vminu2(mn, __shfl_xor_sync(kFull, mn, 4));
       if (it == 0u && b < 32u) hNew[b] = min(mn & 0xffffu, mn >> 16);  // Rasterizer.cpp:1287-1290
     }
+#endif
     __syncwarp();
     if (upd) {
       h = hNew[lane];

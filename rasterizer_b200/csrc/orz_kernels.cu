@@ -103,7 +103,9 @@ struct orz_context {
   uint32_t* d_counter = nullptr;
   void* d_scratch[12] = {nullptr};
   size_t scratchBytes[12] = {0};
-  uint32_t* h_pinned = nullptr;  // small pinned mailbox for scalar results
+  uint32_t* h_pinned = nullptr;  // small pinned + mapped mailbox for scalar results (k_query2d writes its tagged answer straight into it)
+  uint32_t* d_mail = nullptr;    // the same words as the device sees them
+  uint32_t mailSeq = 0;          // tag of the last per-call query
   static constexpr int kGroups = 4;          // sub-batches pipelined on auxiliary streams
   cudaStream_t aux[kGroups] = {nullptr};
   cudaEvent_t evFork = nullptr, evJoin[kGroups] = {nullptr};
@@ -173,7 +175,9 @@ extern "C" int orz_context_create(int device, orz_context** out) {
   ORZ_CUDA_OR(orz_context_destroy(ctx), cudaMalloc(&ctx->d_rcp, ctx->h_rcp.size() * 4));
   ORZ_CUDA_OR(orz_context_destroy(ctx), cudaMemcpy(ctx->d_rcp, ctx->h_rcp.data(), ctx->h_rcp.size() * 4, cudaMemcpyHostToDevice));
   ORZ_CUDA_OR(orz_context_destroy(ctx), cudaMalloc(&ctx->d_counter, 64));
-  ORZ_CUDA_OR(orz_context_destroy(ctx), cudaHostAlloc(&ctx->h_pinned, 64, cudaHostAllocDefault));
+  ORZ_CUDA_OR(orz_context_destroy(ctx), cudaHostAlloc(&ctx->h_pinned, 64, cudaHostAllocMapped));
+  memset(ctx->h_pinned, 0, 64);
+  ORZ_CUDA_OR(orz_context_destroy(ctx), cudaHostGetDevicePointer((void**)&ctx->d_mail, ctx->h_pinned, 0));
   *out = ctx;
   return ORZ_OK;
 }
@@ -342,12 +346,22 @@ extern "C" int orz_rasterizer_query2d(orz_rasterizer* r, uint32_t minX, uint32_t
   if (!r || !visible) return fail(ORZ_ERR_ARG, "orz_rasterizer_query2d: bad arguments");
   if (maxX >= r->T.width || maxY >= r->T.height || minX > maxX || minY > maxY) return fail(ORZ_ERR_ARG, "orz_rasterizer_query2d: rectangle outside the buffer");
   ORZ_CUDA(cudaSetDevice(r->ctx->device));
-  k_query2d<<<1, 256, 0, r->ctx->stream>>>(r->T, minX, maxX, minY, maxY, maxZ, r->ctx->d_counter + 8);
-  r->ctx->launches++;
-  ORZ_CUDA(cudaMemcpyAsync(r->ctx->h_pinned, r->ctx->d_counter + 8, 4, cudaMemcpyDeviceToHost, r->ctx->stream));
-  ORZ_CUDA(cudaStreamSynchronize(r->ctx->stream));
-  *visible = r->ctx->h_pinned[0] ? 1 : 0;
-  return ORZ_OK;
+  // the answer comes back through mapped pinned memory, tagged with this call's sequence number: no copy, no stream sync
+  orz_context* ctx = r->ctx;
+  const uint32_t tag = (++ctx->mailSeq) << 1;
+  k_query2d<<<1, 256, 0, ctx->stream>>>(r->T, minX, maxX, minY, maxY, maxZ, ctx->d_mail, tag);
+  ctx->launches++;
+  ORZ_CUDA(cudaGetLastError());
+  volatile uint32_t* mail = ctx->h_pinned;
+  for (uint32_t spins = 0;; ++spins) {
+    const uint32_t v = *mail;
+    if ((v & ~1u) == tag) { *visible = (int)(v & 1u); return ORZ_OK; }
+    if ((spins & 0x3fffu) == 0x3fffu) {  // now and then: has the stream failed (or finished without our store)?
+      const cudaError_t q = cudaStreamQuery(ctx->stream);
+      if (q != cudaSuccess && q != cudaErrorNotReady) return fail(ORZ_ERR_CUDA, std::string("orz_rasterizer_query2d: ") + cudaGetErrorString(q));
+      if (q == cudaSuccess && ((*mail) & ~1u) != tag) return fail(ORZ_ERR_CUDA, "orz_rasterizer_query2d: the query kernel finished without an answer");
+    }
+  }
 }
 extern "C" int orz_rasterizer_query_visibility(orz_rasterizer* r, const float* bmin, const float* bmax, int* visible, int* needsClipping) {
   if (!r || !bmin || !bmax || !visible) return fail(ORZ_ERR_ARG, "orz_rasterizer_query_visibility: bad arguments");

@@ -80,13 +80,18 @@ __global__ void k_query_boxes(const ViewMatrices vm, const float4* boxes, uint32
   if (i < n) out[i] = f.status == kBoxNearClip ? 3 : (vis ? 1 : 0);
 }
 
-__global__ void k_query2d(Target T, uint32_t minX, uint32_t maxX, uint32_t minY, uint32_t maxY, uint32_t maxZ, uint32_t* out) {
+// `out` is a word of MAPPED pinned host memory: the answer travels with the tag of the call (sequence number << 1) in one
+// 32-bit store, and the host thread that is waiting for this bool sees it without a copy, an event or a stream sync
+__global__ void k_query2d(Target T, uint32_t minX, uint32_t maxX, uint32_t minY, uint32_t maxY, uint32_t maxZ, volatile uint32_t* out, uint32_t tag) {
   __shared__ uint32_t s_flag;
   if (threadIdx.x == 0) s_flag = 0u;
   __syncthreads();
   query2d_coop(T, minX, maxX, minY, maxY, maxZ, threadIdx.x, blockDim.x, &s_flag);
   __syncthreads();
-  if (threadIdx.x == 0) *out = s_flag;
+  if (threadIdx.x == 0) {
+    *out = tag | (s_flag ? 1u : 0u);
+    __threadfence_system();
+  }
 }
 
 // readBackDepth, Rasterizer.cpp:351-399: one thread per pixel, BGRA8 row-major

@@ -3,8 +3,10 @@
 // the frame loop of Main.cpp:181-206 over a prepared scene file.  Compiled by tests/test_dropin_cpp.py
 // against rasterizer_b200/csrc/dropin; the same source would compile against the reference headers.
 //   usage: dropin_frame scene.orzscn width height mvp.bin order.bin out.bin
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <memory>
@@ -71,5 +73,28 @@ int main(int argc, char** argv) {
   out.write(reinterpret_cast<const char*>(depth.data()), depth.size() * 2);
   out.write(reinterpret_cast<const char*>(image.data()), image.size());
   std::printf("ok %u batches %u quads\n", nBatches, nQuads);
+  // optional timing of the same frame loop (ORZ_FRAME_REPS=n): what an unchanged application pays per frame
+  if (const char* reps = std::getenv("ORZ_FRAME_REPS")) {
+    const int n = atoi(reps);
+    unsigned visibleCount = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    for (int rep = 0; rep < n; ++rep) {
+      rasterizer.clear();
+      rasterizer.setModelViewProjection(mvp.data());
+      for (size_t i = 0; i < order.size(); ++i) {
+        const auto& occluder = occluders[order[i]];
+        bool needsClipping = false;
+        if (rasterizer.queryVisibility(occluder->m_boundsMin, occluder->m_boundsMax, needsClipping)) {
+          ++visibleCount;
+          if (needsClipping) rasterizer.rasterize<true>(*occluder);
+          else rasterizer.rasterize<false>(*occluder);
+        }
+      }
+    }
+    bool nc = false;  // the last query also waits for the last rasterize
+    rasterizer.queryVisibility(occluders[0]->m_boundsMin, occluders[0]->m_boundsMax, nc);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / (n > 0 ? n : 1);
+    std::printf("frame_ms %.4f visible_per_frame %u\n", ms, n > 0 ? visibleCount / unsigned(n) : 0u);
+  }
   return 0;
 }

@@ -35,7 +35,9 @@ def test_cpp_frame_loop(tmp_path, name, size):
     mvp = cam.view_projection(c["pos"], c["dir"], c["up"], c["fov"], w, h)
     order = cam.front_to_back_order(np.stack([b[1] for b in baked]), c["pos"])
     mvp.tofile(tmp_path / "mvp.bin"); order.tofile(tmp_path / "order.bin")
-    subprocess.check_call([exe, scene_file, str(w), str(h), str(tmp_path / "mvp.bin"), str(tmp_path / "order.bin"), str(tmp_path / "out.bin")])
+    log = subprocess.check_output([exe, scene_file, str(w), str(h), str(tmp_path / "mvp.bin"), str(tmp_path / "order.bin"), str(tmp_path / "out.bin")],
+                                  env=dict(os.environ, ORZ_FRAME_REPS="50"), text=True)
+    print(log)  # frame_ms: the per-call frame loop as an unchanged application runs it
     raw = np.fromfile(tmp_path / "out.bin", np.uint8)
     n, blocks = len(order), (w // 8) * (h // 8)
     gate = raw[:n]

@@ -53,6 +53,15 @@
 #ifndef ORZ_BLOCK_BOUND_SKIP
 #define ORZ_BLOCK_BOUND_SKIP 0  // 1: skip the block updates whose corner bound proves they change nothing (exact, every parity suite passes; measured 1-2 % SLOWER on Castle and Sponza: the test costs more than the skipped passes save)
 #endif
+#ifndef ORZ_CHAIN_F32X2
+#define ORZ_CHAIN_F32X2 1  // 1: the two chains of a lane advance with one packed add.rn.f32x2 (sm_100: two IEEE single adds in one instruction)
+#endif
+#ifndef ORZ_HIZ_ATOMIC
+#define ORZ_HIZ_ATOMIC 1  // 1: a block's new HiZ is folded with one shared-memory atomicMin per lane instead of three shuffles per pass
+#endif
+#ifndef ORZ_COVERED_WORD
+#define ORZ_COVERED_WORD 1  // 1: the covered-block list is stored pass-major so that a group fetches its (up to) eight blocks with ONE 64-bit load
+#endif
 #ifndef ORZ_TILE_PREFETCH
 #define ORZ_TILE_PREFETCH 1  // flush: prefetch the next tile's depth blocks into L1 while the current tile is processed
 #endif
@@ -248,11 +257,32 @@ __device__ __forceinline__ void step_chain(float cur, const float incX, const fl
   }
 }
 
+// two IEEE single-precision adds (round to nearest even, denormals kept) in one instruction: sm_100's packed add
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float lo_f32x2(uint64_t v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
+__device__ __forceinline__ float hi_f32x2(uint64_t v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
 // Two chains of the same (tile row, columns) per lane: independent add sequences that share the loop overhead and hide
 // each other's latency (ORZ_CHAIN_MERGED: depth chain l and, in the lanes with l < 4, edge chain l).
 __device__ __forceinline__ void step_chain2(float a, const float aX, const float aY, float b, const float bX, const float bY, const uint32_t nyCommon,
                                             const uint32_t nyExtra, const uint32_t nPre, const uint32_t cA, const uint32_t cB, const bool actA,
                                             const bool actB, float* outA, float* outB) {
+#if ORZ_CHAIN_F32X2
+  uint64_t ab = pack_f32x2(a, b);
+  const uint64_t incY = pack_f32x2(aY, bY), incX = pack_f32x2(aX, bX);
+#pragma unroll kChainUnroll
+  for (uint32_t i = 0; i < nyCommon; ++i) ab = add_f32x2(ab, incY);  // Rasterizer.cpp:1130-1131
+#pragma unroll
+  for (uint32_t i = 0; i < kTileH - 1u; ++i) ab = i < nyExtra ? add_f32x2(ab, incY) : ab;
+#pragma unroll kChainUnroll
+  for (uint32_t i = 0; i < nPre; ++i) ab = add_f32x2(incX, ab);      // Rasterizer.cpp:1145-1146
+  for (uint32_t c = cA; c <= cB; ++c) {
+    if (actA) outA[c] = lo_f32x2(ab);
+    if (actB) outB[c] = hi_f32x2(ab);
+    ab = add_f32x2(incX, ab);
+  }
+#else
 #pragma unroll kChainUnroll
   for (uint32_t i = 0; i < nyCommon; ++i) { a = a + aY; b = b + bY; }  // Rasterizer.cpp:1130-1131
 #pragma unroll
@@ -264,6 +294,7 @@ __device__ __forceinline__ void step_chain2(float a, const float aX, const float
     if (actB) outB[c] = b;
     a = aX + a; b = bX + b;
   }
+#endif
 }
 
 // One primitive on the tile a warp has open (Rasterizer.cpp:1098-1292 restricted to the tile's
@@ -374,7 +405,15 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
   const uint32_t updMask = __ballot_sync(kFull, upd);
   if (upd) {
     reinterpret_cast<uint2*>(aux)[lane] = mk;  // the eight lanes that will share this block read their half of it
-    reinterpret_cast<uint8_t*>(aux + 96u)[__popc(updMask & ((1u << lane) - 1u))] = (uint8_t)lane;  // covered blocks, compacted
+    const uint32_t at = (uint32_t)__popc(updMask & ((1u << lane) - 1u));  // covered blocks, compacted
+#if ORZ_COVERED_WORD
+    reinterpret_cast<uint8_t*>(aux + 96u)[(at & 3u) * 8u + (at >> 2)] = (uint8_t)lane;  // pass-major: group g's blocks are bytes 8 g .. 8 g + 7
+#else
+    reinterpret_cast<uint8_t*>(aux + 96u)[at] = (uint8_t)lane;
+#endif
+#if ORZ_HIZ_ATOMIC
+    aux[64u + lane] = 0xffffffffu;
+#endif
   }
   __syncwarp();
   if (!updMask) return;
@@ -409,19 +448,33 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
       if (it == 0u && bB < 32u) hNew[bB] = min(mnB & 0xffffu, mnB >> 16);
     }
 #else
+#if ORZ_COVERED_WORD
+    const uint2 cw = reinterpret_cast<const uint2*>(covered)[g];
+    uint64_t mine8 = (uint64_t)cw.x | ((uint64_t)cw.y << 32);
+#endif
     for (uint32_t j = g; j < n + g; j += 4u) {  // (n + g: every group makes the same number of passes -- the shuffles below are full width)
+#if ORZ_COVERED_WORD
+      const uint32_t b = j < n ? (uint32_t)mine8 & 0xffu : 32u;
+      mine8 >>= 8;
+#else
       const uint32_t b = j < n ? (uint32_t)covered[j] : 32u;  // block (= owner lane) this group of eight lanes takes in this pass
+#endif
       uint32_t mn = 0xffffffffu;
       if (b < 32u) {
         uint4* slot = tile + b * 8u + (it ^ (b & 7u));
         uint4 d = *slot;
         mn = update_item(c0[b], c1[b], dzdx, dzdy, i >= 2u, aux[2u * b + half] >> shift, d.x, d.y, d.z, d.w);
         *slot = d;
+#if ORZ_HIZ_ATOMIC
+        atomicMin(&hNew[b], min(mn & 0xffffu, mn >> 16));  // Rasterizer.cpp:1287-1290
+#endif
       }
+#if !ORZ_HIZ_ATOMIC
       mn = __vminu2(mn, __shfl_xor_sync(kFull, mn, 1));
       mn = __vminu2(mn, __shfl_xor_sync(kFull, mn, 2));
       mn = __vminu2(mn, __shfl_xor_sync(kFull, mn, 4));
       if (it == 0u && b < 32u) hNew[b] = min(mn & 0xffffu, mn >> 16);  // Rasterizer.cpp:1287-1290
+#endif
     }
 #endif
     __syncwarp();
@@ -640,7 +693,6 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
   T.depth = p.depth + (size_t)view * p.depthStride;
   T.hiz = p.hiz + (size_t)view * p.hizStride;
   const bool useGate = (p.flags & ORZ_BATCH_NO_GATE) == 0u;
-  const bool forceClip = (p.flags & ORZ_BATCH_FORCE_CLIPPED) != 0u;
   const uint4* recInfo = p.recInfo + (size_t)view * nOcc * 2u;
   uint16_t* myHiz = s_hiz + (size_t)warp * K * 32u + lane;  // + 32 k
   float* myChain = s_chain + warp * (12 * kChainStride);
@@ -649,7 +701,6 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
   uint4* myTile = reinterpret_cast<uint4*>(s_tileAll + (uint32_t)warp * kTileWords);
   uint32_t* myAux = s_tileAll + (uint32_t)GW * kTileWords + (uint32_t)warp * kTileAuxWords;
   const uint32_t lx = (uint32_t)lane & 7u, ly = (uint32_t)lane >> 3;
-  const bool reporter = rank == 0u && warp == 0 && lane == 0;  // writes the per-slot outputs of the view
 
   TileWalker tw;
   tw.T = T; tw.lane = lane; tw.lx = lx; tw.ly = ly;
@@ -676,17 +727,13 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
     if (!tiles_meeting(hd[1] >> 3, hd[2] >> 3, hd[3] >> 3, hd[4] >> 3)) answer_no(s);
   }
 
-  uint32_t quadsSubmitted = 0;
   uint4 infoNext = recInfo[0], boxNext = recInfo[1];  // {records, first slot, quads}, {block rectangle}: fetched one slot ahead of the walk
   for (uint32_t s = 0; s < nOcc; ++s) {
     const uint32_t* hd = s_head + s * kHeadWords;
     const uint32_t status = hd[0];
     const uint4 info = infoNext, box = boxNext;
     if (s + 1u < nOcc) { infoNext = recInfo[2u * s + 2u]; boxNext = recInfo[2u * s + 3u]; }
-    if (status == kBoxCulled) {
-      if (p.gate && reporter) p.gate[(size_t)view * nOcc + s] = 0;
-      continue;
-    }
+    if (status == kBoxCulled) continue;
     // my tiles that the occluder's primitives can touch; their record headers start their way to the SM now, so that
     // the gate test and the wait for the decision hide the L2 round trip (wasted on the candidates the gate rejects)
     uint32_t tmOcc = 0u;
@@ -696,10 +743,8 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
 #if ORZ_HDR_PREFETCH_EARLY
     if (tmOcc && (uint32_t)lane * 16u < info.x) prefetch_l1(hdrs + (uint32_t)lane * 16u);  // <= 504 headers = 32 lines
 #endif
-    bool visible = true, clipped = false;
-    if (status == kBoxNearClip) {
-      clipped = useGate ? true : forceClip;
-    } else {
+    bool visible = true;
+    if (status != kBoxNearClip) {
       // ---- gate: query2D (Rasterizer.cpp:283-349) on the part of the rectangle that lies on my tiles
       const uint32_t minX = hd[1], maxX = hd[2], minY = hd[3], maxY = hd[4], maxZ = hd[5];
       const uint32_t bx0 = minX >> 3, bx1 = maxX >> 3, by0 = minY >> 3, by1 = maxY >> 3;
@@ -718,6 +763,10 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
         if (found) { if (lane < C) st_flag_remote(s_vis + s, (uint32_t)lane, 1u); }
         else if (!flag_set_warp(vis)) answer_no(s);
       }
+      // Only the warps that would rasterise the occluder -- its primitives touch their tiles -- depend on the decision;
+      // every other warp has given its answer and walks on (the view's outputs are read from the decision words after
+      // the final barrier, when all of them are final)
+      if (!tmOcc) continue;
       // visible as soon as ONE warp says so, invisible when all 16 C warps have said no
       const uint32_t* done = s_doneCta + s;
       for (;;) {
@@ -728,14 +777,9 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
 #endif
       }
     }
-    if (reporter) {
-      if (p.gate) p.gate[(size_t)view * nOcc + s] = (uint8_t)((visible ? 1 : 0) | (clipped && useGate ? 2 : 0));
-      if (visible) quadsSubmitted += info.z;
-    }
-    if (!visible || info.x == 0u) continue;
+    if (!visible || !tmOcc) continue;
 
     // ---- rasterize<clipped>(occluder): the records k_setup_views wrote, on my tiles
-    if (!tmOcc) continue;
     const uint32_t cnt = info.x;
     const uint32_t* recs = p.recBuf + recBase * kRecStride;
 #if !ORZ_HDR_PREFETCH_EARLY
@@ -744,9 +788,20 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
 
     tw.rasterize(recs, hdrs, cnt, tmOcc);
   }
-  if (p.quadsSubmitted && reporter) p.quadsSubmitted[view] = quadsSubmitted;
   if (p.exportDepth) tw.zero_cleared_tiles();
   cluster.sync();  // no CTA may leave while another one can still write its decision words
+  // ---- the view's per-slot outputs (Main.cpp:195-204), from the now final decision words
+  if (rank == 0u && warp == 0 && (p.gate || p.quadsSubmitted)) {
+    uint32_t quadsSubmitted = 0;
+    for (uint32_t s = (uint32_t)lane; s < nOcc; s += 32u) {
+      const uint32_t status = s_head[s * kHeadWords];
+      const bool visible = status == kBoxNearClip || (status == kBoxRect && s_vis[s] != 0u);
+      if (p.gate) p.gate[(size_t)view * nOcc + s] = (uint8_t)((visible ? 1 : 0) | (status == kBoxNearClip && useGate ? 2 : 0));
+      if (visible) quadsSubmitted += recInfo[2u * s].z;
+    }
+    quadsSubmitted = __reduce_add_sync(kFull, quadsSubmitted);
+    if (p.quadsSubmitted && lane == 0) p.quadsSubmitted[view] = quadsSubmitted;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -18,7 +18,9 @@ marks = [
     ("tile_prim: depth rows + merge + HiZ", "// ---- depth rows, merge, HiZ (Rasterizer.cpp:1241-1290)"),
     ("kernel prologue (tables, clear)", "k_raster_views_cluster(const FrameParams p) {"),
     ("pre-announce loop", "// ---- candidates whose rectangle does not touch my tiles"),
-    ("walk: slot bookkeeping", "  uint32_t quadsSubmitted = 0;"),
+    ("walk: slot bookkeeping", "  uint4 infoNext = recInfo[0]"),
+    ("decision words (ld_flag / votes: polling)", "__device__ __forceinline__ uint32_t ld_flag("),
+    ("gate test: one block (query_block_h)", "// one block of query2D (Rasterizer.cpp:305-343)"),
     ("gate test on my tiles", "// ---- gate: query2D (Rasterizer.cpp:283-349) on the part"),
     ("decision wait (spin)", "// visible as soon as ONE warp says so"),
     ("occluder prologue (info, box)", "// ---- rasterize<clipped>(occluder): the records k_setup_views wrote"),
@@ -26,7 +28,7 @@ marks = [
     ("flush: tile open (load)", "// open the tile: its depth goes to shared memory"),
     ("flush: tile close (store)", "        if (dirty) {"),
     ("header scan + staging", "    for (uint32_t r0 = 0; r0 < cnt; r0 += 32u) {"),
-    ("epilogue (zero fill, final barrier)", "  if (p.quadsSubmitted && reporter)"),
+    ("epilogue (zero fill, final barrier, outputs)", "cluster.sync();  // no CTA may leave"),
 ]
 bounds = sorted((line_of(m), name) for name, m in marks)
 def region(f, n):

@@ -62,6 +62,12 @@
 #ifndef ORZ_COVERED_WORD
 #define ORZ_COVERED_WORD 1  // 1: the covered-block list is stored pass-major so that a group fetches its (up to) eight blocks with ONE 64-bit load
 #endif
+#ifndef ORZ_LUT_BULK
+#define ORZ_LUT_BULK 1  // 1: the 32 KB edge-mask table comes in with ONE cp.async.bulk (TMA engine, mbarrier complete_tx) instead of a copy loop
+#endif
+#ifndef ORZ_ASYNC_GATHER
+#define ORZ_ASYNC_GATHER 1  // 1: staged records are gathered with cp.async (no registers, no scoreboard wait): the L2 round trip overlaps the tile test and the first tile's open
+#endif
 #ifndef ORZ_TILE_PREFETCH
 #define ORZ_TILE_PREFETCH 1  // flush: prefetch the next tile's depth blocks into L1 while the current tile is processed
 #endif
@@ -201,6 +207,29 @@ __global__ void __launch_bounds__(256) k_setup_views(const FrameParams p) {
   }
 }
 
+// ---- asynchronous copies: cp.async (per-lane, 4 bytes: records are 84 bytes at arbitrary slots) and the bulk copy engine
+__device__ __forceinline__ void cp_async_word(uint32_t* smemDst, const uint32_t* gmemSrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gmemSrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smemDst, const void* gmemSrc, uint32_t bytes, uint64_t* bar) {
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((uint32_t)__cvta_generic_to_shared(smemDst)),
+               "l"(gmemSrc), "r"(bytes), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(b), "r"(parity) : "memory");
+}
+
 // Decision words of the cluster kernel are read and written concurrently by design (monotonic
 // flags / counters): strong relaxed accesses at cluster scope, which the PTX memory model allows
 // to race (no data is published through them, only the decision itself).  compute-sanitizer's
@@ -259,8 +288,8 @@ __device__ __forceinline__ void step_chain(float cur, const float incX, const fl
 
 // two IEEE single-precision adds (round to nearest even, denormals kept) in one instruction: sm_100's packed add
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ float lo_f32x2(uint64_t v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
-__device__ __forceinline__ float hi_f32x2(uint64_t v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
+__device__ __forceinline__ float lo_f32x2(uint64_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi_f32x2(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
 __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
 // Two chains of the same (tile row, columns) per lane: independent add sequences that share the loop overhead and hide
@@ -554,10 +583,20 @@ struct TileWalker {
     // staged records -> my tiles, tile-major, each tile's primitives in order
     auto flush = [&]() {
       __syncwarp();
+#if ORZ_ASYNC_GATHER
+      // the records start their way from L2 now and are waited for after the first tile has been opened
+#pragma unroll 8
+      for (uint32_t i = 0; i < nStaged; ++i)
+        if (lane < kRecStride) cp_async_word(myStage + i * kRecStride + lane, recs + (size_t)myIdx[i] * kRecStride + lane);
+      bool gathered = false;
+      uint2 myHdr = make_uint2(0u, 0u);
+      if ((uint32_t)lane < nStaged) myHdr = hdrs[myIdx[lane]];  // (L1: the scan has just read it)
+#else
 #pragma unroll 8
       for (uint32_t i = 0; i < nStaged; ++i)
         if (lane < kRecStride) myStage[i * kRecStride + lane] = recs[(size_t)myIdx[i] * kRecStride + lane];
       __syncwarp();
+#endif
       // which staged records touch which of my tiles: lane k keeps the answer for tile k
       uint32_t myHits = 0u;
       for (uint32_t m = tmOcc; m; m &= m - 1u) {
@@ -566,7 +605,11 @@ struct TileWalker {
         const uint32_t x1 = min(x0 + kTileW, T.blocksX), y1 = min(y0 + kTileH, T.blocksY);
         bool touches = false;
         if ((uint32_t)lane < nStaged) {
+#if ORZ_ASYNC_GATHER
+          const uint32_t a = myHdr.x, b = myHdr.y;
+#else
           const uint32_t a = myStage[lane * kRecStride], b = myStage[lane * kRecStride + 1];
+#endif
           const uint32_t minX = a & 0xffffu, minY = a >> 16;
           touches = minX < x1 && minX + (b & 0xffffu) > x0 && minY < y1 && minY + (b >> 16) > y0;
         }
@@ -606,6 +649,9 @@ struct TileWalker {
           mine[(rr * 4u + 2u) ^ sw] = make_uint4(R[0].z, R[1].z, R[2].z, R[3].z);
           mine[(rr * 4u + 3u) ^ sw] = make_uint4(R[0].w, R[1].w, R[2].w, R[3].w);
         }
+#if ORZ_ASYNC_GATHER
+        if (!gathered) { cp_async_wait_all(); gathered = true; }
+#endif
         __syncwarp();
         bool dirty = false;
         for (; hits; hits &= hits - 1u)
@@ -625,6 +671,9 @@ struct TileWalker {
         }
         __syncwarp();  // the next tile's open overwrites the slots other lanes may still be reading
       }
+#if ORZ_ASYNC_GATHER
+      if (!gathered) cp_async_wait_all();  // (no tile was opened: the staging area must still be quiet before it is refilled)
+#endif
       __syncwarp();
       nStaged = 0;
     };
@@ -684,7 +733,14 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
   const uint32_t nOcc = p.nOcc;
 
   const uint32_t* front = p.frontBuf + (size_t)view * nOcc * kFrontWords;
+#if ORZ_LUT_BULK && ORZ_CLUSTER_LUT_SMEM
+  __shared__ __align__(8) uint64_t s_lutBar;
+  if (tid == 0) mbar_init(&s_lutBar, 1u);
+  __syncthreads();
+  if (tid == 0) bulk_load(s_lut, p.lut, 4096u * 8u, &s_lutBar);  // one bulk copy, in flight while the heads are staged and the tiles cleared
+#else
   if (ORZ_CLUSTER_LUT_SMEM) for (uint32_t i = tid; i < 4096u; i += NT) s_lut[i] = p.lut[i];
+#endif
   for (uint32_t i = tid; i < nOcc * kHeadWords; i += NT) s_head[i] = front[(size_t)(i / kHeadWords) * kFrontWords + i % kHeadWords];
   for (uint32_t i = tid; i < nOcc * 3u; i += NT) s_vis[i] = 0u;
 
@@ -709,6 +765,9 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
   tw.own_tiles(gw, kWarps, K);
   tw.clear_tiles();
   const uint32_t tileX0 = tw.tileX0, tileY0 = tw.tileY0;
+#if ORZ_LUT_BULK && ORZ_CLUSTER_LUT_SMEM
+  mbar_wait(&s_lutBar, 0u);
+#endif
   cluster.sync();  // tables staged, decision words zero in every CTA before the first remote access
 
   // "no visible pixel on my tiles" for candidate s: per-CTA count, forwarded by the CTA's last warp

@@ -45,7 +45,7 @@
 #define ORZ_CLUSTER_CTAS_PER_SM 0  // > 0: compile with __launch_bounds__(threads, this) instead of the register cap
 #endif
 #ifndef ORZ_ROUNDS_X2
-#define ORZ_ROUNDS_X2 0  // 1: the eight-lanes-per-block update takes two covered blocks per group and pass
+#define ORZ_ROUNDS_X2 0  // 1: the eight-lanes-per-block update takes two covered blocks per group and pass (needs ORZ_HIZ_ATOMIC and ORZ_COVERED_WORD; measured neutral to 1.5 % slower, profiles/r2y_*)
 #endif
 #ifndef ORZ_CHAIN_MERGED
 #define ORZ_CHAIN_MERGED 1  // depth chains are stepped together with the edge chains: one pass, two independent add sequences per lane (0: depth chains only after the coverage test; measured 4-10 % slower, profiles/r2_variants.txt)
@@ -460,21 +460,35 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
     const uint32_t n = (uint32_t)__popc(updMask);
 #if ORZ_ROUNDS_X2
     // two blocks per group and pass: the two updates are independent, so their shared-memory and ALU latencies overlap
-    for (uint32_t j = g; j < n + g; j += 8u) {  // (n + g: every group makes the same number of passes -- the shuffles below are full width)
-      const uint32_t bA = j < n ? (uint32_t)covered[j] : 32u, bB = j + 4u < n ? (uint32_t)covered[j + 4u] : 32u;
-      uint32_t mnA = 0xffffffffu, mnB = 0xffffffffu;
-      uint4 dA, dB;
+    const uint2 cw2 = reinterpret_cast<const uint2*>(covered)[g];
+    uint64_t mine8 = (uint64_t)cw2.x | ((uint64_t)cw2.y << 32);  // pass-major list: bytes 2 t, 2 t + 1 = this group's blocks of pass t
+    for (uint32_t j = g; j < n; j += 8u) {
+      const uint32_t bA = (uint32_t)mine8 & 0xffu, bB = j + 4u < n ? (uint32_t)(mine8 >> 8) & 0xffu : 32u;
+      mine8 >>= 16;
       uint4* slotA = tile + bA * 8u + (it ^ (bA & 7u));
-      uint4* slotB = tile + bB * 8u + (it ^ (bB & 7u));
-      if (bA < 32u) dA = *slotA;
-      if (bB < 32u) dB = *slotB;
-      if (bA < 32u) { mnA = update_item(c0[bA], c1[bA], dzdx, dzdy, i >= 2u, aux[2u * bA + half] >> shift, dA.x, dA.y, dA.z, dA.w); *slotA = dA; }
-      if (bB < 32u) { mnB = update_item(c0[bB], c1[bB], dzdx, dzdy, i >= 2u, aux[2u * bB + half] >> shift, dB.x, dB.y, dB.z, dB.w); *slotB = dB; }
-      mnA = __vminu2(mnA, __shfl_xor_sync(kFull, mnA, 1)); mnB = __vminu2(mnB, __shfl_xor_sync(kFull, mnB, 1));
-      mnA = __vminu2(mnA, __shfl_xor_sync(kFull, mnA, 2)); mnB = __vminu2(mnB, __shfl_xor_sync(kFull, mnB, 2));
-      mnA = __vminu2(mnA, __shfl_xor_sync(kFull, mnA, 4)); mnB = __vminu2(mnB, __shfl_xor_sync(kFull, mnB, 4));
-      if (it == 0u && bA < 32u) hNew[bA] = min(mnA & 0xffffu, mnA >> 16);  // Rasterizer.cpp:1287-1290
-      if (it == 0u && bB < 32u) hNew[bB] = min(mnB & 0xffffu, mnB >> 16);
+      uint4* slotB = tile + (bB & 31u) * 8u + (it ^ (bB & 7u));
+      uint4 dA = *slotA, dB = *slotB;
+      const uint32_t mnA = update_item(c0[bA], c1[bA], dzdx, dzdy, i >= 2u, aux[2u * bA + half] >> shift, dA.x, dA.y, dA.z, dA.w);
+      *slotA = dA;
+      atomicMin(&hNew[bA], min(mnA & 0xffffu, mnA >> 16));  // Rasterizer.cpp:1287-1290
+      if (bB < 32u) {
+        const uint32_t mnB = update_item(c0[bB], c1[bB], dzdx, dzdy, i >= 2u, aux[2u * bB + half] >> shift, dB.x, dB.y, dB.z, dB.w);
+        *slotB = dB;
+        atomicMin(&hNew[bB], min(mnB & 0xffffu, mnB >> 16));
+      }
+    }
+#else
+#if ORZ_HIZ_ATOMIC && ORZ_COVERED_WORD
+    const uint2 cw = reinterpret_cast<const uint2*>(covered)[g];
+    uint64_t mine8 = (uint64_t)cw.x | ((uint64_t)cw.y << 32);
+    for (uint32_t j = g; j < n; j += 4u) {  // (no collective inside: every group makes just the passes it has blocks for)
+      const uint32_t b = (uint32_t)mine8 & 0xffu;  // block (= owner lane) this group of eight lanes takes in this pass
+      mine8 >>= 8;
+      uint4* slot = tile + b * 8u + (it ^ (b & 7u));
+      uint4 d = *slot;
+      const uint32_t mn = update_item(c0[b], c1[b], dzdx, dzdy, i >= 2u, aux[2u * b + half] >> shift, d.x, d.y, d.z, d.w);
+      *slot = d;
+      atomicMin(&hNew[b], min(mn & 0xffffu, mn >> 16));  // Rasterizer.cpp:1287-1290
     }
 #else
 #if ORZ_COVERED_WORD
@@ -505,6 +519,7 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
       if (it == 0u && b < 32u) hNew[b] = min(mn & 0xffffu, mn >> 16);  // Rasterizer.cpp:1287-1290
 #endif
     }
+#endif
 #endif
     __syncwarp();
     if (upd) {
@@ -743,6 +758,7 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
 #endif
   for (uint32_t i = tid; i < nOcc * kHeadWords; i += NT) s_head[i] = front[(size_t)(i / kHeadWords) * kFrontWords + i % kHeadWords];
   for (uint32_t i = tid; i < nOcc * 3u; i += NT) s_vis[i] = 0u;
+  if (tid * 4u < nOcc) prefetch_l1(p.recInfo + (size_t)view * nOcc * 2u + tid * 8u);  // the walk reads two uint4 per slot: four slots per line
 
   Target T;
   T.width = p.width; T.height = p.height; T.blocksX = p.width >> 3; T.blocksY = p.height >> 3;

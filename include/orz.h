@@ -194,6 +194,11 @@ int orz_context_set_traversal(orz_context* ctx, int mapping);
 int orz_context_set_cluster_views(orz_context* ctx, int maxViews);
 /* tuning: CTAs (of 16 warps) per cluster on that path: 1, 2, 4, 8 or 16; 0 = automatic (from the target size and the batch) */
 int orz_context_set_cluster_size(orz_context* ctx, int ctas);
+/* tuning: height of the screen tiles a warp owns, in 8x8 blocks.  Cluster path: 4 (8 x 4 blocks, lane <-> block; what
+ * 0 = automatic picks) or 1 (8 x 1 strips: four times the tiles; measured slower for the view batches, kept selectable);
+ * per-call rasterize (orz_rasterizer_rasterize): 1 (default, measured faster there) or 4.  Results are identical for
+ * every choice. */
+int orz_context_set_tile_height(orz_context* ctx, int clusterTileHeight, int perCallTileHeight);
 /* tuning: warps cooperating on one view in the batch kernel (1, 2, 4, 8, 16); 0 = automatic */
 int orz_context_set_group_warps(orz_context* ctx, int warps);
 

@@ -74,6 +74,7 @@ EXPORTS = {
     "orz_context_set_arena_bytes": (C.c_int, [C.c_void_p, C.c_size_t]),
     "orz_context_set_cluster_views": (C.c_int, [C.c_void_p, C.c_int]),
     "orz_context_set_cluster_size": (C.c_int, [C.c_void_p, C.c_int]),
+    "orz_context_set_tile_height": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "orz_context_set_traversal": (C.c_int, [C.c_void_p, C.c_int]),
     "orz_edge_mask_table": (C.c_int, [C.c_void_p]),
     "orz_probe_host_rcp": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -252,6 +253,9 @@ class Context:
 
     def set_cluster_size(self, ctas: int):
         _check(lib().orz_context_set_cluster_size(self.h, ctas))
+
+    def set_tile_height(self, cluster: int = 0, per_call: int = 1):
+        _check(lib().orz_context_set_tile_height(self.h, cluster, per_call))
 
     def set_arena_bytes(self, nbytes: int):
         _check(lib().orz_context_set_arena_bytes(self.h, nbytes))

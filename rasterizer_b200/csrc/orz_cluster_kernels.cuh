@@ -272,12 +272,13 @@ __device__ __forceinline__ bool query_block_h(const Target& T, uint32_t bx, uint
 // cA, then the values at tile columns [cA, cB] go to out[c].  Trip counts are warp uniform except
 // nyExtra (0-3, the row inside the tile); every add is the reference's own (same operands, same
 // order), only lanes differ in what they own.
+template <uint32_t TH>
 __device__ __forceinline__ void step_chain(float cur, const float incX, const float incY, const uint32_t nyCommon, const uint32_t nyExtra,
                                            const uint32_t nPre, const uint32_t cA, const uint32_t cB, const bool active, float* out) {
 #pragma unroll kChainUnroll
   for (uint32_t i = 0; i < nyCommon; ++i) cur = cur + incY;  // Rasterizer.cpp:1130-1131
 #pragma unroll
-  for (uint32_t i = 0; i < kTileH - 1u; ++i) cur = i < nyExtra ? cur + incY : cur;
+  for (uint32_t i = 0; i + 1u < TH; ++i) cur = i < nyExtra ? cur + incY : cur;
 #pragma unroll kChainUnroll
   for (uint32_t i = 0; i < nPre; ++i) cur = incX + cur;      // Rasterizer.cpp:1145-1146
   for (uint32_t c = cA; c <= cB; ++c) {
@@ -294,6 +295,7 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) { uint64_t
 
 // Two chains of the same (tile row, columns) per lane: independent add sequences that share the loop overhead and hide
 // each other's latency (ORZ_CHAIN_MERGED: depth chain l and, in the lanes with l < 4, edge chain l).
+template <uint32_t TH>
 __device__ __forceinline__ void step_chain2(float a, const float aX, const float aY, float b, const float bX, const float bY, const uint32_t nyCommon,
                                             const uint32_t nyExtra, const uint32_t nPre, const uint32_t cA, const uint32_t cB, const bool actA,
                                             const bool actB, float* outA, float* outB) {
@@ -303,7 +305,7 @@ __device__ __forceinline__ void step_chain2(float a, const float aX, const float
 #pragma unroll kChainUnroll
   for (uint32_t i = 0; i < nyCommon; ++i) ab = add_f32x2(ab, incY);  // Rasterizer.cpp:1130-1131
 #pragma unroll
-  for (uint32_t i = 0; i < kTileH - 1u; ++i) ab = i < nyExtra ? add_f32x2(ab, incY) : ab;
+  for (uint32_t i = 0; i + 1u < TH; ++i) ab = i < nyExtra ? add_f32x2(ab, incY) : ab;
 #pragma unroll kChainUnroll
   for (uint32_t i = 0; i < nPre; ++i) ab = add_f32x2(incX, ab);      // Rasterizer.cpp:1145-1146
   for (uint32_t c = cA; c <= cB; ++c) {
@@ -315,7 +317,7 @@ __device__ __forceinline__ void step_chain2(float a, const float aX, const float
 #pragma unroll kChainUnroll
   for (uint32_t i = 0; i < nyCommon; ++i) { a = a + aY; b = b + bY; }  // Rasterizer.cpp:1130-1131
 #pragma unroll
-  for (uint32_t i = 0; i < kTileH - 1u; ++i) { a = i < nyExtra ? a + aY : a; b = i < nyExtra ? b + bY : b; }
+  for (uint32_t i = 0; i + 1u < TH; ++i) { a = i < nyExtra ? a + aY : a; b = i < nyExtra ? b + bY : b; }
 #pragma unroll kChainUnroll
   for (uint32_t i = 0; i < nPre; ++i) { a = aX + a; b = bX + b; }      // Rasterizer.cpp:1145-1146
   for (uint32_t c = cA; c <= cB; ++c) {
@@ -328,6 +330,7 @@ __device__ __forceinline__ void step_chain2(float a, const float aX, const float
 
 // One primitive on the tile a warp has open (Rasterizer.cpp:1098-1292 restricted to the tile's
 // blocks).  d[8] / h are the lane's block and its HiZ, kept in registers between primitives.
+template <uint32_t TH>
 __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, const int lane, const uint32_t x0, const uint32_t y0,
                                           const uint32_t x1, const uint32_t y1, const uint2* __restrict__ lut, float* __restrict__ sm,
                                           uint4* __restrict__ tile, uint32_t* __restrict__ aux, uint32_t& h, bool& dirty) {
@@ -355,7 +358,7 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
     const float s = -0.5f + 1.0f / 16.0f;
     const float curD = ORZ_FMA(dzdx, s + 0.125f * (float)(l & 3u), ORZ_FMA(dzdy, (l >> 2) ? s + 0.125f : s, u2f(rec[5])));
     const float curE = u2f(rec[14 + e]), eX = u2f(rec[6 + e]), eY = u2f(rec[10 + e]);
-    step_chain2(curD, dzdx, dzdy, curE, eX, eY, ya - minY, r - rFirst, x0 + cA - minX + rec[20], cA, cB, active, active && l < 4u,
+    step_chain2<TH>(curD, dzdx, dzdy, curE, eX, eY, ya - minY, r - rFirst, x0 + cA - minX + rec[20], cA, cB, active, active && l < 4u,
                 sm + (4u + l) * kChainStride + r * 8u, sm + e * kChainStride + r * 8u);
   }
 #else
@@ -367,7 +370,7 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
     const bool active = lane < 16 && r >= rFirst && r <= rLast;
     float cur = 0.0f, incX = 0.0f, incY = 0.0f;
     if (active) { cur = u2f(rec[14 + e]); incX = u2f(rec[6 + e]); incY = u2f(rec[10 + e]); }
-    step_chain(cur, incX, incY, ya - minY, r - rFirst, x0 + cA - minX + rec[20], cA, cB, active, sm + e * kChainStride + r * 8u);
+    step_chain<TH>(cur, incX, incY, ya - minY, r - rFirst, x0 + cA - minX + rec[20], cA, cB, active, sm + e * kChainStride + r * 8u);
   }
 #endif
   __syncwarp();
@@ -412,7 +415,7 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
     const bool active = r >= rLo && r <= rLast;
     const float s = -0.5f + 1.0f / 16.0f;
     const float cur = ORZ_FMA(dzdx, s + 0.125f * (float)(l & 3u), ORZ_FMA(dzdy, (l >> 2) ? s + 0.125f : s, u2f(rec[5])));
-    step_chain(cur, dzdx, dzdy, y0 + rLo - minY, r - rLo, x0 + cA - minX + rec[20], cA, cB, active, sm + (4u + l) * kChainStride + r * 8u);
+    step_chain<TH>(cur, dzdx, dzdy, y0 + rLo - minY, r - rLo, x0 + cA - minX + rec[20], cA, cB, active, sm + (4u + l) * kChainStride + r * 8u);
   }
   __syncwarp();
 #endif
@@ -540,7 +543,8 @@ __device__ __forceinline__ void tile_prim(const uint32_t* __restrict__ rec, cons
 // Per-warp state of the tile-major traversal: the tiles a warp owns (lane k keeps tile k) and its slices of the CTA's
 // shared memory.  Shared by the cluster kernel (one view per cluster, gated) and k_raster_tiles (one ungated view over
 // the whole GPU): both hand an occluder's records to rasterize().
-struct TileWalker {
+template <uint32_t TH>  // tile height in blocks: 4 (lane <-> block, 8 x 4) or 1 (8 x 1 strips, lanes 8-31 own nothing: four times
+struct TileWalkerT {    // the tiles -- finer ownership and shorter per-tile chains for the few-view and per-call paths)
   Target T;
   int lane;
   uint32_t lx, ly;          // my block inside a tile
@@ -556,11 +560,11 @@ struct TileWalker {
 
   // tile t belongs to warp t mod nWarps of the group that shares the view
   __device__ __forceinline__ void own_tiles(uint32_t gw, uint32_t nWarps, uint32_t K) {
-    const uint32_t tilesX = (T.blocksX + kTileW - 1u) / kTileW, tilesY = (T.blocksY + kTileH - 1u) / kTileH, nTiles = tilesX * tilesY;
+    const uint32_t tilesX = (T.blocksX + kTileW - 1u) / kTileW, tilesY = (T.blocksY + TH - 1u) / TH, nTiles = tilesX * tilesY;
     tileX0 = 0xffffu; tileY0 = 0xffffu;
     if ((uint32_t)lane < K) {
       const uint32_t t = gw + (uint32_t)lane * nWarps;
-      if (t < nTiles) { const uint32_t ty = t / tilesX; tileX0 = (t - ty * tilesX) * kTileW; tileY0 = ty * kTileH; }
+      if (t < nTiles) { const uint32_t ty = t / tilesX; tileX0 = (t - ty * tilesX) * kTileW; tileY0 = ty * TH; }
     }
     allTiles = __ballot_sync(kFull, tileX0 != 0xffffu);
   }
@@ -570,13 +574,13 @@ struct TileWalker {
       const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
       const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
       myHiz[32u * k] = 1;
-      if (bx < T.blocksX && by < T.blocksY) T.hiz[by * T.blocksX + bx] = 1;
+      if (bx < T.blocksX && by < T.blocksY && ly < TH) T.hiz[by * T.blocksX + bx] = 1;
     }
     __syncwarp();
   }
   // my tiles that meet the block rectangle [bx0, bx1] x [by0, by1] (inclusive), as a mask over k
   __device__ __forceinline__ uint32_t tiles_meeting(uint32_t bx0, uint32_t bx1, uint32_t by0, uint32_t by1) const {
-    return __ballot_sync(kFull, tileX0 != 0xffffu && tileX0 <= bx1 && tileX0 + kTileW > bx0 && tileY0 <= by1 && tileY0 + kTileH > by0);
+    return __ballot_sync(kFull, tileX0 != 0xffffu && tileX0 <= bx1 && tileX0 + kTileW > bx0 && tileY0 <= by1 && tileY0 + TH > by0);
   }
   // canonical depth for the caller: blocks that stayed cleared read as zero
   __device__ __forceinline__ void zero_cleared_tiles() {
@@ -584,22 +588,94 @@ struct TileWalker {
     for (uint32_t m = allTiles; m; m &= m - 1u) {
       const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
       const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
-      if (bx < T.blocksX && by < T.blocksY && myHiz[32u * k] == 1) {
+      if (bx < T.blocksX && by < T.blocksY && ly < TH && myHiz[32u * k] == 1) {
         uint4* d4 = reinterpret_cast<uint4*>(T.depth) + (size_t)(by * T.blocksX + bx) * 8u;
 #pragma unroll
         for (int y = 0; y < 8; ++y) d4[y] = z;
       }
     }
   }
+  // which of <= 32 staged records (lane i holds the header words a, b of record i, `valid` when it has one) touch which
+  // of my tiles `tm`: lane k gets the answer for tile k
+  __device__ __forceinline__ uint32_t tile_hits(const uint32_t tm, const bool valid, const uint32_t a, const uint32_t b) const {
+    uint32_t myHits = 0u;
+    const uint32_t minX = a & 0xffffu, minY = a >> 16;
+    for (uint32_t m = tm; m; m &= m - 1u) {
+      const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+      const uint32_t x0 = __shfl_sync(kFull, tileX0, (int)k), y0 = __shfl_sync(kFull, tileY0, (int)k);
+      const uint32_t x1 = min(x0 + kTileW, T.blocksX), y1 = min(y0 + TH, T.blocksY);
+      const bool touches = valid && minX < x1 && minX + (b & 0xffffu) > x0 && minY < y1 && minY + (b >> 16) > y0;
+      const uint32_t hitsK = __ballot_sync(kFull, touches);
+      if ((uint32_t)lane == k) myHits = hitsK;
+    }
+    return myHits;
+  }
+  // staged records (`stage`, kRecStride words each) -> my tiles, tile-major, each tile's primitives in order; myHits from
+  // tile_hits.  `gathered` false: the records are still on their way (cp.async) and are waited for after the first open.
+  __device__ __forceinline__ void tile_loop(const uint32_t* __restrict__ stage, const uint32_t myHits, bool& gathered) {
+    for (uint32_t m = __ballot_sync(kFull, myHits != 0u); m;) {
+      const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+      m &= m - 1u;
+      uint32_t hits = __shfl_sync(kFull, myHits, (int)k);
+      const uint32_t x0 = __shfl_sync(kFull, tileX0, (int)k), y0 = __shfl_sync(kFull, tileY0, (int)k);
+      const uint32_t x1 = min(x0 + kTileW, T.blocksX), y1 = min(y0 + TH, T.blocksY);
+#if ORZ_TILE_PREFETCH
+      if (m) {  // the NEXT tile's stored depth starts its way from L2 / HBM while this one is worked on
+        const uint32_t k2 = (uint32_t)__ffs((int)m) - 1u;
+        const uint32_t bxn = __shfl_sync(kFull, tileX0, (int)k2) + lx, byn = __shfl_sync(kFull, tileY0, (int)k2) + ly;
+        if (bxn < T.blocksX && byn < T.blocksY && ly < TH && myHiz[32u * k2] != 1) prefetch_l1(reinterpret_cast<uint4*>(T.depth) + (size_t)(byn * T.blocksX + bxn) * 8u);
+      }
+#endif
+      // open the tile: its depth goes to shared memory, one block per lane, as 8 items (rr, i) of 4 row pairs each
+      // (item slot swizzled by the block so that both this lane-per-block pass and the eight-lanes-per-block
+      // update passes are bank-conflict free); cleared blocks (HiZ 1) enter as zero
+      const uint32_t bx = x0 + lx, by = y0 + ly;
+      const bool inScreen = bx < x1 && by < y1;
+      uint4* dp = reinterpret_cast<uint4*>(T.depth) + (size_t)(by * T.blocksX + bx) * 8u;
+      uint32_t h = inScreen ? (uint32_t)myHiz[32u * k] : 0xffffu;  // off-screen lanes never pass
+      const bool load = inScreen && h != 1u;
+      uint4* mine = myTile + (uint32_t)lane * 8u;
+      const uint32_t sw = (uint32_t)lane & 7u;
+#pragma unroll
+      for (uint32_t rr = 0; rr < 2u; ++rr) {
+        uint4 R[4];
+#pragma unroll
+        for (uint32_t kk = 0; kk < 4u; ++kk) R[kk] = load ? dp[2u * kk + rr] : make_uint4(0u, 0u, 0u, 0u);
+        mine[(rr * 4u + 0u) ^ sw] = make_uint4(R[0].x, R[1].x, R[2].x, R[3].x);
+        mine[(rr * 4u + 1u) ^ sw] = make_uint4(R[0].y, R[1].y, R[2].y, R[3].y);
+        mine[(rr * 4u + 2u) ^ sw] = make_uint4(R[0].z, R[1].z, R[2].z, R[3].z);
+        mine[(rr * 4u + 3u) ^ sw] = make_uint4(R[0].w, R[1].w, R[2].w, R[3].w);
+      }
+#if ORZ_ASYNC_GATHER
+      if (!gathered) { cp_async_wait_all(); gathered = true; }
+#endif
+      __syncwarp();
+      bool dirty = false;
+      for (; hits; hits &= hits - 1u)
+        tile_prim<TH>(stage + ((uint32_t)__ffs((int)hits) - 1u) * kRecStride, lane, x0, y0, x1, y1, lut, myChain, myTile, myAux, h, dirty);
+      if (dirty) {  // close: the blocks this occluder changed go back to HBM / L2 in the reference's row layout
+#pragma unroll
+        for (uint32_t rr = 0; rr < 2u; ++rr) {
+          const uint4 I0 = mine[(rr * 4u + 0u) ^ sw], I1 = mine[(rr * 4u + 1u) ^ sw], I2 = mine[(rr * 4u + 2u) ^ sw], I3 = mine[(rr * 4u + 3u) ^ sw];
+          dp[0u + rr] = make_uint4(I0.x, I1.x, I2.x, I3.x);
+          dp[2u + rr] = make_uint4(I0.y, I1.y, I2.y, I3.y);
+          dp[4u + rr] = make_uint4(I0.z, I1.z, I2.z, I3.z);
+          dp[6u + rr] = make_uint4(I0.w, I1.w, I2.w, I3.w);
+        }
+        myHiz[32u * k] = (uint16_t)h;
+        T.hiz[by * T.blocksX + bx] = (uint16_t)h;
+      }
+      __syncwarp();  // the next tile's open overwrites the slots other lanes may still be reading
+    }
+  }
   // rasterize<clipped>(occluder) restricted to my tiles: `cnt` records (k_setup_views) with their bounding-box headers;
   // tmOcc = my tiles that meet the occluder's block rectangle
   __device__ __forceinline__ void rasterize(const uint32_t* __restrict__ recs, const uint2* __restrict__ hdrs, const uint32_t cnt, const uint32_t tmOcc) {
     uint32_t nStaged = 0;
-    // staged records -> my tiles, tile-major, each tile's primitives in order
     auto flush = [&]() {
       __syncwarp();
 #if ORZ_ASYNC_GATHER
-      // the records start their way from L2 now and are waited for after the first tile has been opened
+      // the records start their way from L2 / HBM now and are waited for after the first tile has been opened
 #pragma unroll 8
       for (uint32_t i = 0; i < nStaged; ++i)
         if (lane < kRecStride) cp_async_word(myStage + i * kRecStride + lane, recs + (size_t)myIdx[i] * kRecStride + lane);
@@ -611,81 +687,12 @@ struct TileWalker {
       for (uint32_t i = 0; i < nStaged; ++i)
         if (lane < kRecStride) myStage[i * kRecStride + lane] = recs[(size_t)myIdx[i] * kRecStride + lane];
       __syncwarp();
+      bool gathered = true;
+      uint2 myHdr = make_uint2(0u, 0u);
+      if ((uint32_t)lane < nStaged) myHdr = make_uint2(myStage[lane * kRecStride], myStage[lane * kRecStride + 1]);
 #endif
-      // which staged records touch which of my tiles: lane k keeps the answer for tile k
-      uint32_t myHits = 0u;
-      for (uint32_t m = tmOcc; m; m &= m - 1u) {
-        const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
-        const uint32_t x0 = __shfl_sync(kFull, tileX0, (int)k), y0 = __shfl_sync(kFull, tileY0, (int)k);
-        const uint32_t x1 = min(x0 + kTileW, T.blocksX), y1 = min(y0 + kTileH, T.blocksY);
-        bool touches = false;
-        if ((uint32_t)lane < nStaged) {
-#if ORZ_ASYNC_GATHER
-          const uint32_t a = myHdr.x, b = myHdr.y;
-#else
-          const uint32_t a = myStage[lane * kRecStride], b = myStage[lane * kRecStride + 1];
-#endif
-          const uint32_t minX = a & 0xffffu, minY = a >> 16;
-          touches = minX < x1 && minX + (b & 0xffffu) > x0 && minY < y1 && minY + (b >> 16) > y0;
-        }
-        const uint32_t hitsK = __ballot_sync(kFull, touches);
-        if ((uint32_t)lane == k) myHits = hitsK;
-      }
-      for (uint32_t m = __ballot_sync(kFull, myHits != 0u); m;) {
-        const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
-        m &= m - 1u;
-        uint32_t hits = __shfl_sync(kFull, myHits, (int)k);
-        const uint32_t x0 = __shfl_sync(kFull, tileX0, (int)k), y0 = __shfl_sync(kFull, tileY0, (int)k);
-        const uint32_t x1 = min(x0 + kTileW, T.blocksX), y1 = min(y0 + kTileH, T.blocksY);
-#if ORZ_TILE_PREFETCH
-        if (m) {  // the NEXT tile's stored depth starts its way from L2 / HBM while this one is worked on
-          const uint32_t k2 = (uint32_t)__ffs((int)m) - 1u;
-          const uint32_t bxn = __shfl_sync(kFull, tileX0, (int)k2) + lx, byn = __shfl_sync(kFull, tileY0, (int)k2) + ly;
-          if (bxn < T.blocksX && byn < T.blocksY && myHiz[32u * k2] != 1) prefetch_l1(reinterpret_cast<uint4*>(T.depth) + (size_t)(byn * T.blocksX + bxn) * 8u);
-        }
-#endif
-        // open the tile: its depth goes to shared memory, one block per lane, as 8 items (rr, i) of 4 row pairs each
-        // (item slot swizzled by the block so that both this lane-per-block pass and the eight-lanes-per-block
-        // update passes are bank-conflict free); cleared blocks (HiZ 1) enter as zero
-        const uint32_t bx = x0 + lx, by = y0 + ly;
-        const bool inScreen = bx < x1 && by < y1;
-        uint4* dp = reinterpret_cast<uint4*>(T.depth) + (size_t)(by * T.blocksX + bx) * 8u;
-        uint32_t h = inScreen ? (uint32_t)myHiz[32u * k] : 0xffffu;  // off-screen lanes never pass
-        const bool load = inScreen && h != 1u;
-        uint4* mine = myTile + (uint32_t)lane * 8u;
-        const uint32_t sw = (uint32_t)lane & 7u;
-#pragma unroll
-        for (uint32_t rr = 0; rr < 2u; ++rr) {
-          uint4 R[4];
-#pragma unroll
-          for (uint32_t kk = 0; kk < 4u; ++kk) R[kk] = load ? dp[2u * kk + rr] : make_uint4(0u, 0u, 0u, 0u);
-          mine[(rr * 4u + 0u) ^ sw] = make_uint4(R[0].x, R[1].x, R[2].x, R[3].x);
-          mine[(rr * 4u + 1u) ^ sw] = make_uint4(R[0].y, R[1].y, R[2].y, R[3].y);
-          mine[(rr * 4u + 2u) ^ sw] = make_uint4(R[0].z, R[1].z, R[2].z, R[3].z);
-          mine[(rr * 4u + 3u) ^ sw] = make_uint4(R[0].w, R[1].w, R[2].w, R[3].w);
-        }
-#if ORZ_ASYNC_GATHER
-        if (!gathered) { cp_async_wait_all(); gathered = true; }
-#endif
-        __syncwarp();
-        bool dirty = false;
-        for (; hits; hits &= hits - 1u)
-          tile_prim(myStage + ((uint32_t)__ffs((int)hits) - 1u) * kRecStride, lane, x0, y0, x1, y1, lut, myChain, myTile,
-                    myAux, h, dirty);
-        if (dirty) {  // close: the blocks this occluder changed go back to HBM / L2 in the reference's row layout
-#pragma unroll
-          for (uint32_t rr = 0; rr < 2u; ++rr) {
-            const uint4 I0 = mine[(rr * 4u + 0u) ^ sw], I1 = mine[(rr * 4u + 1u) ^ sw], I2 = mine[(rr * 4u + 2u) ^ sw], I3 = mine[(rr * 4u + 3u) ^ sw];
-            dp[0u + rr] = make_uint4(I0.x, I1.x, I2.x, I3.x);
-            dp[2u + rr] = make_uint4(I0.y, I1.y, I2.y, I3.y);
-            dp[4u + rr] = make_uint4(I0.z, I1.z, I2.z, I3.z);
-            dp[6u + rr] = make_uint4(I0.w, I1.w, I2.w, I3.w);
-          }
-          myHiz[32u * k] = (uint16_t)h;
-          T.hiz[by * T.blocksX + bx] = (uint16_t)h;
-        }
-        __syncwarp();  // the next tile's open overwrites the slots other lanes may still be reading
-      }
+      const uint32_t myHits = tile_hits(tmOcc, (uint32_t)lane < nStaged, myHdr.x, myHdr.y);
+      tile_loop(myStage, myHits, gathered);
 #if ORZ_ASYNC_GATHER
       if (!gathered) cp_async_wait_all();  // (no tile was opened: the staging area must still be quiet before it is refilled)
 #endif
@@ -702,7 +709,7 @@ struct TileWalker {
       for (uint32_t m = tmOcc; m; m &= m - 1u) {
         const int k = __ffs((int)m) - 1;
         const uint32_t x0 = __shfl_sync(kFull, tileX0, k), y0 = __shfl_sync(kFull, tileY0, k);
-        touches = touches || (hx0 < x0 + kTileW && hx1 > x0 && hy0 < y0 + kTileH && hy1 > y0);
+        touches = touches || (hx0 < x0 + kTileW && hx1 > x0 && hy0 < y0 + TH && hy1 > y0);
       }
       uint32_t hits = __ballot_sync(kFull, touches);
       while (hits) {
@@ -717,8 +724,9 @@ struct TileWalker {
     if (nStaged) flush();
   }
 };
+typedef TileWalkerT<kTileH> TileWalker;
 
-template <int C>
+template <int C, uint32_t TH>
 #if ORZ_CLUSTER_CTAS_PER_SM
 __global__ void __launch_bounds__(kClusterGW * 32, ORZ_CLUSTER_CTAS_PER_SM) k_raster_views_cluster(const FrameParams p) {
 #else
@@ -774,7 +782,7 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
   uint32_t* myAux = s_tileAll + (uint32_t)GW * kTileWords + (uint32_t)warp * kTileAuxWords;
   const uint32_t lx = (uint32_t)lane & 7u, ly = (uint32_t)lane >> 3;
 
-  TileWalker tw;
+  TileWalkerT<TH> tw;
   tw.T = T; tw.lane = lane; tw.lx = lx; tw.ly = ly;
   tw.myHiz = myHiz; tw.myChain = myChain; tw.myStage = myStage; tw.myIdx = myIdx; tw.myTile = myTile; tw.myAux = myAux;
   tw.lut = ORZ_CLUSTER_LUT_SMEM ? s_lut : p.lut;
@@ -831,7 +839,7 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
           const uint32_t k = (uint32_t)__ffs((int)tm) - 1u;
           const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
           if (flag_set_warp(vis)) break;  // another warp already found a visible pixel
-          const bool hit = bx >= bx0 && bx <= bx1 && by >= by0 && by <= by1 && bx < T.blocksX && by < T.blocksY &&
+          const bool hit = ly < TH && bx >= bx0 && bx <= bx1 && by >= by0 && by <= by1 && bx < T.blocksX && by < T.blocksY &&
                            query_block_h(T, bx, by, (uint32_t)myHiz[32u * k], minX, maxX, minY, maxY, maxZ);
           if (__any_sync(kFull, hit)) { found = true; break; }
         }

@@ -21,6 +21,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
 #include <string>
 #include <vector>
 
@@ -103,9 +104,15 @@ struct orz_context {
   uint32_t* d_counter = nullptr;
   void* d_scratch[12] = {nullptr};
   size_t scratchBytes[12] = {0};
-  uint32_t* h_pinned = nullptr;  // small pinned + mapped mailbox for scalar results (k_query2d writes its tagged answer straight into it)
+  // pinned + mapped mailbox for the per-call queries: the answering kernel stores tag | answer straight into a word the
+  // waiting host thread polls (no copy, no event, no stream sync); slots are handed out round robin, tags never repeat
+  static constexpr uint32_t kMailSlots = 256;
+  uint32_t* h_pinned = nullptr;
   uint32_t* d_mail = nullptr;    // the same words as the device sees them
-  uint32_t mailSeq = 0;          // tag of the last per-call query
+  uint32_t mailSeq = 0;          // sequence number of the last query handed to the GPU (tag = sequence << 2)
+  uint32_t mailNext = 0;         // next slot
+  size_t smemCall = 0;           // k_rasterize_call
+  bool percallLegacy = false;    // ORZ_PERCALL_LEGACY=1: one launch per rasterize (round-1 kernel) and per query, no predicted chains
   static constexpr int kGroups = 4;          // sub-batches pipelined on auxiliary streams
   cudaStream_t aux[kGroups] = {nullptr};
   cudaEvent_t evFork = nullptr, evJoin[kGroups] = {nullptr};
@@ -113,7 +120,9 @@ struct orz_context {
   // dynamic shared memory already granted to a kernel instantiation on this context's device (cudaFuncSetAttribute is
   // per device and idempotent: keeping the record per context avoids process-wide mutable state)
   size_t smemViews[2][5] = {{0}};   // [traversal - 1][log2 GW]
-  size_t smemCluster[5] = {0};      // [log2 C]
+  size_t smemCluster[10] = {0};     // [log2 C (+ 5 for 8 x 1 tiles)]
+  int clusterTileH = 0;             // tile height of the cluster path: 4, 1, or 0 = automatic = 4 (ORZ_CLUSTER_TILE_H)
+  uint32_t percallTileH = 1;        // tile height of the per-call rasterize (ORZ_PERCALL_TILE_H)
   size_t smemTiles = 0;             // k_raster_tiles
 };
 struct orz_occluder {
@@ -127,6 +136,13 @@ struct orz_rasterizer {
   Target T;
   ViewMatrices vm;
   uint8_t* d_boxOut = nullptr;
+  // ---- predicted query chains (orz_percall_kernels.cuh): the frame loop of Main.cpp:192-206 asks the same boxes in
+  // (nearly) the same order frame after frame, so every launch also answers the rectangle queries expected next.
+  typedef std::array<uint32_t, 8> BoxKey;  // bit patterns of boundsMin / boundsMax
+  std::vector<BoxKey> history, current;   // boxes asked in the previous frame / so far in this one (a frame = clear() to clear())
+  size_t cursor = 0;                      // history[cursor] is the query expected next
+  struct Pending { uint32_t rect[5], slot, tag; };
+  std::vector<Pending> pending;           // answers under way for the buffers AS THEY ARE NOW (dropped by rasterize / clear)
 };
 struct orz_scene {
   orz_context* ctx;
@@ -175,8 +191,12 @@ extern "C" int orz_context_create(int device, orz_context** out) {
   ORZ_CUDA_OR(orz_context_destroy(ctx), cudaMalloc(&ctx->d_rcp, ctx->h_rcp.size() * 4));
   ORZ_CUDA_OR(orz_context_destroy(ctx), cudaMemcpy(ctx->d_rcp, ctx->h_rcp.data(), ctx->h_rcp.size() * 4, cudaMemcpyHostToDevice));
   ORZ_CUDA_OR(orz_context_destroy(ctx), cudaMalloc(&ctx->d_counter, 64));
-  ORZ_CUDA_OR(orz_context_destroy(ctx), cudaHostAlloc(&ctx->h_pinned, 64, cudaHostAllocMapped));
-  memset(ctx->h_pinned, 0, 64);
+  ORZ_CUDA_OR(orz_context_destroy(ctx), cudaHostAlloc(&ctx->h_pinned, orz_context::kMailSlots * 4, cudaHostAllocMapped));
+  memset(ctx->h_pinned, 0, orz_context::kMailSlots * 4);
+  ORZ_CUDA_OR(orz_context_destroy(ctx), cudaMemset(ctx->d_counter, 0, 64));
+  if (const char* legacy = getenv("ORZ_PERCALL_LEGACY")) ctx->percallLegacy = legacy[0] == '1';
+  if (const char* th = getenv("ORZ_PERCALL_TILE_H")) ctx->percallTileH = atoi(th) == 4 ? 4u : 1u;
+  if (const char* th = getenv("ORZ_CLUSTER_TILE_H")) ctx->clusterTileH = atoi(th) == 1 ? 1 : atoi(th) == 4 ? 4 : 0;
   ORZ_CUDA_OR(orz_context_destroy(ctx), cudaHostGetDevicePointer((void**)&ctx->d_mail, ctx->h_pinned, 0));
   *out = ctx;
   return ORZ_OK;
@@ -222,6 +242,13 @@ extern "C" int orz_context_set_cluster_views(orz_context* ctx, int maxViews) {
 extern "C" int orz_context_set_cluster_size(orz_context* ctx, int ctas) {
   if (!ctx || (ctas != 0 && ctas != 1 && ctas != 2 && ctas != 4 && ctas != 8 && ctas != 16)) return fail(ORZ_ERR_ARG, "cluster size must be 0, 1, 2, 4, 8 or 16");
   ctx->clusterSize = ctas;
+  return ORZ_OK;
+}
+extern "C" int orz_context_set_tile_height(orz_context* ctx, int clusterTileH, int perCallTileH) {
+  if (!ctx || (clusterTileH != 0 && clusterTileH != 1 && clusterTileH != 4) || (perCallTileH != 1 && perCallTileH != 4))
+    return fail(ORZ_ERR_ARG, "tile heights: 0 (automatic), 1 or 4 for the cluster path, 1 or 4 for the per-call path");
+  ctx->clusterTileH = clusterTileH;
+  ctx->percallTileH = (uint32_t)perCallTileH;
   return ORZ_OK;
 }
 extern "C" int orz_context_set_arena_bytes(orz_context* ctx, size_t bytes) {
@@ -325,12 +352,93 @@ extern "C" int orz_rasterizer_clear(orz_rasterizer* r) {
   k_clear<<<r->ctx->numSMs * 2, 256, 0, r->ctx->stream>>>(r->T.depth, r->T.hiz, blocks);
   r->ctx->launches++;
   ORZ_CUDA(cudaGetLastError());
+  r->pending.clear();  // a new frame: what was asked in the last one is the prediction for this one
+  r->history.swap(r->current);
+  r->current.clear();
+  r->cursor = 0;
   return ORZ_OK;
+}
+
+static uint32_t tiles_of(uint32_t width, uint32_t height, uint32_t tileH);
+// ---- predicted query chains -------------------------------------------------------------------------------------
+static void chain_add(orz_rasterizer* r, QueryChain& qc, const uint32_t rect[5]) {
+  orz_context* ctx = r->ctx;
+  const uint32_t q = qc.n++;
+  for (int i = 0; i < 5; ++i) qc.rect[q][i] = rect[i];
+  qc.tag[q] = (++ctx->mailSeq) << 2;
+  qc.slot[q] = ctx->mailNext;
+  ctx->mailNext = (ctx->mailNext + 1u) % orz_context::kMailSlots;
+  orz_rasterizer::Pending pe;
+  for (int i = 0; i < 5; ++i) pe.rect[i] = rect[i];
+  pe.slot = qc.slot[q]; pe.tag = qc.tag[q];
+  r->pending.push_back(pe);
+}
+// the rectangle queries expected after history[cursor - 1], under the current matrix: boxes the frustum culls are answered
+// on the host and skipped; a near-clipped box is visible without a test and will be rasterised, which ends the chain
+static void chain_predict(orz_rasterizer* r, QueryChain& qc) {
+  if (r->ctx->percallLegacy) return;
+  const RcpTable rt{r->ctx->h_rcp.data(), 23 - r->ctx->rcpBits};
+  for (size_t j = r->cursor; j < r->history.size() && qc.n < kChainMax; ++j) {
+    float mn[4], mx[4];
+    memcpy(mn, r->history[j].data(), 16);
+    memcpy(mx, r->history[j].data() + 4, 16);
+    const BoxFront f = box_front_half(r->vm, mn, mx, r->T.width, r->T.height, rt);
+    if (f.status == kBoxCulled) continue;
+    if (f.status == kBoxNearClip) break;
+    const uint32_t rect[5] = {f.minX, f.maxX, f.minY, f.maxY, f.maxZ};
+    chain_add(r, qc, rect);
+  }
+}
+// waits for the tagged answer of one mailbox slot: 0 / 1 = the answer, 2 = the chain stopped before this query
+static int mail_wait(orz_context* ctx, uint32_t slot, uint32_t tag, uint32_t* answer) {
+  volatile uint32_t* mail = ctx->h_pinned + slot;
+  for (uint32_t spins = 0;; ++spins) {
+    const uint32_t v = *mail;
+    if ((v & ~3u) == tag) { *answer = v & 3u; return ORZ_OK; }
+    if ((spins & 0x3fffu) == 0x3fffu) {  // now and then: has the stream failed (or finished without our store)?
+      const cudaError_t q = cudaStreamQuery(ctx->stream);
+      if (q != cudaSuccess && q != cudaErrorNotReady) return fail(ORZ_ERR_CUDA, std::string("per-call query: ") + cudaGetErrorString(q));
+      if (q == cudaSuccess && ((*mail) & ~3u) != tag) return fail(ORZ_ERR_CUDA, "per-call query: the kernel finished without an answer");
+    }
+  }
 }
 extern "C" int orz_rasterizer_rasterize(orz_rasterizer* r, const orz_occluder* occ, int clipped) {
   if (!r || !occ) return fail(ORZ_ERR_ARG, "orz_rasterizer_rasterize: bad arguments");
   if (occ->nQuads == 0) return ORZ_OK;
   ORZ_CUDA(cudaSetDevice(r->ctx->device));
+  r->pending.clear();  // the buffers change: answers under way describe the old ones
+  {
+    // one launch, tile major over the whole GPU (8 x 1 strips: the stacked updates of a block row are the critical path), the
+    // queries expected next answered by its last CTA
+    orz_context* ctx = r->ctx;
+    const uint32_t blocks = r->T.blocksX * r->T.blocksY;
+    const uint32_t tileH = ctx->percallTileH;
+    const uint32_t nTiles = tiles_of(r->T.width, r->T.height, tileH);
+    const uint32_t grid = std::min<uint32_t>((uint32_t)ctx->numSMs, (nTiles + kClusterGW - 1u) / kClusterGW);
+    const uint32_t K = (nTiles + grid * kClusterGW - 1u) / (grid * kClusterGW);
+    const size_t smem = CallSmem::bytes(K);
+    if (!ctx->percallLegacy && occ->nQuads <= kCallQuadsMax && blocks <= 65536u && K <= 32u && smem <= ctx->maxSmemOptin) {
+      if (ctx->smemCall < smem) {
+        ORZ_CUDA(cudaFuncSetAttribute(k_rasterize_call<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ORZ_CUDA(cudaFuncSetAttribute(k_rasterize_call<kTileH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->smemCall = smem;
+      }
+      CallMatrix cm;
+      prepare_call(r->vm.baked, occ->refMin, occ->refMax, cm);
+      QueryChain qc;
+      qc.n = 0;
+      chain_predict(r, qc);
+      if (tileH == 1u)
+        k_rasterize_call<1><<<grid, kClusterGW * 32, smem, ctx->stream>>>(cm, occ->d_quads, occ->nQuads, clipped, r->T, ctx->d_rcp, 23 - ctx->rcpBits, ctx->d_lut, K, qc,
+                                                                           ctx->d_mail, ctx->d_counter + 8);
+      else
+        k_rasterize_call<kTileH><<<grid, kClusterGW * 32, smem, ctx->stream>>>(cm, occ->d_quads, occ->nQuads, clipped, r->T, ctx->d_rcp, 23 - ctx->rcpBits, ctx->d_lut, K,
+                                                                                qc, ctx->d_mail, ctx->d_counter + 8);
+      ctx->launches++;
+      ORZ_CUDA(cudaGetLastError());
+      return ORZ_OK;
+    }
+  }
   constexpr int GW = 4;
   const uint32_t grid = (r->T.blocksY + GW - 1) / GW;  // one screen block-row per warp
   const float4 mn = make_float4(occ->refMin[0], occ->refMin[1], occ->refMin[2], occ->refMin[3]);
@@ -346,22 +454,35 @@ extern "C" int orz_rasterizer_query2d(orz_rasterizer* r, uint32_t minX, uint32_t
   if (!r || !visible) return fail(ORZ_ERR_ARG, "orz_rasterizer_query2d: bad arguments");
   if (maxX >= r->T.width || maxY >= r->T.height || minX > maxX || minY > maxY) return fail(ORZ_ERR_ARG, "orz_rasterizer_query2d: rectangle outside the buffer");
   ORZ_CUDA(cudaSetDevice(r->ctx->device));
-  // the answer comes back through mapped pinned memory, tagged with this call's sequence number: no copy, no stream sync
   orz_context* ctx = r->ctx;
-  const uint32_t tag = (++ctx->mailSeq) << 1;
-  k_query2d<<<1, 256, 0, ctx->stream>>>(r->T, minX, maxX, minY, maxY, maxZ, ctx->d_mail, tag);
+  const uint32_t rect[5] = {minX, maxX, minY, maxY, maxZ};
+  // already asked for by an earlier launch (a predicted chain)?
+  for (size_t i = 0; i < r->pending.size(); ++i) {
+    if (memcmp(r->pending[i].rect, rect, sizeof rect) != 0) continue;
+    const orz_rasterizer::Pending pe = r->pending[i];
+    r->pending.erase(r->pending.begin() + (long)i);
+    uint32_t answer = 0;
+    if (int e = mail_wait(ctx, pe.slot, pe.tag, &answer)) return e;
+    if (answer & 2u) break;  // the chain stopped before it got here: ask now
+    *visible = (int)(answer & 1u);
+    return ORZ_OK;
+  }
+  // the answer comes back through mapped pinned memory, tagged with this call's sequence number: no copy, no stream sync;
+  // the launch also carries the queries expected after this one
+  QueryChain qc;
+  qc.n = 0;
+  r->pending.clear();  // (entries of an abandoned chain; answers still under way land in slots nobody reads)
+  chain_add(r, qc, rect);
+  const orz_rasterizer::Pending mine = r->pending.back();
+  r->pending.pop_back();
+  chain_predict(r, qc);
+  k_query_chain<<<1, 256, 0, ctx->stream>>>(r->T, qc, ctx->d_mail);
   ctx->launches++;
   ORZ_CUDA(cudaGetLastError());
-  volatile uint32_t* mail = ctx->h_pinned;
-  for (uint32_t spins = 0;; ++spins) {
-    const uint32_t v = *mail;
-    if ((v & ~1u) == tag) { *visible = (int)(v & 1u); return ORZ_OK; }
-    if ((spins & 0x3fffu) == 0x3fffu) {  // now and then: has the stream failed (or finished without our store)?
-      const cudaError_t q = cudaStreamQuery(ctx->stream);
-      if (q != cudaSuccess && q != cudaErrorNotReady) return fail(ORZ_ERR_CUDA, std::string("orz_rasterizer_query2d: ") + cudaGetErrorString(q));
-      if (q == cudaSuccess && ((*mail) & ~1u) != tag) return fail(ORZ_ERR_CUDA, "orz_rasterizer_query2d: the query kernel finished without an answer");
-    }
-  }
+  uint32_t answer = 0;
+  if (int e = mail_wait(ctx, mine.slot, mine.tag, &answer)) return e;
+  *visible = (int)(answer & 1u);
+  return ORZ_OK;
 }
 extern "C" int orz_rasterizer_query_visibility(orz_rasterizer* r, const float* bmin, const float* bmax, int* visible, int* needsClipping) {
   if (!r || !bmin || !bmax || !visible) return fail(ORZ_ERR_ARG, "orz_rasterizer_query_visibility: bad arguments");
@@ -369,6 +490,17 @@ extern "C" int orz_rasterizer_query_visibility(orz_rasterizer* r, const float* b
   // kernels use, then ask the GPU only for the rectangle test (Rasterizer.cpp:275)
   const RcpTable rt{r->ctx->h_rcp.data(), 23 - r->ctx->rcpBits};
   const BoxFront f = box_front_half(r->vm, bmin, bmax, r->T.width, r->T.height, rt);
+  {  // where this frame is in the last frame's sequence of queries (the prediction for what is asked next)
+    orz_rasterizer::BoxKey key;
+    memcpy(key.data(), bmin, 16);
+    memcpy(key.data() + 4, bmax, 16);
+    if (r->cursor < r->history.size() && r->history[r->cursor] == key) ++r->cursor;
+    else {
+      for (size_t j = 0; j < r->history.size(); ++j)
+        if (r->history[j] == key) { r->cursor = j + 1; break; }
+    }
+    if (r->current.size() < 65536u) r->current.push_back(key);
+  }
   if (f.status == kBoxCulled) { *visible = 0; return ORZ_OK; }  // needsClipping untouched, as in the reference
   if (f.status == kBoxNearClip) { *visible = 1; if (needsClipping) *needsClipping = 1; return ORZ_OK; }
   if (needsClipping) *needsClipping = 0;
@@ -735,14 +867,18 @@ static int occupancy_views(int GW, int trav, int* perSM) {
   }
 }
 
-template <int C>
-static int launch_cluster_t(orz_context* ctx, FrameParams p, uint32_t nViews, uint32_t nTiles, cudaStream_t st) {
+static uint32_t tiles_of(uint32_t width, uint32_t height, uint32_t tileH) {
+  return (((width >> 3) + kTileW - 1u) / kTileW) * (((height >> 3) + tileH - 1u) / tileH);
+}
+template <int C, uint32_t TH>
+static int launch_cluster_t(orz_context* ctx, FrameParams p, uint32_t nViews, cudaStream_t st) {
+  const uint32_t nTiles = tiles_of(p.width, p.height, TH);
   p.clusterK = (nTiles + (uint32_t)(C * kClusterGW) - 1u) / (uint32_t)(C * kClusterGW);
   const size_t smem = ClusterSmem::bytes(p.clusterK, p.nOcc);
-  constexpr int kLog = C == 1 ? 0 : C == 2 ? 1 : C == 4 ? 2 : C == 8 ? 3 : 4;
+  constexpr int kLog = (C == 1 ? 0 : C == 2 ? 1 : C == 4 ? 2 : C == 8 ? 3 : 4) + (TH == 1 ? 5 : 0);
   if (ctx->smemCluster[kLog] < smem) {
-    ORZ_CUDA(cudaFuncSetAttribute(k_raster_views_cluster<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (C > 8) ORZ_CUDA(cudaFuncSetAttribute(k_raster_views_cluster<C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    ORZ_CUDA(cudaFuncSetAttribute(k_raster_views_cluster<C, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (C > 8) ORZ_CUDA(cudaFuncSetAttribute(k_raster_views_cluster<C, TH>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     ctx->smemCluster[kLog] = smem;
   }
   cudaLaunchConfig_t cfg;
@@ -756,40 +892,60 @@ static int launch_cluster_t(orz_context* ctx, FrameParams p, uint32_t nViews, ui
   at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  ORZ_CUDA(cudaLaunchKernelEx(&cfg, k_raster_views_cluster<C>, p));
+  ORZ_CUDA(cudaLaunchKernelEx(&cfg, k_raster_views_cluster<C, TH>, p));
   ctx->launches++;
   return ORZ_OK;
 }
 // one cluster per view.  Cluster size: as many CTAs as the view can use (one tile per warp) while all
 // views of the batch still fit the GPU in one wave; at least enough that a warp owns <= 32 tiles and the CTA's
 // shared memory (tables, staging, the open tiles, decision words of every occluder, HiZ mirror) fits.
+// Tile height: 8 x 4 blocks; 8 x 1 strips (four times the tiles to hand out, a quarter of the stacked updates per tile)
+// can be asked for with orz_context_set_tile_height.
 // Returns 0 when no cluster size works: the caller stays on the large-batch kernel.
-static uint32_t pick_cluster_size(const orz_context* ctx, uint32_t width, uint32_t height, uint32_t nOcc, uint32_t nBatch) {
-  const uint32_t nTiles = (((width >> 3) + kTileW - 1u) / kTileW) * (((height >> 3) + kTileH - 1u) / kTileH);
-  auto tilesPerWarp = [&](uint32_t c) { return (nTiles + c * kClusterGW - 1u) / (c * kClusterGW); };
-  auto fits = [&](uint32_t c) { return tilesPerWarp(c) <= 32u && ClusterSmem::bytes(tilesPerWarp(c), nOcc) <= ctx->maxSmemOptin; };
+struct ClusterShape { uint32_t c, tileH; };
+static ClusterShape pick_cluster_shape(const orz_context* ctx, uint32_t width, uint32_t height, uint32_t nOcc, uint32_t nBatch) {
+  auto tilesPerWarp = [&](uint32_t c, uint32_t th) { return (tiles_of(width, height, th) + c * kClusterGW - 1u) / (c * kClusterGW); };
+  auto fits = [&](uint32_t c, uint32_t th) { return tilesPerWarp(c, th) <= 32u && ClusterSmem::bytes(tilesPerWarp(c, th), nOcc) <= ctx->maxSmemOptin; };
+  const uint32_t nTiles = tiles_of(width, height, kTileH);
   uint32_t c = 1;
   while (c < 16u && c * kClusterGW < nTiles && nBatch * c * 2u <= (uint32_t)ctx->numSMs) c *= 2u;
   if (ctx->clusterSize) c = (uint32_t)ctx->clusterSize;
-  else while (c < 16u && !fits(c)) c *= 2u;
-  return fits(c) ? c : 0u;
+  else while (c < 16u && !fits(c, kTileH)) c *= 2u;
+  uint32_t th = kTileH;
+  if (ctx->clusterTileH == 1) {
+    // strips (only on request: measured 7-20 % SLOWER than 8 x 4 tiles for one view -- every strip pays the HiZ test, the
+    // chains and the coverage test of a primitive again, and that overhead is what the busiest warp's time is made of),
+    // on the largest cluster that still leaves every warp a tile
+    uint32_t c1 = ctx->clusterSize ? c : 16u;
+    while (!ctx->clusterSize && c1 > 1u && (c1 / 2u) * kClusterGW >= tiles_of(width, height, 1u)) c1 /= 2u;
+    if (fits(c1, 1u)) { c = c1; th = 1u; }
+  }
+  ClusterShape sh = {fits(c, th) ? c : 0u, th};
+  return sh;
 }
-static int launch_cluster(orz_context* ctx, const FrameParams& p, uint32_t nViews, uint32_t nBatch, cudaStream_t st) {
-  const uint32_t nTiles = (((p.width >> 3) + kTileW - 1u) / kTileW) * (((p.height >> 3) + kTileH - 1u) / kTileH);
-  const uint32_t c = pick_cluster_size(ctx, p.width, p.height, p.nOcc, nBatch);
-  if (!c) return fail(ORZ_ERR_ARG, "cluster path: target too large (or too many occluders) for this cluster size");
+static uint32_t pick_cluster_size(const orz_context* ctx, uint32_t width, uint32_t height, uint32_t nOcc, uint32_t nBatch) {
+  return pick_cluster_shape(ctx, width, height, nOcc, nBatch).c;
+}
+template <uint32_t TH>
+static int launch_cluster_c(orz_context* ctx, const FrameParams& p, uint32_t c, uint32_t nViews, cudaStream_t st) {
+  const uint32_t nTiles = tiles_of(p.width, p.height, TH);
   switch (c) {
     case 16:  // non-portable cluster size: when the device (e.g. a partitioned one) cannot place it, use 8
-      if (launch_cluster_t<16>(ctx, p, nViews, nTiles, st) == ORZ_OK) return ORZ_OK;
+      if (launch_cluster_t<16, TH>(ctx, p, nViews, st) == ORZ_OK) return ORZ_OK;
       (void)cudaGetLastError();
       if ((nTiles + 8u * kClusterGW - 1u) / (8u * kClusterGW) > 32u || ClusterSmem::bytes((nTiles + 8u * kClusterGW - 1u) / (8u * kClusterGW), p.nOcc) > ctx->maxSmemOptin)
         return fail(ORZ_ERR_CUDA, "cluster path: 16-CTA clusters are not available on this device");
-      return launch_cluster_t<8>(ctx, p, nViews, nTiles, st);
-    case 8: return launch_cluster_t<8>(ctx, p, nViews, nTiles, st);
-    case 4: return launch_cluster_t<4>(ctx, p, nViews, nTiles, st);
-    case 2: return launch_cluster_t<2>(ctx, p, nViews, nTiles, st);
-    default: return launch_cluster_t<1>(ctx, p, nViews, nTiles, st);
+      return launch_cluster_t<8, TH>(ctx, p, nViews, st);
+    case 8: return launch_cluster_t<8, TH>(ctx, p, nViews, st);
+    case 4: return launch_cluster_t<4, TH>(ctx, p, nViews, st);
+    case 2: return launch_cluster_t<2, TH>(ctx, p, nViews, st);
+    default: return launch_cluster_t<1, TH>(ctx, p, nViews, st);
   }
+}
+static int launch_cluster(orz_context* ctx, const FrameParams& p, uint32_t nViews, uint32_t nBatch, cudaStream_t st) {
+  const ClusterShape sh = pick_cluster_shape(ctx, p.width, p.height, p.nOcc, nBatch);
+  if (!sh.c) return fail(ORZ_ERR_ARG, "cluster path: target too large (or too many occluders) for this cluster size");
+  return sh.tileH == 1u ? launch_cluster_c<1>(ctx, p, sh.c, nViews, st) : launch_cluster_c<kTileH>(ctx, p, sh.c, nViews, st);
 }
 
 // Error paths between the fork of the auxiliary streams and their join must not leave work running on them that later

@@ -40,6 +40,191 @@ __global__ void __launch_bounds__(GW * 32) k_rasterize_single(const ViewMatrices
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The per-call frame loop (Main.cpp:192-206) is a chain of host round trips: queryVisibility returns a bool the
+// application branches on.  Two things take the round trips off the critical path without changing a result:
+//   * rasterize<clipped>(occluder) is ONE launch that splits the occluder over the whole GPU, tile major: every CTA sets
+//     up the <= 512 quads of the batch into shared memory (one lane per quad, in-order compaction) and every warp walks
+//     the records on the tiles it owns with the cluster kernel's traversal (TileWalker::tile_loop);
+//   * the LAST CTA to finish then answers the rectangle queries the application is expected to ask next (`chain`: the
+//     previous frame's sequence of queries, see orz_rasterizer in orz_kernels.cu) -- in order, until the first visible
+//     one (the application will rasterise then, so later answers would be stale).  Queries are read only, so a wrong
+//     prediction costs nothing but the unused answer.
+constexpr uint32_t kChainMax = 12;   // predicted queries a launch carries
+constexpr uint32_t kCallQuadsMax = 512;
+struct QueryChain {
+  uint32_t n;
+  uint32_t rect[kChainMax][5];  // minX, maxX, minY, maxY, maxZ
+  uint32_t tag[kChainMax];      // sequence number << 2 of the expected call; the answer is tag | visible, or tag | 2 = not evaluated
+  uint32_t slot[kChainMax];     // word of the mapped mailbox
+};
+
+// hiz / depth as L2 holds them (other CTAs of this launch have just written them: an L1 line of this SM may be older)
+__device__ __forceinline__ bool query_block_cg(const Target& T, uint32_t bx, uint32_t by, uint32_t minX, uint32_t maxX, uint32_t minY,
+                                               uint32_t maxY, uint32_t maxZ) {
+  const uint32_t b = by * T.blocksX + bx;
+  const uint32_t h = __ldcg(T.hiz + b);
+  if (maxZ <= h) return false;  // Rasterizer.cpp:310
+  if (h == 1u) return true;
+  const int sX = max((int)minX - (int)(8u * bx), 0), eX = min((int)maxX - (int)(8u * bx), 7);
+  const int sY = max((int)minY - (int)(8u * by), 0), eY = min((int)maxY - (int)(8u * by), 7);
+  if (sX == 0 && eX == 7 && sY == 0 && eY == 7) return true;  // Rasterizer.cpp:319-325
+  const uint4* rows = reinterpret_cast<const uint4*>(T.depth + (size_t)b * 64u);
+  const uint32_t mz = maxZ | (maxZ << 16);
+  uint32_t any = 0;
+  for (int y = sY; y <= eY; ++y) {
+    const uint4 r = __ldcg(rows + y);  // visible where depth < maxZ (Rasterizer.cpp:335-339)
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t sel = ((2 * i >= sX && 2 * i <= eX) ? 0x0000ffffu : 0u) | ((2 * i + 1 >= sX && 2 * i + 1 <= eX) ? 0xffff0000u : 0u);
+      any |= __vcmpltu2(w[i], mz) & sel;
+    }
+  }
+  return any != 0u;
+}
+
+// the chain, by all threads of one CTA: query2D (Rasterizer.cpp:283-349) of each rectangle in order, answers into the mailbox
+__device__ __forceinline__ void answer_chain(const Target& T, const QueryChain& chain, volatile uint32_t* mail, uint32_t* s_flag) {
+  const uint32_t tid = threadIdx.x, nThreads = blockDim.x;
+  for (uint32_t q = 0; q < chain.n; ++q) {
+    if (tid == 0) *s_flag = 0u;
+    __syncthreads();
+    const uint32_t minX = chain.rect[q][0], maxX = chain.rect[q][1], minY = chain.rect[q][2], maxY = chain.rect[q][3], maxZ = chain.rect[q][4];
+    const uint32_t bx0 = minX >> 3, by0 = minY >> 3, cols = (maxX >> 3) - bx0 + 1u, rows = (maxY >> 3) - by0 + 1u, n = cols * rows;
+    for (uint32_t base = 0; base < n; base += nThreads) {
+      const uint32_t i = base + tid;
+      bool hit = false;
+      if (i < n) {
+        const uint32_t ry = i / cols, rx = i - ry * cols;
+        hit = query_block_cg(T, bx0 + rx, by0 + ry, minX, maxX, minY, maxY, maxZ);
+      }
+      if (__syncthreads_or(hit ? 1 : 0)) { if (tid == 0) *s_flag = 1u; break; }  // (uniform: every thread sees the same OR)
+    }
+    __syncthreads();
+    const uint32_t vis = *s_flag;
+    if (tid == 0) mail[chain.slot[q]] = chain.tag[q] | vis;
+    if (vis) {  // the application rasterises now: what follows would be answered on an outdated buffer
+      if (tid > q && tid < chain.n) mail[chain.slot[tid]] = chain.tag[tid] | 2u;
+      break;
+    }
+  }
+  __threadfence_system();
+}
+
+__global__ void __launch_bounds__(256) k_query_chain(Target T, const QueryChain chain, volatile uint32_t* mail) {
+  __shared__ uint32_t s_flag;
+  answer_chain(T, chain, mail, &s_flag);
+}
+
+struct CallSmem {
+  static constexpr uint32_t kFixedWords = ClusterSmem::kLutWords + ClusterSmem::kTileAllWords + ClusterSmem::kChainWords + kCallQuadsMax * kRecStride;
+  static size_t bytes(uint32_t tilesPerWarp) { return (size_t)kFixedWords * 4 + (size_t)kClusterGW * tilesPerWarp * 32 * 2; }
+};
+
+template <uint32_t TH>
+__global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_rasterize_call(const CallMatrix cm, const uint4* __restrict__ quads, const uint32_t nq, const int clipped, Target T,
+                                                                 const uint32_t* rcp, const int rcpShift, const uint2* lutGlobal, const uint32_t K,
+                                                                 const QueryChain chain, volatile uint32_t* mail, uint32_t* ticket) {
+  constexpr uint32_t GW = kClusterGW;
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  __shared__ uint32_t s_cnt[GW], s_box[4], s_last, s_flag;
+  uint2* s_lut = reinterpret_cast<uint2*>(s_dyn);
+  uint32_t* s_tileAll = s_dyn + ClusterSmem::kLutWords;
+  float* s_chain = reinterpret_cast<float*>(s_tileAll + ClusterSmem::kTileAllWords);
+  uint32_t* s_recs = reinterpret_cast<uint32_t*>(s_chain) + ClusterSmem::kChainWords;
+  uint16_t* s_hiz = reinterpret_cast<uint16_t*>(s_recs + kCallQuadsMax * kRecStride);  // [GW][K][32]
+  const uint32_t tid = threadIdx.x;
+  const int warp = (int)(tid >> 5), lane = (int)(tid & 31u);
+#if ORZ_LUT_BULK && ORZ_CLUSTER_LUT_SMEM
+  __shared__ __align__(8) uint64_t s_lutBar;
+  if (tid == 0) mbar_init(&s_lutBar, 1u);
+  if (tid < 4) s_box[tid] = tid < 2 ? 0xffffffffu : 0u;
+  __syncthreads();
+  if (tid == 0) bulk_load(s_lut, lutGlobal, 4096u * 8u, &s_lutBar);
+#else
+  if (tid < 4) s_box[tid] = tid < 2 ? 0xffffffffu : 0u;
+  if (ORZ_CLUSTER_LUT_SMEM) for (uint32_t i = tid; i < 4096u; i += GW * 32u) s_lut[i] = lutGlobal[i];
+#endif
+
+  if (tid < 64u && tid * 32u < (1u << (23 - rcpShift))) prefetch_l1(rcp + tid * 32u);  // the reciprocal table (8 KB) on its way before the setup needs it
+  TileWalkerT<TH> tw;
+  tw.T = T;
+  tw.lane = lane; tw.lx = (uint32_t)lane & 7u; tw.ly = (uint32_t)lane >> 3;
+  tw.myHiz = s_hiz + (size_t)warp * K * 32u + lane;
+  tw.myChain = s_chain + warp * (12 * kChainStride);
+  tw.myStage = s_recs; tw.myIdx = nullptr;
+  tw.myTile = reinterpret_cast<uint4*>(s_tileAll + (uint32_t)warp * kTileWords);
+  tw.myAux = s_tileAll + (uint32_t)GW * kTileWords + (uint32_t)warp * kTileAuxWords;
+  tw.lut = ORZ_CLUSTER_LUT_SMEM ? s_lut : lutGlobal;
+  tw.own_tiles(blockIdx.x * GW + (uint32_t)warp, gridDim.x * GW, K);
+  // the buffers continue where the previous calls left them: HiZ of my tiles as L2 holds it
+  for (uint32_t m = tw.allTiles; m; m &= m - 1u) {
+    const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+    const uint32_t bx = __shfl_sync(kFull, tw.tileX0, (int)k) + tw.lx, by = __shfl_sync(kFull, tw.tileY0, (int)k) + tw.ly;
+    tw.myHiz[32u * k] = (bx < T.blocksX && by < T.blocksY && tw.ly < TH) ? __ldcg(T.hiz + by * T.blocksX + bx) : (uint16_t)0xffffu;
+  }
+
+  // ---- setup (Rasterizer.cpp:657-1086): one lane per quad, valid primitives compacted in order into shared memory
+  const RcpTable rt{rcp, rcpShift};
+  bool ok = false;
+  Prim P;
+  if (tid < nq) {
+    const uint4 v = quads[tid];
+    const uint32_t word[4] = {v.x, v.y, v.z, v.w};
+    ok = clipped ? setup_quad<true>(word, cm, rt, c_modeNibbles, (int32_t)T.blocksX, (int32_t)T.blocksY, P)
+                 : setup_quad<false>(word, cm, rt, c_modeNibbles, (int32_t)T.blocksX, (int32_t)T.blocksY, P);
+  }
+  const uint32_t okMask = __ballot_sync(kFull, ok);
+  if (lane == 0) s_cnt[warp] = (uint32_t)__popc(okMask);
+  __syncthreads();
+  uint32_t base = 0, total = 0;
+#pragma unroll
+  for (int w2 = 0; w2 < (int)GW; ++w2) { const uint32_t c = s_cnt[w2]; base += w2 < warp ? c : 0u; total += c; }
+  if (ok) {
+    store_record(s_recs + (base + (uint32_t)__popc(okMask & ((1u << lane) - 1u))) * kRecStride, P);
+    s_recs[(base + (uint32_t)__popc(okMask & ((1u << lane) - 1u))) * kRecStride + 20] = 0u;  // no index wrap on this path (<= 65 536 blocks)
+  }
+  uint32_t bx0 = ok ? (uint32_t)P.minX : 0xffffffffu, by0 = ok ? (uint32_t)P.minY : 0xffffffffu;
+  uint32_t bx1 = ok ? (uint32_t)(P.minX + P.rangeX) : 0u, by1 = ok ? (uint32_t)(P.minY + P.rangeY) : 0u;
+  bx0 = __reduce_min_sync(kFull, bx0); by0 = __reduce_min_sync(kFull, by0);
+  bx1 = __reduce_max_sync(kFull, bx1); by1 = __reduce_max_sync(kFull, by1);
+  if (lane == 0 && okMask) { atomicMin(&s_box[0], bx0); atomicMin(&s_box[1], by0); atomicMax(&s_box[2], bx1); atomicMax(&s_box[3], by1); }
+#if ORZ_LUT_BULK && ORZ_CLUSTER_LUT_SMEM
+  mbar_wait(&s_lutBar, 0u);
+#endif
+  __syncthreads();
+
+  // ---- traversal (Rasterizer.cpp:1088-1293) on my tiles
+  if (total) {
+    const uint32_t tmOcc = tw.tiles_meeting(s_box[0], s_box[2] - 1u, s_box[1], s_box[3] - 1u);
+    if (tmOcc) {
+      for (uint32_t c = 0; c < total; c += 32u) {
+        const uint32_t* stage = s_recs + c * kRecStride;
+        const bool valid = c + (uint32_t)lane < total;
+        const uint32_t a = valid ? stage[lane * kRecStride] : 0u, b = valid ? stage[lane * kRecStride + 1] : 0u;
+        const uint32_t myHits = tw.tile_hits(tmOcc, valid, a, b);
+        bool gathered = true;
+        tw.tile_loop(stage, myHits, gathered);
+      }
+    }
+  }
+
+  // ---- the last CTA to get here answers the queries that are expected next
+  if (chain.n == 0u) return;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t t = atomicAdd(ticket, 1u);
+    s_last = t == gridDim.x - 1u ? 1u : 0u;
+    if (s_last) *ticket = 0u;  // the next launch on this stream starts from zero
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  answer_chain(T, chain, mail, &s_flag);
+}
+
 // setup records of every quad, uncompacted (parity tests of the setup stage)
 __global__ void k_debug_setup(const ViewMatrices vm, const uint4* quads, uint32_t nq, const float4 refMin, const float4 refMax,
                               int clipped, Target T, const uint32_t* rcp, int rcpShift, orz_prim_record* out) {
@@ -78,20 +263,6 @@ __global__ void k_query_boxes(const ViewMatrices vm, const float4* boxes, uint32
   }
   const bool vis = query2d_warp(T, f, (int)(threadIdx.x & 31u));
   if (i < n) out[i] = f.status == kBoxNearClip ? 3 : (vis ? 1 : 0);
-}
-
-// `out` is a word of MAPPED pinned host memory: the answer travels with the tag of the call (sequence number << 1) in one
-// 32-bit store, and the host thread that is waiting for this bool sees it without a copy, an event or a stream sync
-__global__ void k_query2d(Target T, uint32_t minX, uint32_t maxX, uint32_t minY, uint32_t maxY, uint32_t maxZ, volatile uint32_t* out, uint32_t tag) {
-  __shared__ uint32_t s_flag;
-  if (threadIdx.x == 0) s_flag = 0u;
-  __syncthreads();
-  query2d_coop(T, minX, maxX, minY, maxY, maxZ, threadIdx.x, blockDim.x, &s_flag);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    *out = tag | (s_flag ? 1u : 0u);
-    __threadfence_system();
-  }
 }
 
 // readBackDepth, Rasterizer.cpp:351-399: one thread per pixel, BGRA8 row-major

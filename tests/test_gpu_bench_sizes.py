@@ -118,6 +118,31 @@ def test_explicit_cluster_sizes(ctx, size, csize, n):
     sc.close()
 
 
+@pytest.mark.parametrize("scene,size,csize,tile_h,n", [("castle", (1920, 1080), 16, 1, 3), ("castle", (1920, 1080), 8, 1, 5), ("castle", (1920, 1080), 16, 4, 2),
+                                                        ("castle", (512, 256), 16, 1, 2), ("castle", (512, 256), 4, 1, 9), ("castle", (512, 256), 2, 1, 12),
+                                                        ("castle", (1280, 720), 8, 1, 4), ("sponza", (1920, 1080), 16, 1, 2), ("castle", (1920, 1080), 0, 0, 1),
+                                                        ("castle", (1920, 1080), 0, 0, 4), ("castle", (640, 360), 0, 1, 3)])
+def test_tile_heights(ctx, scene, size, csize, tile_h, n):
+    """8 x 1 strips (the few-view / latency shape of the cluster path) and 8 x 4 tiles, forced and automatic, incl. a target
+    whose block rows are not a multiple of anything (45 rows) -- identical results for every shape."""
+    if not wl.have_scene(scene):
+        pytest.skip("prepared scene missing")
+    cs = case(scene)
+    w, h = size
+    mvps, poss = wl.camera_path(cs.ps, n, w, h)
+    boxes = cs.boxes[::3]
+    sc = api.Scene.from_prepared(ctx, cs.ps, boxes=boxes)
+    ctx.set_cluster_size(csize)
+    ctx.set_tile_height(tile_h, 1)
+    try:
+        out = sc.render_views(w, h, mvps, cam_pos=poss, want=ALL)
+    finally:
+        ctx.set_cluster_size(0)
+        ctx.set_tile_height(0, 1)
+    check(cs, w, h, mvps, poss, out, boxes)
+    sc.close()
+
+
 def test_batch_kernel_four_groups_1080p(ctx):
     """The large-batch kernel's >= 64-view path (four sub-batches, atomic view counters) at 1080p."""
     cs = case("castle")

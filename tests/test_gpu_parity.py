@@ -143,6 +143,56 @@ def test_per_call_api_frame(ctx, lut, name, size):
     r.close(); port.close()
 
 
+@pytest.mark.parametrize("name,size,tile_h", [("castle", (1920, 1080), 1), ("castle", (1920, 1080), 4), ("castle", (512, 256), 1), ("city", (640, 360), 1)])
+def test_per_call_api_frames_with_predicted_chains(ctx, lut, name, size, tile_h):
+    """Frame after frame through the per-call API: from the second frame on every launch also answers the queries the
+    previous frame's sequence predicts (orz_percall_kernels.cuh).  Right predictions (same camera again), partly wrong
+    ones (the camera moves: other order, other gate decisions), wrong ones (reversed order, queries without rasterize,
+    repeated queries) -- every answer and every buffer must still be the reference's."""
+    B = bundle(name)
+    w, h = size
+    mvps, poss = wl.camera_path(B.ps, 5, w, h)
+    m0, p0 = B.default_view(w, h)
+    views = [(m0, p0), (m0, p0), (mvps[1], poss[1]), (mvps[4], poss[4]), (m0, p0)]
+    port = po.PortRasterizer(w, h, lut)
+    occs = [api.Occluder(ctx, p, B.ps.ref_min, B.ps.ref_max) for p in B.packed]
+    r = api.Rasterizer(ctx, w, h)
+    ctx.set_tile_height(0, tile_h)
+    for f, (mvp, pos) in enumerate(views):
+        order = cam.front_to_back_order(B.centers, pos)
+        if f == 3:
+            order = order[::-1].copy()  # back to front: nothing the last frame predicts comes in that order
+        r.clear(); port.clear()
+        r.setModelViewProjection(mvp); port.set_mvp(mvp)
+        n_visible = 0
+        for slot, o in enumerate(order):
+            g = port.query(B.bmin[o], B.bmax[o])
+            vis, clip = r.queryVisibility(B.bmin[o], B.bmax[o])
+            assert (int(vis) | (int(clip) << 1)) == g, (f, slot, o)
+            if f == 2 and slot % 5 == 0:  # something unrelated in between, then the same box again
+                o2 = order[(slot * 7 + 3) % len(order)]
+                assert r.queryVisibility(B.bmin[o2], B.bmax[o2])[0] == bool(port.query(B.bmin[o2], B.bmax[o2]) & 1), (f, slot, o2)
+                assert r.queryVisibility(B.bmin[o], B.bmax[o]) == (vis, clip)
+            if vis:
+                n_visible += 1
+                r.rasterize(occs[o], clip)
+                port.rasterize(B.packed[o], B.ps.ref_min, B.ps.ref_max, clip)
+        assert n_visible > 2
+        d, hz = r.download()
+        assert np.array_equal(hz, port.hiz()), f
+        assert np.array_equal(d, port.depth()), f
+    # queries only, no rasterize in between (the chain must not stop answering after a visible one)
+    r.clear()
+    port.clear(); port.set_mvp(m0)
+    r.setModelViewProjection(m0)
+    for o in range(len(occs)):
+        assert r.queryVisibility(B.bmin[o], B.bmax[o])[0] == bool(port.query(B.bmin[o], B.bmax[o]) & 1)
+    ctx.set_tile_height(0, 1)
+    for o in occs:
+        o.close()
+    r.close(); port.close()
+
+
 @pytest.mark.parametrize("trav", [1, 2])
 @pytest.mark.parametrize("gw", [1, 2, 4, 8])
 @pytest.mark.parametrize("name,size,nviews", [("city", (640, 360), 6), ("castle", (1920, 1080), 5), ("castle", (512, 256), 12)])

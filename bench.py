@@ -578,7 +578,7 @@ def run_ours(args):
         kern = res["kernel_ms"]
         achieved = alg / (kern / 1e3) / 1e9
         traffic = ncu_traffic()
-        cluster_limit = args.cluster_views if args.cluster_views >= 0 else 1024
+        cluster_limit = args.cluster_views if args.cluster_views >= 0 else 16384
         cluster_path = n_views <= cluster_limit and (w // 8) * (h // 8) <= 65536
         line = {
             "metric": "views_per_sec", "value": res["value"], "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

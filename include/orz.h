@@ -188,9 +188,9 @@ int orz_context_set_arena_bytes(orz_context* ctx, size_t bytes);
 /* tuning: block traversal mapping of the view-batch kernel: 1 = one warp per 8x8 block,
  * 2 = one lane per block (up to 32 blocks of a primitive in flight per warp) */
 int orz_context_set_traversal(orz_context* ctx, int mapping);
-/* tuning: batches of at most maxViews views (default 1024) run one thread-block cluster (2-16 CTAs x 16 warps)
- * per view -- the latency path for single views (BASELINE configs 1 and 2); 0 = always use the one-CTA-per-view
- * batch kernel */
+/* tuning: batches of at most maxViews views (default 16384) run one thread-block cluster (1-16 CTAs x 16 warps)
+ * per view -- the latency path for single views (BASELINE configs 1 and 2) and, since round 2, the faster path for
+ * every batch size measured; 0 = always use the one-CTA-per-view batch kernel */
 int orz_context_set_cluster_views(orz_context* ctx, int maxViews);
 /* tuning: CTAs (of 16 warps) per cluster on that path: 1, 2, 4, 8 or 16; 0 = automatic (from the target size and the batch) */
 int orz_context_set_cluster_size(orz_context* ctx, int ctas);

@@ -301,6 +301,9 @@ class Occluder:
             self.h = None
 
 
+DEFAULT_CLUSTER_VIEWS = 16384  # orz_context's default for set_cluster_views
+
+
 class Rasterizer:
     """Per-call API of the reference (Rasterizer.h:10-61) on one view's device buffers."""
 

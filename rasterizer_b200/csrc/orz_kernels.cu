@@ -98,7 +98,7 @@ struct orz_context {
   uint64_t launches = 0;
   int groupWarps = 0;
   int traversal = 2;  // 1 = warp per block, 2 = lane per block (default)
-  int clusterViews = 1024;  // batches of at most this many views run one thread-block cluster per view (0 = never)
+  int clusterViews = 16384;  // batches of at most this many views run one thread-block cluster per view (0 = never); measured faster than the large-batch kernel at every size (profiles/r2_probe_matrix_paths.txt)
   int clusterSize = 0;     // CTAs per cluster (2, 4, 8, 16); 0 = automatic
   // grow-only device scratch
   uint32_t* d_counter = nullptr;
@@ -1002,6 +1002,7 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
   const size_t recBudget = size_t(8) << 30;
   if (ctx->clusterViews > 0 && b->nViews <= (size_t)ctx->clusterViews && recPerView > 0 && recBudget / recPerView >= 256)
     chunk = std::min<size_t>(chunk, recBudget / recPerView);
+  if (chunk < b->nViews) chunk = (b->nViews + (b->nViews + chunk - 1) / chunk - 1) / ((b->nViews + chunk - 1) / chunk);  // equal chunks
   if (ownTargets) {
     const size_t perView = blocks * 128 + hizStride * 2;
     const size_t budget = std::max<size_t>(ctx->arenaBudget, perView);

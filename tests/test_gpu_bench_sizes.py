@@ -72,14 +72,20 @@ def test_castle_1080p_1024_views_default_path(ctx):
     sc.close()
 
 
-@pytest.mark.parametrize("n", [1024, 8192])
-def test_castle_512x256_probes(ctx, n):
-    """BASELINE config 5: the per-GPU slice of an 8-GPU run (1 024 probes) and the whole batch on one GPU (8 192)."""
+@pytest.mark.parametrize("n,cluster_views", [(1024, None), (8192, None), (8192, 1024)])
+def test_castle_512x256_probes(ctx, n, cluster_views):
+    """BASELINE config 5: the per-GPU slice of an 8-GPU run (1 024 probes) and the whole batch on one GPU (8 192: the cluster
+    path in three chunks of views, and -- cluster_views 1024 -- the large-batch kernel with its four sub-batches)."""
     cs = case("castle")
     w, h = 512, 256
     mvps, poss = wl.probe_views(cs.ps, n, w, h)
     sc = api.Scene.from_prepared(ctx, cs.ps)
-    out = sc.render_views(w, h, mvps, cam_pos=poss, want=ALL)
+    if cluster_views is not None:
+        ctx.set_cluster_views(cluster_views)
+    try:
+        out = sc.render_views(w, h, mvps, cam_pos=poss, want=ALL)
+    finally:
+        ctx.set_cluster_views(api.DEFAULT_CLUSTER_VIEWS)
     check(cs, w, h, mvps, poss, out, cs.boxes)
     out2 = sc.render_views(w, h, mvps, cam_pos=poss, want=("vis",))  # what the bench asks for: bits only
     assert np.array_equal(out2["vis"], out["vis"])
@@ -153,7 +159,7 @@ def test_batch_kernel_four_groups_1080p(ctx):
     try:
         out = sc.render_views(w, h, mvps, cam_pos=poss, want=ALL)
     finally:
-        ctx.set_cluster_views(1024)
+        ctx.set_cluster_views(api.DEFAULT_CLUSTER_VIEWS)
     check(cs, w, h, mvps, poss, out, cs.boxes)
     sc.close()
 

@@ -226,7 +226,7 @@ def test_view_batch(ctx, lut, name, size, nviews, gw, trav):
     assert np.array_equal(out2["gate"], out["gate"])
     ctx.set_group_warps(0)
     ctx.set_traversal(2)
-    ctx.set_cluster_views(1024)
+    ctx.set_cluster_views(api.DEFAULT_CLUSTER_VIEWS)
     sc.close(); port.close()
 
 
@@ -238,7 +238,7 @@ def test_view_cluster_path(ctx, lut, name, size, nviews):
     view run as a dataflow machine (tile-local gates, DSMEM decision flags, k_raster_views_cluster)."""
     B = bundle(name)
     w, h = size
-    ctx.set_cluster_views(1024)
+    ctx.set_cluster_views(api.DEFAULT_CLUSTER_VIEWS)
     mvps, poss = wl.camera_path(B.ps, nviews - 1, w, h) if size[0] >= 640 else wl.probe_views(B.ps, nviews - 1, w, h)
     m0, p0 = B.default_view(w, h)
     mvps = np.concatenate([m0[None], mvps]); poss = np.concatenate([p0[None], poss])
@@ -264,7 +264,7 @@ def test_view_cluster_path(ctx, lut, name, size, nviews):
     # and the batch kernel gives the same answer
     ctx.set_cluster_views(0)
     out3 = sc.render_views(w, h, mvps, orders=orders, want=("vis", "gate", "depth", "hiz"))
-    ctx.set_cluster_views(1024)
+    ctx.set_cluster_views(api.DEFAULT_CLUSTER_VIEWS)
     for k in ("vis", "gate", "depth", "hiz"):
         assert np.array_equal(out3[k], out[k]), k
     sc.close(); port.close()
@@ -282,7 +282,7 @@ def test_no_gate_forced_clip_and_4k_wrap(ctx, lut, size, cluster):
     orders = wl.orders_for(B.centers, poss)
     sc = B.scene(ctx, B.boxes[::7])
     out = sc.render_views(w, h, mvps, orders=orders, flags=api.BATCH_NO_GATE | api.BATCH_FORCE_CLIPPED, want=("vis", "depth", "hiz"))
-    ctx.set_cluster_views(1024)
+    ctx.set_cluster_views(api.DEFAULT_CLUSTER_VIEWS)
     vis = api.unpack_bits(out["vis"], len(B.boxes[::7]))
     port = po.PortRasterizer(w, h, lut)
     for v in range(2):
@@ -321,7 +321,7 @@ def test_soup_near_clipped(ctx, lut, cluster):
                 assert np.array_equal(out["gate"][v], gate)
             assert np.array_equal(out["hiz"][v], port.hiz())
             assert np.array_equal(out["depth"][v], port.depth())
-    ctx.set_cluster_views(1024)
+    ctx.set_cluster_views(api.DEFAULT_CLUSTER_VIEWS)
     sc.close(); port.close()
 
 

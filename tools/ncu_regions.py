@@ -24,10 +24,11 @@ marks = [
     ("gate test on my tiles", "// ---- gate: query2D (Rasterizer.cpp:283-349) on the part"),
     ("decision wait (spin)", "// visible as soon as ONE warp says so"),
     ("occluder prologue (info, box)", "// ---- rasterize<clipped>(occluder): the records k_setup_views wrote"),
-    ("flush: gather + tile loop", "    auto flush = [&]() {"),
+    ("flush: gather + tile loop", "auto flush = [&]() {"),
+    ("tile_hits / tile_loop (which record on which tile, tile order)", "__device__ __forceinline__ uint32_t tile_hits("),
     ("flush: tile open (load)", "// open the tile: its depth goes to shared memory"),
-    ("flush: tile close (store)", "        if (dirty) {"),
-    ("header scan + staging", "    for (uint32_t r0 = 0; r0 < cnt; r0 += 32u) {"),
+    ("flush: tile close (store)", "if (dirty) {  // close"),
+    ("header scan + staging", "for (uint32_t r0 = 0; r0 < cnt; r0 += 32u) {"),
     ("epilogue (zero fill, final barrier, outputs)", "cluster.sync();  // no CTA may leave"),
 ]
 bounds = sorted((line_of(m), name) for name, m in marks)

@@ -121,6 +121,7 @@ struct orz_context {
   // per device and idempotent: keeping the record per context avoids process-wide mutable state)
   size_t smemViews[2][5] = {{0}};   // [traversal - 1][log2 GW]
   size_t smemCluster[10] = {0};     // [log2 C (+ 5 for 8 x 1 tiles)]
+  uint32_t groupCut[kGroups + 1] = {0, 250, 500, 750, 1000};  // cumulative per-mille shares of the cluster path's sub-batches (ORZ_GROUP_CUTS="a,b,c")
   int clusterTileH = 0;             // tile height of the cluster path: 4, 1, or 0 = automatic = 4 (ORZ_CLUSTER_TILE_H)
   uint32_t percallTileH = 1;        // tile height of the per-call rasterize (ORZ_PERCALL_TILE_H)
   size_t smemTiles = 0;             // k_raster_tiles
@@ -195,6 +196,10 @@ extern "C" int orz_context_create(int device, orz_context** out) {
   memset(ctx->h_pinned, 0, orz_context::kMailSlots * 4);
   ORZ_CUDA_OR(orz_context_destroy(ctx), cudaMemset(ctx->d_counter, 0, 64));
   if (const char* legacy = getenv("ORZ_PERCALL_LEGACY")) ctx->percallLegacy = legacy[0] == '1';
+  if (const char* cuts = getenv("ORZ_GROUP_CUTS")) {
+    unsigned a = 250, b = 500, c = 750;
+    if (sscanf(cuts, "%u,%u,%u", &a, &b, &c) == 3 && a <= b && b <= c && c <= 1000) { ctx->groupCut[1] = a; ctx->groupCut[2] = b; ctx->groupCut[3] = c; }
+  }
   if (const char* th = getenv("ORZ_PERCALL_TILE_H")) ctx->percallTileH = atoi(th) == 4 ? 4u : 1u;
   if (const char* th = getenv("ORZ_CLUSTER_TILE_H")) ctx->clusterTileH = atoi(th) == 1 ? 1 : atoi(th) == 4 ? 4 : 0;
   ORZ_CUDA_OR(orz_context_destroy(ctx), cudaHostGetDevicePointer((void**)&ctx->d_mail, ctx->h_pinned, 0));
@@ -1170,8 +1175,11 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
         cudaStream_t st = groupsC > 1 ? ctx->aux[g] : ctx->stream;
         if (groupsC > 1) ORZ_CUDA(cudaStreamWaitEvent(st, ctx->evFork, 0));
         FrameParams pg = pc;
-        pg.viewBase = (uint32_t)((uint64_t)nv * g / groupsC);
-        pg.groupViews = (uint32_t)((uint64_t)nv * (g + 1) / groupsC) - pg.viewBase;
+        // cumulative shares of the sub-batches (per mille): the first one's setup and the last one's queries have nothing
+        // to overlap with, so the ends are smaller than the middle
+        pg.viewBase = groupsC > 1 ? (uint32_t)((uint64_t)nv * ctx->groupCut[g] / 1000u) : 0u;
+        pg.groupViews = (groupsC > 1 ? (uint32_t)((uint64_t)nv * ctx->groupCut[g + 1] / 1000u) : nv) - pg.viewBase;
+        if (pg.groupViews == 0u) continue;
         k_setup_views<<<dim3(pg.nOcc, pg.groupViews), 256, 0, st>>>(pg);
         ctx->launches++;
         ORZ_CUDA(cudaGetLastError());

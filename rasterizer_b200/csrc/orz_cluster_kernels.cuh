@@ -871,6 +871,16 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
 
     tw.rasterize(recs, hdrs, cnt, tmOcc);
   }
+  if (p.coarseHiz) {  // the view is final on my tiles: their smallest HiZ, for the occludee queries' coarse look (orz_query.cuh)
+    uint16_t* coarse = p.coarseHiz + (size_t)view * p.coarseStride;
+    for (uint32_t m = tw.allTiles; m; m &= m - 1u) {
+      const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+      const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
+      const uint32_t h = (bx < T.blocksX && by < T.blocksY && ly < TH) ? (uint32_t)myHiz[32u * k] : 0xffffu;
+      const uint32_t lo = __reduce_min_sync(kFull, h);
+      if (lane == 0) coarse[gw + k * kWarps] = (uint16_t)lo;
+    }
+  }
   if (p.exportDepth) tw.zero_cleared_tiles();
   cluster.sync();  // no CTA may leave while another one can still write its decision words
   // ---- the view's per-slot outputs (Main.cpp:195-204), from the now final decision words

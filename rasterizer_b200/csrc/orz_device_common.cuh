@@ -87,4 +87,6 @@ struct FrameParams {
   uint4* recInfo;       // [nViews][nOcc][2]: {records, first record slot, quadCount, -}, {block rectangle of all records, half open}
   uint2* occBox;        // [nViews][nOcc]: the same block rectangle packed {x0 | y0 << 16, x1 | y1 << 16}, {~0, 0} when there are no records
   uint32_t totalQuads;  // record slots per view (2 per quad above 65 536 blocks: index wrap)
+  uint16_t* coarseHiz;  // [nViews][coarseStride]: smallest HiZ per tile of 8 x coarseCellH blocks, written by the cluster kernel for k_query_views (or NULL)
+  uint32_t coarseStride, coarseCellH;
 };

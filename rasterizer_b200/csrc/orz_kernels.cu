@@ -102,8 +102,8 @@ struct orz_context {
   int clusterSize = 0;     // CTAs per cluster (2, 4, 8, 16); 0 = automatic
   // grow-only device scratch
   uint32_t* d_counter = nullptr;
-  void* d_scratch[12] = {nullptr};
-  size_t scratchBytes[12] = {0};
+  void* d_scratch[14] = {nullptr};
+  size_t scratchBytes[14] = {0};
   // pinned + mapped mailbox for the per-call queries: the answering kernel stores tag | answer straight into a word the
   // waiting host thread polls (no copy, no event, no stream sync); slots are handed out round robin, tags never repeat
   static constexpr uint32_t kMailSlots = 256;
@@ -123,6 +123,7 @@ struct orz_context {
   size_t smemCluster[10] = {0};     // [log2 C (+ 5 for 8 x 1 tiles)]
   uint32_t groupCut[kGroups + 1] = {0, 250, 500, 750, 1000};  // cumulative per-mille shares of the cluster path's sub-batches (ORZ_GROUP_CUTS="a,b,c")
   int clusterTileH = 0;             // tile height of the cluster path: 4, 1, or 0 = automatic = 4 (ORZ_CLUSTER_TILE_H)
+  bool coarseQuery = false;         // cluster path: occludee queries look at per-tile HiZ minima first (ORZ_COARSE_QUERY=1; exact, measured neutral: off)
   uint32_t percallTileH = 1;        // tile height of the per-call rasterize (ORZ_PERCALL_TILE_H)
   size_t smemTiles = 0;             // k_raster_tiles
 };
@@ -196,6 +197,7 @@ extern "C" int orz_context_create(int device, orz_context** out) {
   memset(ctx->h_pinned, 0, orz_context::kMailSlots * 4);
   ORZ_CUDA_OR(orz_context_destroy(ctx), cudaMemset(ctx->d_counter, 0, 64));
   if (const char* legacy = getenv("ORZ_PERCALL_LEGACY")) ctx->percallLegacy = legacy[0] == '1';
+  if (const char* cq = getenv("ORZ_COARSE_QUERY")) ctx->coarseQuery = cq[0] != '0';
   if (const char* cuts = getenv("ORZ_GROUP_CUTS")) {
     unsigned a = 250, b = 500, c = 750;
     if (sscanf(cuts, "%u,%u,%u", &a, &b, &c) == 3 && a <= b && b <= c && c <= 1000) { ctx->groupCut[1] = a; ctx->groupCut[2] = b; ctx->groupCut[3] = c; }
@@ -1164,6 +1166,14 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
       pc.recBuf = (uint32_t*)((uint8_t*)pc.recInfo + (size_t)nv * nOcc * 32);
       pc.totalQuads = (uint32_t)recSlots;
       pc.occBox = nullptr;
+      if ((p.visBits || p.clipBits) && ctx->coarseQuery) {  // per-tile HiZ minima for the occludee queries
+        const ClusterShape sh = pick_cluster_shape(ctx, b->width, b->height, (uint32_t)nOcc, nv);
+        const uint32_t nTilesQ = tiles_of(b->width, b->height, sh.tileH);
+        if ((e = ensure_scratch(ctx, 12, (size_t)nv * nTilesQ * 2))) return e;
+        pc.coarseHiz = (uint16_t*)ctx->d_scratch[12];
+        pc.coarseStride = nTilesQ;
+        pc.coarseCellH = sh.tileH;
+      }
       // Large batches: sub-batches (by descending cost) on auxiliary streams, so that the occludee queries of a
       // finished sub-batch fill the SMs the cluster kernel of the next one leaves idle; each sub-batch sets up its
       // own views first, so the heaviest views start rasterising after a quarter of the setup work.

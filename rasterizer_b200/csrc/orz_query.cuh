@@ -47,7 +47,12 @@ __device__ bool query2d_serial(const Target& T, uint32_t minX, uint32_t maxX, ui
 // (which would leave 31 lanes idle for hundreds of iterations) are taken one at a time by the whole
 // warp, 32 blocks per step with coalesced HiZ reads.  query2D is an OR over blocks, so the visiting
 // order does not matter.  Returns this lane's visibility.
-__device__ __forceinline__ bool query2d_warp(const Target& T, const BoxFront& f, const int lane) {
+// `coarse` (optional): per cell of 8 x cellH blocks the SMALLEST HiZ of its blocks (written by the cluster kernel at the end
+// of a view).  query2D only passes a block when maxZ > its HiZ (Rasterizer.cpp:310), so a large rectangle none of whose
+// cells has maxZ > the cell's minimum cannot pass anywhere: the common case of an occluded box costs one look per cell
+// instead of one per block.  Everything else takes the block walk unchanged.
+__device__ __forceinline__ bool query2d_warp(const Target& T, const BoxFront& f, const int lane, const uint16_t* __restrict__ coarse = nullptr,
+                                             const uint32_t cellH = 4u) {
   bool vis = false, big = false;
   if (f.status == kBoxRect) {
     const uint32_t nb = ((f.maxX >> 3) - (f.minX >> 3) + 1u) * ((f.maxY >> 3) - (f.minY >> 3) + 1u);
@@ -63,6 +68,16 @@ __device__ __forceinline__ bool query2d_warp(const Target& T, const BoxFront& f,
     const uint32_t maxZ = __shfl_sync(kFull, f.maxZ, src);
     const uint32_t bx0 = minX >> 3, by0 = minY >> 3;
     const uint32_t cols = (maxX >> 3) - bx0 + 1u, rows = (maxY >> 3) - by0 + 1u;
+    if (coarse) {
+      const uint32_t cellsX = (T.blocksX + 7u) >> 3;
+      const uint32_t cx0 = bx0 >> 3, cy0 = by0 / cellH, ccols = ((maxX >> 3) >> 3) - cx0 + 1u, ncell = ccols * ((maxY >> 3) / cellH - cy0 + 1u);
+      bool open = false;
+      for (uint32_t c = (uint32_t)lane; c < ncell; c += 32u) {
+        const uint32_t cy = c / ccols, cx = c - cy * ccols;
+        open = open || maxZ > (uint32_t)coarse[(cy0 + cy) * cellsX + cx0 + cx];
+      }
+      if (!__any_sync(kFull, open)) continue;  // vis of lane src stays false
+    }
     // lane j starts at block j of the rectangle (row major) and advances 32 blocks at a time:
     // (row, column) are stepped incrementally, two divisions per box instead of one per block
     const uint32_t q32 = 32u / cols, r32 = 32u - q32 * cols;
@@ -155,7 +170,8 @@ __global__ void __launch_bounds__(256) k_query_views(const FrameParams p) {
     f = box_front_half(s_vm, bmn, bmx, p.width, p.height, rt);
   }
   const bool clip = f.status == kBoxNearClip;
-  const bool seen = query2d_warp(T, f, (int)(tid & 31u));  // every lane must take part (warp collectives inside)
+  const bool seen = query2d_warp(T, f, (int)(tid & 31u), p.coarseHiz ? p.coarseHiz + (size_t)view * p.coarseStride : nullptr,
+                                 p.coarseCellH);  // every lane must take part (warp collectives inside)
   const bool vis = clip || seen;
   const uint32_t vb = __ballot_sync(kFull, vis), cb = __ballot_sync(kFull, clip);
   const uint32_t word = i >> 5;

@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(128) k_prepare_views(const FrameParams p) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) { out[6 + k] = f2u(cm.rx[k]); out[10 + k] = f2u(cm.ry[k]); out[14 + k] = f2u(cm.rw[k]); }
     out[18] = f2u(cm.c0); out[19] = f2u(cm.c1);
+    out[20] = om.quadOffset; out[21] = om.quadCount;  // (k_setup_views: one read instead of order -> occluder meta)
     if (f.status != kBoxCulled) cost += om.quadCount;
   }
   // per-view work estimate for longest-first scheduling of the render kernel

@@ -107,7 +107,10 @@ struct ClusterSmem {
 };
 
 // ---- speculative setup of every occluder that survives the frustum, Rasterizer.cpp:657-1086
-__global__ void __launch_bounds__(256) k_setup_views(const FrameParams p) {
+#ifndef ORZ_SETUP_CTAS
+#define ORZ_SETUP_CTAS 4
+#endif
+__global__ void __launch_bounds__(256, ORZ_SETUP_CTAS) k_setup_views(const FrameParams p) {
   __shared__ uint32_t s_cnt[8];
   __shared__ uint32_t s_box[4];
   // grid: (order slot, rank of the view in this launch's group of the cost-sorted batch)
@@ -125,8 +128,7 @@ __global__ void __launch_bounds__(256) k_setup_views(const FrameParams p) {
   }
   const bool useGate = (p.flags & ORZ_BATCH_NO_GATE) == 0u;
   const bool clipped = status == kBoxNearClip ? (useGate ? true : (p.flags & ORZ_BATCH_FORCE_CLIPPED) != 0u) : false;
-  const uint32_t* order = p.orders ? p.orders + (size_t)view * p.nOcc : p.orderBuf + (size_t)view * p.nOcc;
-  const OccMeta& om = p.occ[order[slot]];
+  struct { uint32_t quadOffset, quadCount; } om = {fr[20], fr[21]};  // the occluder of this order slot (k_prepare_views)
   const RcpTable rt{p.rcp, p.rcpShift};
   CallMatrix cm;
 #pragma unroll

@@ -48,7 +48,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 // (avg_u16x2 and the other packed-u16 helpers: orz_pixel.h)
 
 
-constexpr int kFrontWords = 20;  // status, minX, maxX, minY, maxY, maxZ, CallMatrix (14 floats)
+constexpr int kFrontWords = 22;  // status, minX, maxX, minY, maxY, maxZ, CallMatrix (14 floats), quadOffset, quadCount of the occluder in this order slot
 
 struct FrameParams {
   const uint4* quads;

@@ -34,12 +34,41 @@ __device__ __forceinline__ bool query_block(const Target& T, uint32_t bx, uint32
   return block_fine_test(T.depth, b, maxZ, sX, eX, sY, eY);
 }
 
-// one thread walks the whole rectangle (occludee queries)
+#ifndef ORZ_QUERY_SERIAL_MAX
+#define ORZ_QUERY_SERIAL_MAX 48u  // rectangles of at most this many blocks are walked by their own lane (6 / 12 / 24 / 48 / 96 / 192 measured: profiles/r2ag_*, r2ah_*)
+#endif
+#ifndef ORZ_QUERY_SERIAL_PAIRS
+#define ORZ_QUERY_SERIAL_PAIRS 0  // 1: that walk keeps two HiZ reads in flight
+#endif
+// the same with the block's HiZ already loaded
+__device__ __forceinline__ bool query_block_loaded(const Target& T, uint32_t bx, uint32_t by, uint32_t h, uint32_t minX, uint32_t maxX,
+                                                   uint32_t minY, uint32_t maxY, uint32_t maxZ) {
+  if (maxZ <= h) return false;  // Rasterizer.cpp:310
+  if (h == 1u) return true;
+  const int sX = max((int)minX - (int)(8u * bx), 0), eX = min((int)maxX - (int)(8u * bx), 7);
+  const int sY = max((int)minY - (int)(8u * by), 0), eY = min((int)maxY - (int)(8u * by), 7);
+  if (sX == 0 && eX == 7 && sY == 0 && eY == 7) return true;  // Rasterizer.cpp:319-325
+  return block_fine_test(T.depth, by * T.blocksX + bx, maxZ, sX, eX, sY, eY);
+}
+
+// one thread walks the whole rectangle (occludee queries); query2D is an OR over blocks, so two HiZ reads are kept in
+// flight per step (a rectangle behind the occluders is a chain of dependent L1 / L2 round trips otherwise)
 __device__ bool query2d_serial(const Target& T, uint32_t minX, uint32_t maxX, uint32_t minY, uint32_t maxY, uint32_t maxZ) {
   const uint32_t bx0 = minX >> 3, bx1 = maxX >> 3, by0 = minY >> 3, by1 = maxY >> 3;
+#if ORZ_QUERY_SERIAL_PAIRS
+  for (uint32_t by = by0; by <= by1; ++by) {
+    const uint16_t* row = T.hiz + by * T.blocksX;
+    for (uint32_t bx = bx0; bx <= bx1; bx += 2u) {
+      const uint32_t h0 = row[bx], h1 = bx + 1u <= bx1 ? (uint32_t)row[bx + 1u] : 0xffffu;  // maxZ <= 0xffff: never passes
+      if (query_block_loaded(T, bx, by, h0, minX, maxX, minY, maxY, maxZ)) return true;
+      if (query_block_loaded(T, bx + 1u, by, h1, minX, maxX, minY, maxY, maxZ)) return true;
+    }
+  }
+#else
   for (uint32_t by = by0; by <= by1; ++by)
     for (uint32_t bx = bx0; bx <= bx1; ++bx)
       if (query_block(T, bx, by, minX, maxX, minY, maxY, maxZ)) return true;
+#endif
   return false;
 }
 
@@ -56,7 +85,7 @@ __device__ __forceinline__ bool query2d_warp(const Target& T, const BoxFront& f,
   bool vis = false, big = false;
   if (f.status == kBoxRect) {
     const uint32_t nb = ((f.maxX >> 3) - (f.minX >> 3) + 1u) * ((f.maxY >> 3) - (f.minY >> 3) + 1u);
-    if (nb <= 6u) vis = query2d_serial(T, f.minX, f.maxX, f.minY, f.maxY, f.maxZ);
+    if (nb <= ORZ_QUERY_SERIAL_MAX) vis = query2d_serial(T, f.minX, f.maxX, f.minY, f.maxY, f.maxZ);
     else big = true;
   }
   uint32_t pending = __ballot_sync(kFull, big);

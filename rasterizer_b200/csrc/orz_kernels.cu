@@ -807,14 +807,14 @@ extern "C" void orz_scene_destroy(orz_scene* s) {
 // queryVisibility of every occludee box for views [pg.viewBase, pg.viewBase + pg.groupViews) of the (sorted) batch:
 // 1-D grids of (view, 256-box chunk) CTAs, in slabs of views when one grid cannot hold them all
 static int launch_query(orz_context* ctx, FrameParams pg, uint32_t nBoxes, cudaStream_t st) {
-  pg.queryChunks = (nBoxes + 255u) / 256u;
+  pg.queryChunks = (nBoxes + kQueryThreads - 1u) / kQueryThreads;
   if (pg.queryChunks == 0u || pg.groupViews == 0u) return ORZ_OK;
   const uint32_t slab = std::max<uint32_t>(1u, 0x7fffffffu / pg.queryChunks);
   const uint32_t first = pg.viewBase, last = pg.viewBase + pg.groupViews;
   for (uint32_t v = first; v < last; v += slab) {
     pg.viewBase = v;
     pg.groupViews = std::min(slab, last - v);
-    k_query_views<<<pg.groupViews * pg.queryChunks, 256, 0, st>>>(pg);
+    k_query_views<<<pg.groupViews * pg.queryChunks, kQueryThreads, 0, st>>>(pg);
     ctx->launches++;
     ORZ_CUDA(cudaGetLastError());
   }

@@ -178,7 +178,11 @@ __device__ __forceinline__ void query2d_coop(const Target& T, uint32_t minX, uin
 
 
 // queryVisibility for every (view, occludee box) on the finished buffers; Rasterizer.cpp:123-349
-__global__ void __launch_bounds__(256) k_query_views(const FrameParams p) {
+#ifndef ORZ_QUERY_THREADS
+#define ORZ_QUERY_THREADS 128  // 64 / 96 / 128 / 256 / 512 measured (profiles/r2aj_*, r2ak_*)
+#endif
+constexpr uint32_t kQueryThreads = ORZ_QUERY_THREADS;  // boxes per CTA of k_query_views
+__global__ void __launch_bounds__(kQueryThreads) k_query_views(const FrameParams p) {
   __shared__ ViewMatrices s_vm;
   // 1-D grid, view major (grid.y would cap a batch at 65 535 views): CTA = (rank of the view in this launch, chunk of 256 boxes)
   const uint32_t vrank = blockIdx.x / p.queryChunks, chunk = blockIdx.x - vrank * p.queryChunks;

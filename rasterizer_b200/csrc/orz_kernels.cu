@@ -42,6 +42,9 @@
 #ifndef ORZ_SPIN_NAP
 #define ORZ_SPIN_NAP 32  // ns a warp sleeps between two looks at a gate decision (0 = pure spin)
 #endif
+#ifndef ORZ_GROUPS
+#define ORZ_GROUPS 4  // sub-batches of a large batch, each on its own stream (2 / 6 / 8 measured: profiles/r2am_*)
+#endif
 #ifndef ORZ_THREADS_PER_SM_V2
 #define ORZ_THREADS_PER_SM_V2 512  // same, for the lane-per-block traversal (register cap 128)
 #endif
@@ -113,7 +116,7 @@ struct orz_context {
   uint32_t mailNext = 0;         // next slot
   size_t smemCall = 0;           // k_rasterize_call
   bool percallLegacy = false;    // ORZ_PERCALL_LEGACY=1: one launch per rasterize (round-1 kernel) and per query, no predicted chains
-  static constexpr int kGroups = 4;          // sub-batches pipelined on auxiliary streams
+  static constexpr int kGroups = ORZ_GROUPS;  // sub-batches pipelined on auxiliary streams
   cudaStream_t aux[kGroups] = {nullptr};
   cudaEvent_t evFork = nullptr, evJoin[kGroups] = {nullptr};
   size_t arenaBudget = size_t(8) << 30;  // bytes of internal per-view depth+HiZ targets (views are chunked to fit)
@@ -121,7 +124,8 @@ struct orz_context {
   // per device and idempotent: keeping the record per context avoids process-wide mutable state)
   size_t smemViews[2][5] = {{0}};   // [traversal - 1][log2 GW]
   size_t smemCluster[10] = {0};     // [log2 C (+ 5 for 8 x 1 tiles)]
-  uint32_t groupCut[kGroups + 1] = {0, 250, 500, 750, 1000};  // cumulative per-mille shares of the cluster path's sub-batches (ORZ_GROUP_CUTS="a,b,c")
+  uint32_t groupCut[kGroups + 1];   // cumulative per-mille shares of the cluster path's sub-batches (equal; ORZ_GROUP_CUTS="a,b,c" with four groups)
+  orz_context() { for (int g = 0; g <= kGroups; ++g) groupCut[g] = 1000u * (uint32_t)g / (uint32_t)kGroups; }
   int clusterTileH = 0;             // tile height of the cluster path: 4, 1, or 0 = automatic = 4 (ORZ_CLUSTER_TILE_H)
   bool coarseQuery = false;         // cluster path: occludee queries look at per-tile HiZ minima first (ORZ_COARSE_QUERY=1; exact, measured neutral: off)
   uint32_t percallTileH = 1;        // tile height of the per-call rasterize (ORZ_PERCALL_TILE_H)
@@ -200,7 +204,7 @@ extern "C" int orz_context_create(int device, orz_context** out) {
   if (const char* cq = getenv("ORZ_COARSE_QUERY")) ctx->coarseQuery = cq[0] != '0';
   if (const char* cuts = getenv("ORZ_GROUP_CUTS")) {
     unsigned a = 250, b = 500, c = 750;
-    if (sscanf(cuts, "%u,%u,%u", &a, &b, &c) == 3 && a <= b && b <= c && c <= 1000) { ctx->groupCut[1] = a; ctx->groupCut[2] = b; ctx->groupCut[3] = c; }
+    if (orz_context::kGroups == 4 && sscanf(cuts, "%u,%u,%u", &a, &b, &c) == 3 && a <= b && b <= c && c <= 1000) { ctx->groupCut[1] = a; ctx->groupCut[2] = b; ctx->groupCut[3] = c; }
   }
   if (const char* th = getenv("ORZ_PERCALL_TILE_H")) ctx->percallTileH = atoi(th) == 4 ? 4u : 1u;
   if (const char* th = getenv("ORZ_CLUSTER_TILE_H")) ctx->clusterTileH = atoi(th) == 1 ? 1 : atoi(th) == 4 ? 4 : 0;

@@ -37,8 +37,8 @@ __device__ __forceinline__ bool query_block(const Target& T, uint32_t bx, uint32
 #ifndef ORZ_QUERY_SERIAL_MAX
 #define ORZ_QUERY_SERIAL_MAX 48u  // rectangles of at most this many blocks are walked by their own lane (6 / 12 / 24 / 48 / 96 / 192 measured: profiles/r2ag_*, r2ah_*)
 #endif
-#ifndef ORZ_QUERY_SERIAL_PAIRS
-#define ORZ_QUERY_SERIAL_PAIRS 0  // 1: that walk keeps two HiZ reads in flight
+#ifndef ORZ_QUERY_SERIAL_UNROLL
+#define ORZ_QUERY_SERIAL_UNROLL 2  // HiZ reads that walk keeps in flight (1 / 2 / 4 measured: profiles/r2ao_*)
 #endif
 // the same with the block's HiZ already loaded
 __device__ __forceinline__ bool query_block_loaded(const Target& T, uint32_t bx, uint32_t by, uint32_t h, uint32_t minX, uint32_t maxX,
@@ -55,14 +55,21 @@ __device__ __forceinline__ bool query_block_loaded(const Target& T, uint32_t bx,
 // flight per step (a rectangle behind the occluders is a chain of dependent L1 / L2 round trips otherwise)
 __device__ bool query2d_serial(const Target& T, uint32_t minX, uint32_t maxX, uint32_t minY, uint32_t maxY, uint32_t maxZ) {
   const uint32_t bx0 = minX >> 3, bx1 = maxX >> 3, by0 = minY >> 3, by1 = maxY >> 3;
-#if ORZ_QUERY_SERIAL_PAIRS
-  for (uint32_t by = by0; by <= by1; ++by) {
-    const uint16_t* row = T.hiz + by * T.blocksX;
-    for (uint32_t bx = bx0; bx <= bx1; bx += 2u) {
-      const uint32_t h0 = row[bx], h1 = bx + 1u <= bx1 ? (uint32_t)row[bx + 1u] : 0xffffu;  // maxZ <= 0xffff: never passes
-      if (query_block_loaded(T, bx, by, h0, minX, maxX, minY, maxY, maxZ)) return true;
-      if (query_block_loaded(T, bx + 1u, by, h1, minX, maxX, minY, maxY, maxZ)) return true;
+#if ORZ_QUERY_SERIAL_UNROLL > 1
+  // the rectangle's blocks in row-major order, ORZ_QUERY_SERIAL_UNROLL HiZ reads in flight per step
+  const uint32_t cols = bx1 - bx0 + 1u, n = cols * (by1 - by0 + 1u);
+  uint32_t rx = 0u, ry = 0u;
+  for (uint32_t i = 0; i < n; i += ORZ_QUERY_SERIAL_UNROLL) {
+    uint32_t hh[ORZ_QUERY_SERIAL_UNROLL], xs[ORZ_QUERY_SERIAL_UNROLL], ys[ORZ_QUERY_SERIAL_UNROLL];
+#pragma unroll
+    for (int u = 0; u < ORZ_QUERY_SERIAL_UNROLL; ++u) {
+      xs[u] = bx0 + rx; ys[u] = by0 + ry;
+      hh[u] = i + (uint32_t)u < n ? (uint32_t)T.hiz[ys[u] * T.blocksX + xs[u]] : 0xffffu;  // maxZ <= 0xffff: never passes
+      if (++rx == cols) { rx = 0u; ++ry; }
     }
+#pragma unroll
+    for (int u = 0; u < ORZ_QUERY_SERIAL_UNROLL; ++u)
+      if (query_block_loaded(T, xs[u], ys[u], hh[u], minX, maxX, minY, maxY, maxZ)) return true;
   }
 #else
   for (uint32_t by = by0; by <= by1; ++by)

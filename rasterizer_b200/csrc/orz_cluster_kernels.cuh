@@ -107,11 +107,13 @@ struct ClusterSmem {
 };
 
 // ---- speculative setup of every occluder that survives the frustum, Rasterizer.cpp:657-1086
-#ifndef ORZ_SETUP_CTAS
-#define ORZ_SETUP_CTAS 4
-#endif
-__global__ void __launch_bounds__(256, ORZ_SETUP_CTAS) k_setup_views(const FrameParams p) {
-  __shared__ uint32_t s_cnt[8];
+// CTA size: 256 threads when the launch is small (one or a few views: the setup sits on the view's critical path and an
+// occluder's ~335 quads should be set up in two rounds), ONE WARP per CTA for the batches (no block barrier at all, 32
+// resident CTAs per SM; 64 / 96 / 128 / 256 / 512 measured: profiles/r2ap-r2ar_*)
+template <uint32_t kSetupThreads, int kCtasPerSM>
+__global__ void __launch_bounds__(kSetupThreads, kCtasPerSM) k_setup_views(const FrameParams p) {
+  constexpr uint32_t kSetupWarps = kSetupThreads / 32u;
+  __shared__ uint32_t s_cnt[kSetupWarps];
   __shared__ uint32_t s_box[4];
   // grid: (order slot, rank of the view in this launch's group of the cost-sorted batch)
   const uint32_t slot = blockIdx.x, vrank = p.viewBase + blockIdx.y, tid = threadIdx.x;
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(256, ORZ_SETUP_CTAS) k_setup_views(const Frame
   if (tid < 4) s_box[tid] = tid < 2 ? 0xffffffffu : 0u;
   uint32_t written = 0;
   uint32_t bx0 = 0xffffffffu, by0 = 0xffffffffu, bx1 = 0u, by1 = 0u;
-  for (uint32_t q0 = 0; q0 < om.quadCount; q0 += 256u) {
+  for (uint32_t q0 = 0; q0 < om.quadCount; q0 += kSetupThreads) {
     const uint32_t qi = q0 + tid;
     bool ok = false;
     Prim P;
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(256, ORZ_SETUP_CTAS) k_setup_views(const Frame
     __syncthreads();
     uint32_t base = written, total = 0;
 #pragma unroll
-    for (int w2 = 0; w2 < 8; ++w2) { const uint32_t c = s_cnt[w2]; base += w2 < warp ? c : 0u; total += c; }
+    for (int w2 = 0; w2 < (int)kSetupWarps; ++w2) { const uint32_t c = s_cnt[w2]; base += w2 < warp ? c : 0u; total += c; }
     for (uint32_t k = 0; k < nPieces; ++k) {  // binning by prefix-sum compaction
       const uint32_t at = base + incl - nPieces + k;
       uint32_t* rec = recs + (size_t)at * kRecStride;

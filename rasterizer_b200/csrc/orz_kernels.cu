@@ -42,6 +42,9 @@
 #ifndef ORZ_SPIN_NAP
 #define ORZ_SPIN_NAP 32  // ns a warp sleeps between two looks at a gate decision (0 = pure spin)
 #endif
+#ifndef ORZ_SETUP_SMALL_CTAS
+#define ORZ_SETUP_SMALL_CTAS 2048  // launches of at least this many (occluder, view) pairs set up with one-warp CTAs
+#endif
 #ifndef ORZ_GROUPS
 #define ORZ_GROUPS 4  // sub-batches of a large batch, each on its own stream (2 / 6 / 8 measured: profiles/r2am_*)
 #endif
@@ -959,6 +962,12 @@ static int launch_cluster(orz_context* ctx, const FrameParams& p, uint32_t nView
   return sh.tileH == 1u ? launch_cluster_c<1>(ctx, p, sh.c, nViews, st) : launch_cluster_c<kTileH>(ctx, p, sh.c, nViews, st);
 }
 
+// speculative setup of every (occluder in the frustum, view) of a launch: one CTA each
+static void launch_setup(const FrameParams& p, uint32_t nViews, cudaStream_t st) {
+  if ((size_t)p.nOcc * nViews >= (size_t)ORZ_SETUP_SMALL_CTAS) k_setup_views<32, 32><<<dim3(p.nOcc, nViews), 32, 0, st>>>(p);
+  else k_setup_views<256, 4><<<dim3(p.nOcc, nViews), 256, 0, st>>>(p);
+}
+
 // Error paths between the fork of the auxiliary streams and their join must not leave work running on them that later
 // calls (which reuse or free the scratch buffers) know nothing about: the guard drains them unless the join was reached.
 namespace {
@@ -1145,7 +1154,7 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
         pv.occBox = (uint2*)((uint8_t*)pv.recInfo + infoBytes);
         pv.recBuf = (uint32_t*)((uint8_t*)pv.occBox + boxBytes);
         pv.totalQuads = (uint32_t)recSlots;
-        k_setup_views<<<dim3(pv.nOcc, 1), 256, 0, ctx->stream>>>(pv);
+        launch_setup(pv, 1u, ctx->stream);
         k_raster_tiles<<<grid, kClusterGW * 32, smem, ctx->stream>>>(pv, 0u, scene->totalQuads);
         ctx->launches += 2;
         ORZ_CUDA(cudaGetLastError());
@@ -1194,7 +1203,7 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
         pg.viewBase = groupsC > 1 ? (uint32_t)((uint64_t)nv * ctx->groupCut[g] / 1000u) : 0u;
         pg.groupViews = (groupsC > 1 ? (uint32_t)((uint64_t)nv * ctx->groupCut[g + 1] / 1000u) : nv) - pg.viewBase;
         if (pg.groupViews == 0u) continue;
-        k_setup_views<<<dim3(pg.nOcc, pg.groupViews), 256, 0, st>>>(pg);
+        launch_setup(pg, pg.groupViews, st);
         ctx->launches++;
         ORZ_CUDA(cudaGetLastError());
         if ((e = launch_cluster(ctx, pg, pg.groupViews, nv, st))) return e;

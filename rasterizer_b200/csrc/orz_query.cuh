@@ -189,7 +189,10 @@ __device__ __forceinline__ void query2d_coop(const Target& T, uint32_t minX, uin
 #define ORZ_QUERY_THREADS 128  // 64 / 96 / 128 / 256 / 512 measured (profiles/r2aj_*, r2ak_*)
 #endif
 constexpr uint32_t kQueryThreads = ORZ_QUERY_THREADS;  // boxes per CTA of k_query_views
-__global__ void __launch_bounds__(kQueryThreads) k_query_views(const FrameParams p) {
+#ifndef ORZ_QUERY_CTAS
+#define ORZ_QUERY_CTAS 10  // resident CTAs per SM the query kernel is compiled for (48 registers; 9 / 10 / 12 / 16 measured: profiles/r2as_*)
+#endif
+__global__ void __launch_bounds__(kQueryThreads, ORZ_QUERY_CTAS) k_query_views(const FrameParams p) {
   __shared__ ViewMatrices s_vm;
   // 1-D grid, view major (grid.y would cap a batch at 65 535 views): CTA = (rank of the view in this launch, chunk of 256 boxes)
   const uint32_t vrank = blockIdx.x / p.queryChunks, chunk = blockIdx.x - vrank * p.queryChunks;

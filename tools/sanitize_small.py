@@ -24,10 +24,24 @@ ctx.set_cluster_size(0)
 sd = api.Scene.bake_on_device(ctx, ps.batches, ps.ref_min, ps.ref_max)   # device bake
 sd.close()
 out = sc.render_views(w, h, mvps[:2], cam_pos=poss[:2], flags=api.BATCH_NO_GATE | api.BATCH_FORCE_CLIPPED | api.BATCH_WIDE, want=("vis", "depth", "hiz"))
+ctx.set_cluster_views(api.DEFAULT_CLUSTER_VIEWS)
+ctx.set_tile_height(1, 1)     # 8 x 1 strips on the cluster path
+out3 = sc.render_views(w, h, mvps, cam_pos=poss, want=("vis", "clip", "gate", "depth", "hiz", "quads"))
+assert all(np.array_equal(out2[k], out3[k]) for k in out2)
+ctx.set_tile_height(0, 1)
+out = sc.render_views(w, h, mvps[:2], cam_pos=poss[:2], flags=api.BATCH_NO_GATE | api.BATCH_FORCE_CLIPPED, want=("vis", "depth", "hiz"))
+# per-call path: the frame loop twice (the second frame runs on predicted query chains), both tile heights
 r = api.Rasterizer(ctx, w, h)
-occs = [api.Occluder(ctx, p, ps.ref_min, ps.ref_max) for p in sc.packed_list[:6]]
-r.clear(); r.setModelViewProjection(mvps[0])
-for o in occs:
-    r.rasterize(o, False); r.rasterize(o, True)
-r.queryVisibility(sc.bounds_min[0], sc.bounds_max[0]); r.query_boxes(ps.quad_boxes()[:500]); r.readBackDepth(); r.download()
+n_occ = min(12, len(sc.packed_list))
+occs = [api.Occluder(ctx, p, ps.ref_min, ps.ref_max) for p in sc.packed_list[:n_occ]]
+for tile_h in (1, 4):
+    ctx.set_tile_height(0, tile_h)
+    for frame in range(2):
+        r.clear(); r.setModelViewProjection(mvps[frame % len(mvps)])
+        for i, o in enumerate(occs):
+            vis, clip = r.queryVisibility(sc.bounds_min[i], sc.bounds_max[i])
+            if vis:
+                r.rasterize(o, clip)
+ctx.set_tile_height(0, 1)
+r.query_boxes(ps.quad_boxes()[:500]); r.readBackDepth(); r.download()
 print("sanitize workload done", int(out["hiz"].sum()))

@@ -475,6 +475,7 @@ extern "C" int orz_rasterizer_query2d(orz_rasterizer* r, uint32_t minX, uint32_t
     if (memcmp(r->pending[i].rect, rect, sizeof rect) != 0) continue;
     const orz_rasterizer::Pending pe = r->pending[i];
     r->pending.erase(r->pending.begin() + (long)i);
+    if (ctx->mailSeq - (pe.tag >> 2) >= orz_context::kMailSlots) break;  // its mailbox word has been handed out again (other rasterizers of this context): ask now
     uint32_t answer = 0;
     if (int e = mail_wait(ctx, pe.slot, pe.tag, &answer)) return e;
     if (answer & 2u) break;  // the chain stopped before it got here: ask now

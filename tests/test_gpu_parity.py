@@ -193,6 +193,38 @@ def test_per_call_api_frames_with_predicted_chains(ctx, lut, name, size, tile_h)
     r.close(); port.close()
 
 
+def test_per_call_two_rasterizers_interleaved(ctx, lut):
+    """Two Rasterizer objects of one context (one stream, one mailbox) driven in lock step, three frames each: their
+    predicted chains, tags and mailbox words must not get into each other's way."""
+    B = bundle("castle")
+    sizes = [(1920, 1080), (512, 256)]
+    m0, p0 = B.default_view(*sizes[0])
+    m1, p1 = B.default_view(*sizes[1])
+    order = cam.front_to_back_order(B.centers, p0)
+    ports = [po.PortRasterizer(w, h, lut) for w, h in sizes]
+    rs = [api.Rasterizer(ctx, w, h) for w, h in sizes]
+    occs = [api.Occluder(ctx, p, B.ps.ref_min, B.ps.ref_max) for p in B.packed]
+    for f in range(3):
+        for r, port, m in zip(rs, ports, (m0, m1)):
+            r.clear(); port.clear()
+            r.setModelViewProjection(m); port.set_mvp(m)
+        for slot, o in enumerate(order):
+            for k, (r, port) in enumerate(zip(rs, ports)):
+                g = port.query(B.bmin[o], B.bmax[o])
+                vis, clip = r.queryVisibility(B.bmin[o], B.bmax[o])
+                assert (int(vis) | (int(clip) << 1)) == g, (f, slot, o, k)
+                if vis:
+                    r.rasterize(occs[o], clip)
+                    port.rasterize(B.packed[o], B.ps.ref_min, B.ps.ref_max, clip)
+        for r, port in zip(rs, ports):
+            d, hz = r.download()
+            assert np.array_equal(hz, port.hiz()) and np.array_equal(d, port.depth()), f
+    for o in occs:
+        o.close()
+    for r, port in zip(rs, ports):
+        r.close(); port.close()
+
+
 @pytest.mark.parametrize("trav", [1, 2])
 @pytest.mark.parametrize("gw", [1, 2, 4, 8])
 @pytest.mark.parametrize("name,size,nviews", [("city", (640, 360), 6), ("castle", (1920, 1080), 5), ("castle", (512, 256), 12)])

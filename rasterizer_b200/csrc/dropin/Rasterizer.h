@@ -1,8 +1,11 @@
 // Drop-in replacement for the reference's SoftwareRasterizer/Rasterizer.h (Rasterizer.h:10-61):
 // same class name and public signatures; every method forwards to the C ABI in include/orz.h,
 // which runs the CUDA kernels.  Per-call semantics as the reference: setModelViewProjection /
-// clear / rasterize are asynchronous on the context's stream, queryVisibility / query2D /
-// readBackDepth synchronise because they return data to the host.
+// clear / rasterize are asynchronous on the context's stream; queryVisibility / query2D return data
+// to the host: boxes the frustum culls or the near plane clips are answered on the host, a rectangle
+// test either finds its answer in the mapped mailbox (asked for by an earlier launch that predicted
+// this query from the previous frame's sequence) or is launched and waited for;
+// readBackDepth synchronises.
 //
 // Differences a caller can observe (both documented in DESIGN.md):
 //   * clear() also zeroes the depth buffer ("fresh" state): the reference leaves stale depth

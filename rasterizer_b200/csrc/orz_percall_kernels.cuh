@@ -50,6 +50,9 @@ __global__ void __launch_bounds__(GW * 32) k_rasterize_single(const ViewMatrices
 //     previous frame's sequence of queries, see orz_rasterizer in orz_kernels.cu) -- in order, until the first visible
 //     one (the application will rasterise then, so later answers would be stale).  Queries are read only, so a wrong
 //     prediction costs nothing but the unused answer.
+#ifndef ORZ_CALL_LUT_SMEM
+#define ORZ_CALL_LUT_SMEM 1  // k_rasterize_call: edge-mask table staged in shared memory (0: read through L1)
+#endif
 constexpr uint32_t kChainMax = 12;   // predicted queries a launch carries
 constexpr uint32_t kCallQuadsMax = 512;
 struct QueryChain {
@@ -136,12 +139,14 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_rasterize_call(const CallMatrix 
   uint16_t* s_hiz = reinterpret_cast<uint16_t*>(s_recs + kCallQuadsMax * kRecStride);  // [GW][K][32]
   const uint32_t tid = threadIdx.x;
   const int warp = (int)(tid >> 5), lane = (int)(tid & 31u);
-#if ORZ_LUT_BULK && ORZ_CLUSTER_LUT_SMEM
+#if ORZ_LUT_BULK && ORZ_CLUSTER_LUT_SMEM && ORZ_CALL_LUT_SMEM
   __shared__ __align__(8) uint64_t s_lutBar;
   if (tid == 0) mbar_init(&s_lutBar, 1u);
   if (tid < 4) s_box[tid] = tid < 2 ? 0xffffffffu : 0u;
   __syncthreads();
   if (tid == 0) bulk_load(s_lut, lutGlobal, 4096u * 8u, &s_lutBar);
+#elif !ORZ_CALL_LUT_SMEM
+  if (tid < 4) s_box[tid] = tid < 2 ? 0xffffffffu : 0u;
 #else
   if (tid < 4) s_box[tid] = tid < 2 ? 0xffffffffu : 0u;
   if (ORZ_CLUSTER_LUT_SMEM) for (uint32_t i = tid; i < 4096u; i += GW * 32u) s_lut[i] = lutGlobal[i];
@@ -156,7 +161,7 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_rasterize_call(const CallMatrix 
   tw.myStage = s_recs; tw.myIdx = nullptr;
   tw.myTile = reinterpret_cast<uint4*>(s_tileAll + (uint32_t)warp * kTileWords);
   tw.myAux = s_tileAll + (uint32_t)GW * kTileWords + (uint32_t)warp * kTileAuxWords;
-  tw.lut = ORZ_CLUSTER_LUT_SMEM ? s_lut : lutGlobal;
+  tw.lut = (ORZ_CLUSTER_LUT_SMEM && ORZ_CALL_LUT_SMEM) ? s_lut : lutGlobal;
   tw.own_tiles(blockIdx.x * GW + (uint32_t)warp, gridDim.x * GW, K);
   // the buffers continue where the previous calls left them: HiZ of my tiles as L2 holds it
   for (uint32_t m = tw.allTiles; m; m &= m - 1u) {
@@ -190,7 +195,7 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_rasterize_call(const CallMatrix 
   bx0 = __reduce_min_sync(kFull, bx0); by0 = __reduce_min_sync(kFull, by0);
   bx1 = __reduce_max_sync(kFull, bx1); by1 = __reduce_max_sync(kFull, by1);
   if (lane == 0 && okMask) { atomicMin(&s_box[0], bx0); atomicMin(&s_box[1], by0); atomicMax(&s_box[2], bx1); atomicMax(&s_box[3], by1); }
-#if ORZ_LUT_BULK && ORZ_CLUSTER_LUT_SMEM
+#if ORZ_LUT_BULK && ORZ_CLUSTER_LUT_SMEM && ORZ_CALL_LUT_SMEM
   mbar_wait(&s_lutBar, 0u);
 #endif
   __syncthreads();

@@ -68,6 +68,9 @@
 #ifndef ORZ_ASYNC_GATHER
 #define ORZ_ASYNC_GATHER 1  // 1: staged records are gathered with cp.async (no registers, no scoreboard wait): the L2 round trip overlaps the tile test and the first tile's open
 #endif
+#ifndef ORZ_TILE_MAP
+XX
+#endif
 #ifndef ORZ_TILE_PREFETCH
 #define ORZ_TILE_PREFETCH 1  // flush: prefetch the next tile's depth blocks into L1 while the current tile is processed
 #endif
@@ -100,9 +103,10 @@ struct ClusterSmem {
   static constexpr uint32_t kIdxWords = kClusterGW * kStageCap;
   static constexpr uint32_t kChainWords = kClusterGW * 12 * kChainStride;
   static constexpr uint32_t kFixedWords = kLutWords + kTileAllWords + kStageWords + kIdxWords + kChainWords;
-  // + [nOcc][6] gate heads, 3 x [nOcc] decision words, [GW][K][32] u16 HiZ mirror
-  static size_t bytes(uint32_t tilesPerWarp, uint32_t nOcc) {
-    return (size_t)(kFixedWords + nOcc * (kHeadWords + 3u)) * 4 + (size_t)kClusterGW * tilesPerWarp * 32 * 2;
+  // + [nOcc][6] gate heads, 3 x [nOcc] decision words, [GW][K][32] u16 HiZ mirror, [GW][ceil(nTiles / 32)] tile-ownership bitmaps
+  static size_t bytes(uint32_t tilesPerWarp, uint32_t nOcc, uint32_t nTiles) {
+    return (size_t)(kFixedWords + nOcc * (kHeadWords + 3u)) * 4 + (size_t)kClusterGW * tilesPerWarp * 32 * 2 +
+           (ORZ_TILE_MAP ? (size_t)kClusterGW * ((nTiles + 31u) / 32u) * 4 : 0);
   }
 };
 
@@ -561,6 +565,8 @@ struct TileWalkerT {    // the tiles -- finer ownership and shorter per-tile cha
   uint4* myTile;
   uint32_t* myAux;
   const uint2* lut;
+  uint32_t* myMap;          // bit t set: tile t is mine (or NULL: no bitmap)
+  uint32_t tilesX;
 
   // tile t belongs to warp t mod nWarps of the group that shares the view
   __device__ __forceinline__ void own_tiles(uint32_t gw, uint32_t nWarps, uint32_t K) {
@@ -571,6 +577,28 @@ struct TileWalkerT {    // the tiles -- finer ownership and shorter per-tile cha
       if (t < nTiles) { const uint32_t ty = t / tilesX; tileX0 = (t - ty * tilesX) * kTileW; tileY0 = ty * TH; }
     }
     allTiles = __ballot_sync(kFull, tileX0 != 0xffffu);
+    this->tilesX = tilesX;
+    if (myMap) {
+      for (uint32_t i = (uint32_t)lane; i < (nTiles + 31u) / 32u; i += 32u) myMap[i] = 0u;
+      __syncwarp();
+      if (tileX0 != 0xffffu) { const uint32_t t = gw + (uint32_t)lane * nWarps; atomicOr(&myMap[t >> 5], 1u << (t & 31u)); }
+      __syncwarp();
+    }
+  }
+  // does one of my tiles lie in the tile rectangle of the block rectangle [hx0, hx1) x [hy0, hy1)?  (per lane: its own rectangle)
+  __device__ __forceinline__ bool owns_tile_in(uint32_t hx0, uint32_t hx1, uint32_t hy0, uint32_t hy1) const {
+    if (hx1 <= hx0 || hy1 <= hy0) return false;
+    const uint32_t tx0 = hx0 >> 3, tx1 = min((hx1 - 1u) >> 3, tilesX - 1u), ty0 = hy0 / TH, ty1 = (hy1 - 1u) / TH;
+    for (uint32_t ty = ty0; ty <= ty1; ++ty) {
+      const uint32_t lo = ty * tilesX + tx0, hi = ty * tilesX + tx1;  // inclusive bit range of this tile row
+      for (uint32_t w = lo >> 5; w <= (hi >> 5); ++w) {
+        uint32_t bits = myMap[w];
+        if (w == (lo >> 5)) bits &= 0xffffffffu << (lo & 31u);
+        if (w == (hi >> 5)) bits &= 0xffffffffu >> (31u - (hi & 31u));
+        if (bits) return true;
+      }
+    }
+    return false;
   }
   // clear (Rasterizer.cpp:107-121): HiZ := 1 on my tiles; depth is overwritten by the first update
   __device__ __forceinline__ void clear_tiles() {
@@ -710,10 +738,14 @@ struct TileWalkerT {    // the tiles -- finer ownership and shorter per-tile cha
         hx0 = hdr.x & 0xffffu; hy0 = hdr.x >> 16; hx1 = hx0 + (hdr.y & 0xffffu); hy1 = hy0 + (hdr.y >> 16);
       }
       bool touches = false;
-      for (uint32_t m = tmOcc; m; m &= m - 1u) {
-        const int k = __ffs((int)m) - 1;
-        const uint32_t x0 = __shfl_sync(kFull, tileX0, k), y0 = __shfl_sync(kFull, tileY0, k);
-        touches = touches || (hx0 < x0 + kTileW && hx1 > x0 && hy0 < y0 + TH && hy1 > y0);
+      if (ORZ_TILE_MAP && myMap) {
+        touches = owns_tile_in(hx0, hx1, hy0, hy1);
+      } else {
+        for (uint32_t m = tmOcc; m; m &= m - 1u) {
+          const int k = __ffs((int)m) - 1;
+          const uint32_t x0 = __shfl_sync(kFull, tileX0, k), y0 = __shfl_sync(kFull, tileY0, k);
+          touches = touches || (hx0 < x0 + kTileW && hx1 > x0 && hy0 < y0 + TH && hy1 > y0);
+        }
       }
       uint32_t hits = __ballot_sync(kFull, touches);
       while (hits) {
@@ -790,6 +822,10 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
   tw.T = T; tw.lane = lane; tw.lx = lx; tw.ly = ly;
   tw.myHiz = myHiz; tw.myChain = myChain; tw.myStage = myStage; tw.myIdx = myIdx; tw.myTile = myTile; tw.myAux = myAux;
   tw.lut = ORZ_CLUSTER_LUT_SMEM ? s_lut : p.lut;
+  {
+    const uint32_t nTilesAll = ((T.blocksX + kTileW - 1u) / kTileW) * ((T.blocksY + TH - 1u) / TH);
+    tw.myMap = ORZ_TILE_MAP ? reinterpret_cast<uint32_t*>(s_hiz + (size_t)GW * K * 32u) + (uint32_t)warp * ((nTilesAll + 31u) / 32u) : nullptr;
+  }
   tw.own_tiles(gw, kWarps, K);
   tw.clear_tiles();
   const uint32_t tileX0 = tw.tileX0, tileY0 = tw.tileY0;
@@ -941,6 +977,7 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_tiles(const FrameParams p
   tw.myTile = reinterpret_cast<uint4*>(s_tileAll + (uint32_t)warp * kTileWords);
   tw.myAux = s_tileAll + (uint32_t)GW * kTileWords + (uint32_t)warp * kTileAuxWords;
   tw.lut = ORZ_CLUSTER_LUT_SMEM ? s_lut : p.lut;
+  tw.myMap = nullptr;
   // consecutive tiles go to the warps of one CTA, then to the next CTA: a CTA's tiles are short horizontal runs all over the screen
   tw.own_tiles(blockIdx.x * GW + (uint32_t)warp, gridDim.x * GW, K);
   tw.clear_tiles();

@@ -891,7 +891,7 @@ template <int C, uint32_t TH>
 static int launch_cluster_t(orz_context* ctx, FrameParams p, uint32_t nViews, cudaStream_t st) {
   const uint32_t nTiles = tiles_of(p.width, p.height, TH);
   p.clusterK = (nTiles + (uint32_t)(C * kClusterGW) - 1u) / (uint32_t)(C * kClusterGW);
-  const size_t smem = ClusterSmem::bytes(p.clusterK, p.nOcc);
+  const size_t smem = ClusterSmem::bytes(p.clusterK, p.nOcc, nTiles);
   constexpr int kLog = (C == 1 ? 0 : C == 2 ? 1 : C == 4 ? 2 : C == 8 ? 3 : 4) + (TH == 1 ? 5 : 0);
   if (ctx->smemCluster[kLog] < smem) {
     ORZ_CUDA(cudaFuncSetAttribute(k_raster_views_cluster<C, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -922,7 +922,7 @@ static int launch_cluster_t(orz_context* ctx, FrameParams p, uint32_t nViews, cu
 struct ClusterShape { uint32_t c, tileH; };
 static ClusterShape pick_cluster_shape(const orz_context* ctx, uint32_t width, uint32_t height, uint32_t nOcc, uint32_t nBatch) {
   auto tilesPerWarp = [&](uint32_t c, uint32_t th) { return (tiles_of(width, height, th) + c * kClusterGW - 1u) / (c * kClusterGW); };
-  auto fits = [&](uint32_t c, uint32_t th) { return tilesPerWarp(c, th) <= 32u && ClusterSmem::bytes(tilesPerWarp(c, th), nOcc) <= ctx->maxSmemOptin; };
+  auto fits = [&](uint32_t c, uint32_t th) { return tilesPerWarp(c, th) <= 32u && ClusterSmem::bytes(tilesPerWarp(c, th), nOcc, tiles_of(width, height, th)) <= ctx->maxSmemOptin; };
   const uint32_t nTiles = tiles_of(width, height, kTileH);
   uint32_t c = 1;
   while (c < 16u && c * kClusterGW < nTiles && nBatch * c * 2u <= (uint32_t)ctx->numSMs) c *= 2u;
@@ -950,7 +950,7 @@ static int launch_cluster_c(orz_context* ctx, const FrameParams& p, uint32_t c, 
     case 16:  // non-portable cluster size: when the device (e.g. a partitioned one) cannot place it, use 8
       if (launch_cluster_t<16, TH>(ctx, p, nViews, st) == ORZ_OK) return ORZ_OK;
       (void)cudaGetLastError();
-      if ((nTiles + 8u * kClusterGW - 1u) / (8u * kClusterGW) > 32u || ClusterSmem::bytes((nTiles + 8u * kClusterGW - 1u) / (8u * kClusterGW), p.nOcc) > ctx->maxSmemOptin)
+      if ((nTiles + 8u * kClusterGW - 1u) / (8u * kClusterGW) > 32u || ClusterSmem::bytes((nTiles + 8u * kClusterGW - 1u) / (8u * kClusterGW), p.nOcc, nTiles) > ctx->maxSmemOptin)
         return fail(ORZ_ERR_CUDA, "cluster path: 16-CTA clusters are not available on this device");
       return launch_cluster_t<8, TH>(ctx, p, nViews, st);
     case 8: return launch_cluster_t<8, TH>(ctx, p, nViews, st);

@@ -162,6 +162,7 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_rasterize_call(const CallMatrix 
   tw.myTile = reinterpret_cast<uint4*>(s_tileAll + (uint32_t)warp * kTileWords);
   tw.myAux = s_tileAll + (uint32_t)GW * kTileWords + (uint32_t)warp * kTileAuxWords;
   tw.lut = (ORZ_CLUSTER_LUT_SMEM && ORZ_CALL_LUT_SMEM) ? s_lut : lutGlobal;
+  tw.myMap = nullptr;
   tw.own_tiles(blockIdx.x * GW + (uint32_t)warp, gridDim.x * GW, K);
   // the buffers continue where the previous calls left them: HiZ of my tiles as L2 holds it
   for (uint32_t m = tw.allTiles; m; m &= m - 1u) {

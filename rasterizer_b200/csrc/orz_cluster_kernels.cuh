@@ -69,7 +69,7 @@
 #define ORZ_ASYNC_GATHER 1  // 1: staged records are gathered with cp.async (no registers, no scoreboard wait): the L2 round trip overlaps the tile test and the first tile's open
 #endif
 #ifndef ORZ_TILE_MAP
-XX
+#define ORZ_TILE_MAP 0  // 1: the header scan looks a record's tile rectangle up in a per-warp bitmap of owned tiles instead of testing every owned tile of the occluder (measured: batches equal, one view 11 % slower -- few tiles per warp there: profiles/r2av_*)
 #endif
 #ifndef ORZ_TILE_PREFETCH
 #define ORZ_TILE_PREFETCH 1  // flush: prefetch the next tile's depth blocks into L1 while the current tile is processed

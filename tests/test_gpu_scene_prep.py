@@ -100,7 +100,7 @@ def test_scene_from_mesh_in_one_call(ctx):
         assert np.array_equal(got.quads_per_occluder, [b.shape[0] // 4 for b in host.batches])
         pos = np.asarray(c["pos"], np.float32)
         mvp = cam.view_projection(pos, np.asarray(c["dir"], np.float32), np.asarray(c["up"], np.float32), c["fov"], w, h)
-        outs = [s.render_views(w, h, mvp[None], cam_pos=pos[None], want=("vis", "gate", "hiz", "quads")) for s in (got, want)]
+        outs = [s.render_views(w, h, mvp[None], cam_pos=pos[None], want=("vis", "gate", "hiz", "depth", "quads")) for s in (got, want)]
         for key in ("vis", "gate", "hiz", "depth", "quads"):
             assert np.array_equal(outs[0][key], outs[1][key]), (name, key)
         assert outs[0]["quads"][0] > 0

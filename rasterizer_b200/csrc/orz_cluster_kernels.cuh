@@ -68,6 +68,12 @@
 #ifndef ORZ_ASYNC_GATHER
 #define ORZ_ASYNC_GATHER 1  // 1: staged records are gathered with cp.async (no registers, no scoreboard wait): the L2 round trip overlaps the tile test and the first tile's open
 #endif
+#ifndef ORZ_LOOKAHEAD
+#define ORZ_LOOKAHEAD 0  // candidates further down the order a warp tries to answer "no" early after it has rasterised an occluder (0: off; exact -- every parity suite passes with 8 -- but measured: Sponza 256 views 2-3 % faster, Castle equal, probes 8 % and single views 3 % slower: profiles/r2ay_*)
+#endif
+#ifndef ORZ_LOOKAHEAD_WAITING
+#define ORZ_LOOKAHEAD_WAITING 1  // ... and before it starts waiting for a decision
+#endif
 #ifndef ORZ_TILE_MAP
 #define ORZ_TILE_MAP 0  // 1: the header scan looks a record's tile rectangle up in a per-warp bitmap of owned tiles instead of testing every owned tile of the occluder (measured: batches equal, one view 11 % slower -- few tiles per warp there: profiles/r2av_*)
 #endif
@@ -843,11 +849,41 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
   };
   auto tiles_meeting = [&](uint32_t bx0, uint32_t bx1, uint32_t by0, uint32_t by1) -> uint32_t { return tw.tiles_meeting(bx0, bx1, by0, by1); };
 
+  // Which candidates this warp has answered "no" already: bit (s & 31) of lane (s >> 5) -- 1 024 order slots; scenes with more
+  // occluders run without the early answers below.
+  uint32_t answeredBits = 0u;
+  const bool lookahead = ORZ_LOOKAHEAD > 0 && nOcc <= 1024u;
+  auto is_answered = [&](uint32_t s) -> bool { return lookahead && ((__shfl_sync(kFull, answeredBits, (int)(s >> 5)) >> (s & 31u)) & 1u); };
+  auto mark_answered = [&](uint32_t s) { if ((uint32_t)lane == (s >> 5)) answeredBits |= 1u << (s & 31u); };
+  // EARLY "no".  Depth only grows while a view is drawn (max-merge), so a block's HiZ -- the smallest depth in it -- only
+  // grows too, and query2D lets a block pass only when maxZ > HiZ (Rasterizer.cpp:310).  If NOW, for a candidate further down
+  // the order, no block of its rectangle on my tiles has maxZ > HiZ (and none is still cleared: HiZ 1 reads as depth 0), then
+  // the exact test this warp would make when its walk gets there -- after even more occluders -- fails at that first
+  // comparison in every block: the answer can be given today.  A warp that is busy rasterising is the one the others wait
+  // for at every candidate it touches; with the early answers they only wait for it where something may really be visible.
+  auto look_ahead = [&](uint32_t s) {
+    if (!lookahead) return;
+    const uint32_t hi = min(nOcc, s + 1u + (uint32_t)ORZ_LOOKAHEAD);
+    for (uint32_t s2 = s + 1u; s2 < hi; ++s2) {
+      const uint32_t* hd2 = s_head + s2 * kHeadWords;
+      if (hd2[0] != kBoxRect || is_answered(s2) || flag_set_warp(s_vis + s2)) continue;
+      const uint32_t bx0 = hd2[1] >> 3, bx1 = hd2[2] >> 3, by0 = hd2[3] >> 3, by1 = hd2[4] >> 3, maxZ = hd2[5];
+      bool maybe = false;
+      for (uint32_t tm = tiles_meeting(bx0, bx1, by0, by1); tm && !maybe; tm &= tm - 1u) {
+        const uint32_t k = (uint32_t)__ffs((int)tm) - 1u;
+        const uint32_t bx = __shfl_sync(kFull, tileX0, (int)k) + lx, by = __shfl_sync(kFull, tileY0, (int)k) + ly;
+        const uint32_t h = (uint32_t)myHiz[32u * k];
+        maybe = __any_sync(kFull, ly < TH && bx >= bx0 && bx <= bx1 && by >= by0 && by <= by1 && bx < T.blocksX && by < T.blocksY && (h == 1u || maxZ > h));
+      }
+      if (!maybe) { answer_no(s2); mark_answered(s2); }
+    }
+  };
+
   // ---- candidates whose rectangle does not touch my tiles: answered before the walk starts
   for (uint32_t s = 0; s < nOcc; ++s) {
     const uint32_t* hd = s_head + s * kHeadWords;
     if (hd[0] != kBoxRect) continue;
-    if (!tiles_meeting(hd[1] >> 3, hd[2] >> 3, hd[3] >> 3, hd[4] >> 3)) answer_no(s);
+    if (!tiles_meeting(hd[1] >> 3, hd[2] >> 3, hd[3] >> 3, hd[4] >> 3)) { answer_no(s); if (lookahead) mark_answered(s); }
   }
 
   uint4 infoNext = recInfo[0], boxNext = recInfo[1];  // {records, first slot, quads}, {block rectangle}: fetched one slot ahead of the walk
@@ -873,7 +909,7 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
       const uint32_t bx0 = minX >> 3, bx1 = maxX >> 3, by0 = minY >> 3, by1 = maxY >> 3;
       const uint32_t* vis = s_vis + s;
       uint32_t tm = tiles_meeting(bx0, bx1, by0, by1);
-      if (tm && !flag_set_warp(vis)) {
+      if (tm && !is_answered(s) && !flag_set_warp(vis)) {
         bool found = false;
         for (; tm; tm &= tm - 1u) {
           const uint32_t k = (uint32_t)__ffs((int)tm) - 1u;
@@ -892,6 +928,7 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
       if (!tmOcc) continue;
       // visible as soon as ONE warp says so, invisible when all 16 C warps have said no
       const uint32_t* done = s_doneCta + s;
+      if (ORZ_LOOKAHEAD_WAITING && !flag_set_warp(vis) && !flag_reached_warp(done, (uint32_t)C)) look_ahead(s);  // (idle anyway)
       for (;;) {
         if (flag_set_warp(vis)) break;
         if (flag_reached_warp(done, (uint32_t)C)) { visible = flag_set_warp(vis); break; }
@@ -910,6 +947,7 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
 #endif
 
     tw.rasterize(recs, hdrs, cnt, tmOcc);
+    look_ahead(s);  // my tiles have just become more opaque: which of the next candidates are certainly hidden on them now?
   }
   if (p.coarseHiz) {  // the view is final on my tiles: their smallest HiZ, for the occludee queries' coarse look (orz_query.cuh)
     uint16_t* coarse = p.coarseHiz + (size_t)view * p.coarseStride;

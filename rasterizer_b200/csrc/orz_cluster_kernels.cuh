@@ -74,6 +74,9 @@
 #ifndef ORZ_LOOKAHEAD_WAITING
 #define ORZ_LOOKAHEAD_WAITING 1  // ... and before it starts waiting for a decision
 #endif
+#ifndef ORZ_WAIT_STATS
+#define ORZ_WAIT_STATS 0
+#endif
 #ifndef ORZ_TILE_MAP
 #define ORZ_TILE_MAP 0  // 1: the header scan looks a record's tile rectangle up in a per-warp bitmap of owned tiles instead of testing every owned tile of the occluder (measured: batches equal, one view 11 % slower -- few tiles per warp there: profiles/r2av_*)
 #endif
@@ -244,6 +247,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(b), "r"(parity) : "memory");
 }
 
+#if ORZ_WAIT_STATS  // (measurement builds only: make variant NAME=waitstats DEFS=-DORZ_WAIT_STATS=1, tools/wait_stats.py)
+__device__ unsigned long long g_waitStats[8];  // waits entered, ended visible, ended invisible, decided on arrival, spin iterations (visible), (invisible), clocks waited (visible), (invisible)
+#endif
 // Decision words of the cluster kernel are read and written concurrently by design (monotonic
 // flags / counters): strong relaxed accesses at cluster scope, which the PTX memory model allows
 // to race (no data is published through them, only the decision itself).  compute-sanitizer's
@@ -929,13 +935,29 @@ __global__ void __maxnreg__(ORZ_CLUSTER_REGS) k_raster_views_cluster(const Frame
       // visible as soon as ONE warp says so, invisible when all 16 C warps have said no
       const uint32_t* done = s_doneCta + s;
       if (ORZ_LOOKAHEAD_WAITING && !flag_set_warp(vis) && !flag_reached_warp(done, (uint32_t)C)) look_ahead(s);  // (idle anyway)
+#if ORZ_WAIT_STATS
+      const long long t0w = clock64();
+      unsigned long long spins = 0;
+#endif
       for (;;) {
         if (flag_set_warp(vis)) break;
         if (flag_reached_warp(done, (uint32_t)C)) { visible = flag_set_warp(vis); break; }
+#if ORZ_WAIT_STATS
+        ++spins;
+#endif
 #if ORZ_SPIN_NAP
         __nanosleep(ORZ_SPIN_NAP);  // (a longer or growing nap was measured slower: the wake-up delay sits on the dependency chain)
 #endif
       }
+#if ORZ_WAIT_STATS
+      if (lane == 0) {
+        atomicAdd(&g_waitStats[0], 1ull);
+        atomicAdd(&g_waitStats[visible ? 1 : 2], 1ull);
+        if (!spins) atomicAdd(&g_waitStats[3], 1ull);
+        atomicAdd(&g_waitStats[visible ? 4 : 5], spins);
+        atomicAdd(&g_waitStats[visible ? 6 : 7], (unsigned long long)(clock64() - t0w));
+      }
+#endif
     }
     if (!visible || !tmOcc) continue;
 

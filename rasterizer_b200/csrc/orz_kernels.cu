@@ -164,6 +164,15 @@ struct orz_scene {
 };
 
 extern "C" const char* orz_last_error(void) { return g_err.c_str(); }
+#if ORZ_WAIT_STATS
+extern "C" int orz_debug_wait_stats(unsigned long long* out8) {  // measurement builds only: reads and clears the counters
+  unsigned long long zero[8] = {0};
+  ORZ_CUDA(cudaDeviceSynchronize());
+  ORZ_CUDA(cudaMemcpyFromSymbol(out8, orz::g_waitStats, sizeof zero));
+  ORZ_CUDA(cudaMemcpyToSymbol(orz::g_waitStats, zero, sizeof zero));
+  return ORZ_OK;
+}
+#endif
 extern "C" int orz_version(void) { return 100; }
 
 static int ensure_scratch(orz_context* ctx, int idx, size_t bytes) {

@@ -30,7 +30,7 @@ __device__ __forceinline__ void setup_chunk(const uint4* __restrict__ quads, uin
 //                    per occluder in order
 //   k_query_views    one thread per (view, occludee box) on the finished buffers
 
-__global__ void __launch_bounds__(128) k_prepare_views(const FrameParams p) {
+__global__ void __launch_bounds__(512) k_prepare_views(const FrameParams p) {  // 128 threads per view for batches, 512 for a few views (latency)
   __shared__ ViewMatrices s_vm;
   const uint32_t view = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
   const RcpTable rt{p.rcp, p.rcpShift};
@@ -44,15 +44,18 @@ __global__ void __launch_bounds__(128) k_prepare_views(const FrameParams p) {
   if (!order) {
     uint32_t* mine = p.orderBuf + (size_t)view * p.nOcc;
     const float cx = p.camPos[3 * (size_t)view + 0], cy = p.camPos[3 * (size_t)view + 1], cz = p.camPos[3 * (size_t)view + 2];
+    __shared__ float s_key[1024];  // every occluder's key once (this kernel orders at most 1 024 occluders: larger scenes take k_order_keys / k_order_rank)
     for (uint32_t i = tid; i < p.nOcc; i += NT) {
       const float* ci = p.occ[i].center;
       const float dxi = ci[0] - cx, dyi = ci[1] - cy, dzi = ci[2] - cz;
-      const float ki = (dxi * dxi + dyi * dyi) + dzi * dzi;
+      s_key[i] = (dxi * dxi + dyi * dyi) + dzi * dzi;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < p.nOcc; i += NT) {
+      const float ki = s_key[i];
       uint32_t rank = 0;
       for (uint32_t j = 0; j < p.nOcc; ++j) {
-        const float* cj = p.occ[j].center;
-        const float dxj = cj[0] - cx, dyj = cj[1] - cy, dzj = cj[2] - cz;
-        const float kj = (dxj * dxj + dyj * dyj) + dzj * dzj;
+        const float kj = s_key[j];
         rank += (kj < ki || (kj == ki && j < i)) ? 1u : 0u;
       }
       mine[rank] = i;

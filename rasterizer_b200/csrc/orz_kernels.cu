@@ -1100,7 +1100,7 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
       ORZ_CUDA(cudaGetLastError());
       p.orders = p.orderBuf;
     }
-    k_prepare_views<<<nv, 128, 0, ctx->stream>>>(p);
+    k_prepare_views<<<nv, nv <= 16u ? 512 : 128, 0, ctx->stream>>>(p);
     ctx->launches++;
     ORZ_CUDA(cudaGetLastError());
     if (p.viewOrder) {

@@ -125,17 +125,25 @@ __global__ void __launch_bounds__(256) k_order_rank(const FrameParams p, const f
   if (i < p.nOcc) p.orderBuf[(size_t)view * p.nOcc + rank] = i;
 }
 
-// views by descending cost, ties by index (rank sort; nViews is at most a few thousand per chunk)
+// views by descending cost, ties by index: rank sort, one WARP per view (lane l counts the costs l, l + 32, ... that come
+// first; the costs pass through shared memory 1 024 at a time)
 __global__ void __launch_bounds__(256) k_sort_views(const uint32_t* __restrict__ cost, uint32_t n, uint32_t* __restrict__ order) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t ci = cost[i];
+  __shared__ uint32_t s_cost[1024];
+  const uint32_t lane = threadIdx.x & 31u, i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint32_t ci = i < n ? cost[i] : 0u;
   uint32_t rank = 0;
-  for (uint32_t j = 0; j < n; ++j) {
-    const uint32_t cj = cost[j];
-    rank += (cj > ci || (cj == ci && j < i)) ? 1u : 0u;
+  for (uint32_t j0 = 0; j0 < n; j0 += 1024u) {
+    const uint32_t m = min(1024u, n - j0);
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) s_cost[j] = cost[j0 + j];
+    __syncthreads();
+    for (uint32_t j = lane; j < m; j += 32u) {
+      const uint32_t cj = s_cost[j];
+      rank += (cj > ci || (cj == ci && j0 + j < i)) ? 1u : 0u;
+    }
   }
-  order[rank] = i;
+  rank = __reduce_add_sync(kFull, rank);
+  if (i < n && lane == 0u) order[rank] = i;
 }
 
 template <int GW, int kTrav>

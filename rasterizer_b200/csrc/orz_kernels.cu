@@ -1104,7 +1104,7 @@ extern "C" int orz_render_views_device(orz_context* ctx, orz_scene* scene, const
     ctx->launches++;
     ORZ_CUDA(cudaGetLastError());
     if (p.viewOrder) {
-      k_sort_views<<<(nv + 255) / 256, 256, 0, ctx->stream>>>(p.viewCost, nv, p.viewOrder);
+      k_sort_views<<<(nv + 7) / 8, 256, 0, ctx->stream>>>(p.viewCost, nv, p.viewOrder);
       ctx->launches++;
       ORZ_CUDA(cudaGetLastError());
     }
